@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the likelihood hot path (BASELINE.json configs[1]):
+batched photometric log-likelihood, 2^20 live points x 10 bands per GPU, on a
+synthetic MIST grid of the real shape (607 x 140 x 19 x 5 x 9) and a random-init
+photometric ANN of the assumed real architecture (10 x (6 -> 128 -> 128 -> 1)).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path (MIST interpolation -> parameter assembly ->
+photometric MLP + chi-square -> lnL) over one batch of theta already resident in
+HBM.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'phot_loglike_evals_per_sec'
+UNIT = 'evals/s'
+NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+         'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+PHOT_ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--precision', default=os.environ.get('MS_BENCH_PRECISION', 'f32'))
+    ap.add_argument('--batch', type=int, default=1 << 20, help='live points per GPU')
+    ap.add_argument('--hidden', type=int, default=128)
+    ap.add_argument('--small-grid', action='store_true', help='debug: 60x24x7x5 grid')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tf_burst=d['bf16_tflops'], tf_sust=d['bf16_tflops_sustained'],
+                    src='measured')
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+def make_workload(args):
+    from minesweeper_b200 import synth
+    if args.small_grid:
+        mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=0)
+        box = dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0),
+                   afe=(-0.2, 0.6), mass=(0.5, 1.25))
+    else:
+        mist = synth.make_mist(seed=0)
+        box = None
+    phot = synth.make_phot_net(h=args.hidden, seed=1)
+    fitpars = [NAMES, {n: (n in PHOT_ON) for n in NAMES}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot,
+                   obs_phot=synth.demo_obs_phot())
+    runbools = [False, True, False, False, False]
+    return fitargs, fitpars, runbools, box
+
+
+def workload_name(args, mist):
+    g = 'x'.join(str(len(mist[k])) for k in ('eep', 'mass', 'feh', 'afe'))
+    return ('configs[1]: batched photometric loglike, %d live points x 10 bands per GPU, MIST grid %s x 9, '
+            'phot ANN 10 x (6-%d-%d-1) sigmoid' % (args.batch, g, args.hidden, args.hidden))
+
+
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        hi = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
+        return dict(sm_mhz=float(np.median(hi)) if hi else None, sm_max_mhz=max(mx) if mx else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def run_reference(args):
+    """CPU arm: the reference's per-point execution model on all host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from minesweeper_b200 import synth
+    from oracle.cpu_baseline import CpuArm
+    fitargs, fitpars, runbools, box = make_workload(args)
+    theta = synth.draw_theta_phot(1 << 16, seed=3, box=box)
+    arm = CpuArm(fitargs, fitpars, runbools, theta)
+    r1 = arm.calibrate(0.5)
+    budget = 120.0
+    per_step = int(max(r1 * arm.cores * 0.8 * budget / (args.steps + args.warmup), 64 * arm.cores))
+    for _ in range(args.warmup):
+        arm.step(per_step)
+    n_tot, t_tot = 0, 0.0
+    for _ in range(args.steps):
+        n, t = arm.step(per_step)
+        n_tot += n; t_tot += t
+    arm.close()
+    val = n_tot / t_tot
+    sample = '%d evaluations per step over %d worker processes (per-point lnlikefn loop)' % (per_step, arm.cores)
+    print(json.dumps(dict(
+        impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=1e3 * t_tot / args.steps, higher_is_better=True, scaling='weak',
+        vs_baseline=None, dtype='f64', data='synthetic',
+        config=dict(workload=workload_name(args, fitargs['MISTpath']), sample=sample),
+        cpu_baseline=dict(value=val, unit=UNIT, cores=arm.cores, kind='port', sample=sample),
+        e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0)))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    fitargs, fitpars, runbools, box = make_workload(args)
+    from minesweeper_b200 import synth
+
+    # ---- CPU baseline first: its workers are forked, so CUDA must not be initialised yet
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_baseline import CpuArm
+        arm = CpuArm(fitargs, fitpars, runbools, synth.draw_theta_phot(1 << 16, seed=3, box=box))
+        r1 = arm.calibrate(0.5)
+        n = int(max(r1 * arm.cores * 0.8 * args.cpu_seconds, 64 * arm.cores))
+        arm.step(max(n // 20, arm.cores))
+        ne, te = arm.step(n)
+        arm.close()
+        cpu = dict(value=ne / te, unit=UNIT, cores=arm.cores, kind='port',
+                   sample='%d per-point lnlikefn evaluations of the same workload over %d worker '
+                          'processes (%.1f s); single-core probe %.0f evals/s' % (ne, arm.cores, te, r1))
+        del arm
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from minesweeper_b200.likelihood import likelihood
+    L = likelihood(fitargs, fitpars, runbools, precision=args.precision, device=local, verbose=False)
+    eng = L.engine
+    B = args.batch
+    theta_np = synth.draw_theta_phot(B, seed=3 + rank, box=box)
+    theta = torch.from_numpy(theta_np).to(dev)
+    lnl = torch.empty(B, dtype=torch.float64, device=dev)
+    gathered = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def step():
+        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=lnl)
+        if world > 1:                                                   # the only collective: gather results
+            dist.all_gather_into_tensor(gathered, lnl)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.profile(True)
+    l0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()                                                   # L2 flush, outside the timed pair
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    launches = eng.launch_count() - l0
+    prof = eng.profile_read()
+    eng.profile(False)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned host theta in, lnL out, every step
+    th_pin = torch.from_numpy(theta_np).pin_memory()
+    out_pin = torch.empty(B, dtype=torch.float64).pin_memory()
+    th_h, out_h = th_pin.numpy(), out_pin.numpy()
+    for _ in range(3):
+        L.lnlike_batch_host(th_h, lnl_out=out_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        L.lnlike_batch_host(th_h, lnl_out=out_h)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = B * world * args.steps / float(te.item())
+    assert np.array_equal(out_h, lnl.cpu().numpy(), equal_nan=True), 'host and device entry points disagree'
+
+    if rank == 0:
+        pk = peaks()
+        H, nb = args.hidden, len(eng.bands)
+        flop_pt = nb * 2.0 * (6 * H + H * H + H)
+        ph_ms, ph_n = prof['phot']
+        in_ms, in_n = prof['interp']
+        achieved = flop_pt * B * ph_n / (ph_ms * 1e-3) / 1e12 if ph_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get('phot_' + args.precision)
+        tbl_b = 4 if args.precision != 'f64' else 8
+        interp_bytes = 4 * 8 + 16 * 9 * tbl_b + 13 * 8
+        out = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype={'f64': 'f64', 'f32': 'f32', 'tc': 'bf16x3'}[args.precision], data='synthetic',
+            config=dict(workload=workload_name(args, fitargs['MISTpath']), precision=args.precision,
+                        l2='flushed between steps (256 MiB memset outside the timed events)',
+                        collective='all_gather_into_tensor(lnL) per step' if world > 1 else 'none',
+                        flop_per_eval=flop_pt),
+            clocks=clocks,
+            e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=B * theta_np.shape[1] * 8,
+                     d2h_bytes_per_step=B * 8),
+            gpu_launches=int(launches),
+            roofline=dict(bound='tensor', kernel='phot_mlp', achieved=achieved, peak=pk['tf_burst'],
+                          unit='TFLOP/s', frac=achieved / pk['tf_burst'], traffic=traffic,
+                          peak_source=pk['src'], ms_per_launch=ph_ms / max(ph_n, 1),
+                          share_of_step=ph_ms / ms if ms else None),
+            roofline_interp=dict(bound='hbm', kernel='mist_interp',
+                                 achieved=interp_bytes * B * in_n / (in_ms * 1e-3) / 1e9 if in_ms > 0 else 0.0,
+                                 peak=pk['hbm'], unit='GB/s', bytes_per_eval=interp_bytes,
+                                 frac=(interp_bytes * B * in_n / (in_ms * 1e-3) / 1e9 / pk['hbm']) if in_ms > 0 else 0.0,
+                                 ms_per_launch=in_ms / max(in_n, 1)),
+            kernel_ms={k: v[0] / args.steps for k, v in prof.items() if v[1]},
+            cpu_baseline=cpu)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

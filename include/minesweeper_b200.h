@@ -1,0 +1,174 @@
+/* minesweeper_b200 -- C-ABI of the B200-native MINESweeper likelihood hot path.
+ *
+ * The reference (pacargile/MINESweeper) is pure Python and has no FFI; the
+ * entry points below are what a binding for this path replaces, one batched
+ * call per reference method (file:line relative to the reference checkout):
+ *
+ *   ms_create / ms_destroy   likelihood.__init__            likelihood.py:9-69
+ *                            GenMIST.__init__/make_lib/lib_as_grid   fastMISTmod.py:28-98,110-125
+ *                            GenMod._initphotnn/_initspecnn genmod.py:15-44
+ *   ms_set_star              fitargs['obs_phot'|'obs_*_fit'] consumed at likelihood.py:188-195,207-210
+ *   ms_mist_interp           GenMIST.getMIST                fastMISTmod.py:100-108
+ *   ms_phot_sed              GenMod.genphot                 genmod.py:97-142
+ *   ms_spec_model            GenMod.genspec                 genmod.py:58-95
+ *   ms_lnlike_batch          likelihood.lnlikefn + lnlike   likelihood.py:92-181,183-219
+ *   ms_lnlike_batch_host     same, host buffers (what a ctypes/cffi caller with NumPy arrays uses)
+ *
+ * Conventions
+ *   - plain pointers and sizes; every array is caller-owned and row-major.
+ *   - functions return 0 on success or a negative MS_E* code; they never
+ *     throw.  ms_last_error() returns a message for the calling thread.
+ *   - "device" pointers must be device-accessible on the ctx's GPU; "host"
+ *     pointers are ordinary (preferably pinned) host memory.
+ *   - all *_batch / *_interp / *_sed / *_model calls are stream-ordered on
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream)
+ *     and do not synchronise, except ms_lnlike_batch_host which returns with
+ *     its outputs complete.
+ *   - out-of-grid / no-corner / zero-weight points follow the reference:
+ *     lnL = -inf and the nine derived MIST values = +inf (likelihood.py:107-119);
+ *     NaN residuals are dropped from the chi-square (nansum, :193,207).
+ *   - there is no CPU fallback: without a CUDA device ms_create fails with
+ *     MS_ENODEV.
+ */
+#ifndef MINESWEEPER_B200_H
+#define MINESWEEPER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_OK        0
+#define MS_EINVAL   -1   /* bad argument */
+#define MS_ENODEV   -2   /* no usable CUDA device */
+#define MS_ECUDA    -3   /* CUDA runtime error (see ms_last_error) */
+#define MS_ENOMEM   -4
+#define MS_ESTATE   -5   /* model part or star slot not configured */
+
+/* Arithmetic mode of the forward model.  Brackets, weights, the magnitude /
+ * chi-square epilogue and lnL are IEEE f64 in every mode. */
+#define MS_PREC_F64   0  /* f64 table + f64 MLP/FFT on CUDA cores: validation grade */
+#define MS_PREC_F32   1  /* f32 table, f32 MLP/FFT on CUDA cores */
+#define MS_PREC_TC    2  /* f32 table, MLP layers on tcgen05 tensor cores (split-bf16, fp32 accumulate) */
+
+/* canonical parameter ids for `colmap` (theta column -> parameter);
+ * order = fitstar.py:50-67 */
+enum {
+    MS_P_TEFF = 0, MS_P_LOGG, MS_P_FEH, MS_P_AFE, MS_P_VRAD, MS_P_VROT, MS_P_VMIC,
+    MS_P_INST_R, MS_P_LOGR, MS_P_DIST, MS_P_AV, MS_P_LOGA, MS_P_EEP, MS_P_INIT_FEH,
+    MS_P_INIT_AFE, MS_P_INIT_MASS, MS_P_PC0 /* pc_i = MS_P_PC0 + i */
+};
+#define MS_MAX_PC     8
+#define MS_NPARAM     (MS_P_PC0 + MS_MAX_PC)
+
+/* columns of `derived[B, MS_NDERIVED]` = GenMIST.modpararr (fastMISTmod.py:55,60):
+ * EEP, initial_Mass, initial_[Fe/H], initial_[a/Fe], log(Age), Mass, log(R),
+ * log(L), log(Teff), [Fe/H], [a/Fe], log(g), Agewgt */
+#define MS_NDERIVED   13
+
+typedef struct ms_ctx ms_ctx;
+
+/* Dense MIST grid (host pointers, copied to the device by ms_create).
+ * values[na][nf][nm][ne][9] in GenMIST.output column order
+ * (log_age, star_mass, log_R, log_L, log_Teff, [Fe/H], [a/Fe], log_g, Agewgt);
+ * valid[na][nf][nm][ne] != 0 where the track table has that row. */
+typedef struct {
+    int32_t ne, nm, nf, na;
+    const double *eep, *mass, *feh, *afe;     /* strictly increasing axes */
+    const double *values;
+    const uint8_t *valid;
+} ms_grid_desc;
+
+/* Photometric MLP stack, per band d_in -> h -> h -> 1, sigmoid activations.
+ * w1[nb][h][d_in], b1[nb][h], w2[nb][h][h], b2[nb][h], w3[nb][h], b3[nb];
+ * inputs (Teff, logg, feh, afe, Av, Rv)[:d_in] scaled (x-xmin)/(xmax-xmin)-0.5. */
+typedef struct {
+    int32_t nb, d_in, h;
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    const double *xmin, *xmax;
+} ms_phot_net_desc;
+
+/* Spectral MLP d_in -> h -> h -> npix, leaky-ReLU(leak); w0[h][d_in], w1[h][h],
+ * w2[npix][h].  wavelength[npix] must be log-uniform.  resolution is the value
+ * handed to the R-smoothing as `inres` (lambda/sigma units). */
+typedef struct {
+    int32_t d_in, h, npix;
+    const float *w0, *b0, *w1, *b1, *w2, *b2;
+    const double *xmin, *xmax;
+    const double *wavelength;
+    double resolution;
+    double leak;
+    int32_t logt_input;       /* first label is log10(Teff) instead of Teff */
+} ms_spec_net_desc;
+
+/* Run flags = runbools of likelihood.py:16-20 plus the two fitargs switches. */
+typedef struct {
+    int32_t spec, phot, modpoly;     /* runbools[0..2] */
+    int32_t ageweight;               /* fitargs['ageweight']  likelihood.py:23,168-176 */
+    int32_t mistdif;                 /* fitargs['mistdif']    likelihood.py:27,127-132 */
+    int32_t n_pc;                    /* number of blaze coefficients when modpoly */
+} ms_flags;
+
+const char *ms_version(void);
+const char *ms_last_error(void);
+
+/* Any of grid / phot / spec may be NULL when that part is unused. */
+int ms_create(ms_ctx **out, int device, int precision, const ms_grid_desc *grid,
+              const ms_phot_net_desc *phot, const ms_spec_net_desc *spec);
+void ms_destroy(ms_ctx *ctx);
+int ms_precision(const ms_ctx *ctx);
+
+/* Observations of one star (host pointers; copied).  obs_mag/obs_err[nb] in the
+ * ctx's band order, NaN = band not observed (dropped, as the reference iterates
+ * observed bands only).  obs_wave must be increasing; pass n_obs = 0 for none. */
+int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, const double *obs_err,
+                int nb, const double *obs_wave, const double *obs_flux,
+                const double *obs_eflux, int n_obs);
+
+/* theta4[B][4] = (EEP, initial_Mass, initial_[Fe/H], initial_[a/Fe]) device f64.
+ * brackets[B][4] int32 = digitize-1 per axis (may be NULL);
+ * derived[B][13] f64 (may be NULL); ok[B] uint8 (may be NULL). */
+int ms_mist_interp(ms_ctx *ctx, const double *theta4, int64_t B, int32_t *brackets,
+                   double *derived, uint8_t *ok, void *stream);
+
+/* photpars[B][7] = (Teff, logg, feh, afe, logR, Dist, Av) device f64 -> mags[B][nb]. */
+int ms_phot_sed(ms_ctx *ctx, const double *photpars, int64_t B, double *mags, void *stream);
+
+/* specpars[B][8 + n_pc] = (Teff, logg, feh, afe, Vrad, Vrot, Vmic, Inst_R, pc...) device
+ * f64 -> flux[B][n_obs] on star_slot's obs_wave.  Inst_R is the un-multiplied
+ * fit parameter (the 2.355 factor of genmod.py:74-75 is applied inside). */
+int ms_spec_model(ms_ctx *ctx, int star_slot, const double *specpars, int n_pc,
+                  int64_t B, double *flux, void *stream);
+
+/* The batched likelihood.  theta[B][ndim] device f64; colmap[ndim] host int32
+ * mapping each column to an MS_P_* id; fixed[MS_NPARAM] host f64 with NaN for
+ * "not fixed" (fitargs['fixedpars']); star_slot[B] device int32 or NULL (= slot
+ * 0 for every row).  lnL[B] device f64; derived[B][13] and brackets[B][4] may
+ * be NULL. */
+int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double *theta,
+                    const int32_t *star_slot, int64_t B, int ndim, const int32_t *colmap,
+                    const double *fixed, double *lnL, double *derived, int32_t *brackets,
+                    void *stream);
+
+/* Same with HOST buffers: copies theta in, runs, copies lnL (and derived when
+ * non-NULL) out, synchronises. */
+int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const double *theta_host,
+                         int64_t B, int ndim, const int32_t *colmap, const double *fixed,
+                         double *lnL_host, double *derived_host);
+
+/* Number of kernel launches issued by this ctx so far (bench bookkeeping). */
+int64_t ms_launch_count(const ms_ctx *ctx);
+
+/* Live per-kernel timing with CUDA events recorded on the launching stream.
+ * ms_profile_enable(ctx, 1) starts (and clears) collection; ms_profile_read
+ * synchronises and returns the summed device milliseconds and launch counts per
+ * kernel family since then. */
+enum { MS_K_INTERP = 0, MS_K_PARS, MS_K_PHOT, MS_K_SPEC_MLP, MS_K_SPEC_SMOOTH, MS_K_FINALIZE, MS_NKIND };
+int ms_profile_enable(ms_ctx *ctx, int on);
+int ms_profile_read(ms_ctx *ctx, double *ms_by_kind, int64_t *launches_by_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

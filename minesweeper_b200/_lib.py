@@ -1,0 +1,123 @@
+"""ctypes binding of libmsb200.so (include/minesweeper_b200.h).
+
+There is no CPU fallback: if the library is missing this module raises, and
+``ms_create`` itself fails with MS_ENODEV when no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libmsb200.so')
+
+MS_OK, MS_EINVAL, MS_ENODEV, MS_ECUDA, MS_ENOMEM, MS_ESTATE = 0, -1, -2, -3, -4, -5
+MS_PREC_F64, MS_PREC_F32, MS_PREC_TC = 0, 1, 2
+PRECISIONS = {'f64': MS_PREC_F64, 'f32': MS_PREC_F32, 'tc': MS_PREC_TC}
+
+# canonical parameter ids (fitstar.py:50-67 order)
+PARAM_IDS = {
+    'Teff': 0, 'log(g)': 1, '[Fe/H]': 2, '[a/Fe]': 3, 'Vrad': 4, 'Vrot': 5, 'Vmic': 6,
+    'Inst_R': 7, 'log(R)': 8, 'Dist': 9, 'Av': 10, 'log(A)': 11, 'EEP': 12,
+    'initial_[Fe/H]': 13, 'initial_[a/Fe]': 14, 'initial_Mass': 15,
+}
+MS_P_PC0 = 16
+MS_MAX_PC = 8
+MS_NPARAM = MS_P_PC0 + MS_MAX_PC
+MS_NDERIVED = 13
+DERIVED_NAMES = ('EEP', 'initial_Mass', 'initial_[Fe/H]', 'initial_[a/Fe]', 'log(Age)', 'Mass',
+                 'log(R)', 'log(L)', 'log(Teff)', '[Fe/H]', '[a/Fe]', 'log(g)', 'Agewgt')
+
+
+def param_id(name):
+    if name in PARAM_IDS:
+        return PARAM_IDS[name]
+    if name.startswith('pc_'):
+        i = int(name[3:])
+        if 0 <= i < MS_MAX_PC:
+            return MS_P_PC0 + i
+    raise KeyError('parameter %r is not known to the batched likelihood' % name)
+
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class GridDesc(C.Structure):
+    _fields_ = [('ne', C.c_int32), ('nm', C.c_int32), ('nf', C.c_int32), ('na', C.c_int32),
+                ('eep', c_dp), ('mass', c_dp), ('feh', c_dp), ('afe', c_dp),
+                ('values', c_dp), ('valid', c_u8p)]
+
+
+class PhotNetDesc(C.Structure):
+    _fields_ = [('nb', C.c_int32), ('d_in', C.c_int32), ('h', C.c_int32),
+                ('w1', c_fp), ('b1', c_fp), ('w2', c_fp), ('b2', c_fp), ('w3', c_fp), ('b3', c_fp),
+                ('xmin', c_dp), ('xmax', c_dp)]
+
+
+class SpecNetDesc(C.Structure):
+    _fields_ = [('d_in', C.c_int32), ('h', C.c_int32), ('npix', C.c_int32),
+                ('w0', c_fp), ('b0', c_fp), ('w1', c_fp), ('b1', c_fp), ('w2', c_fp), ('b2', c_fp),
+                ('xmin', c_dp), ('xmax', c_dp), ('wavelength', c_dp),
+                ('resolution', C.c_double), ('leak', C.c_double), ('logt_input', C.c_int32)]
+
+
+class Flags(C.Structure):
+    _fields_ = [('spec', C.c_int32), ('phot', C.c_int32), ('modpoly', C.c_int32),
+                ('ageweight', C.c_int32), ('mistdif', C.c_int32), ('n_pc', C.c_int32)]
+
+
+# every exported symbol of include/minesweeper_b200.h with its prototype
+PROTOTYPES = {
+    'ms_version': (C.c_char_p, []),
+    'ms_last_error': (C.c_char_p, []),
+    'ms_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(GridDesc),
+                            C.POINTER(PhotNetDesc), C.POINTER(SpecNetDesc)]),
+    'ms_destroy': (None, [C.c_void_p]),
+    'ms_precision': (C.c_int, [C.c_void_p]),
+    'ms_set_star': (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, C.c_int, c_dp, c_dp, c_dp, C.c_int]),
+    'ms_mist_interp': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
+    'ms_phot_sed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'ms_spec_model': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                C.c_void_p]),
+    'ms_lnlike_batch': (C.c_int, [C.c_void_p, C.POINTER(Flags), C.c_void_p, C.c_void_p, C.c_int64,
+                                  C.c_int, c_ip, c_dp, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    'ms_lnlike_batch_host': (C.c_int, [C.c_void_p, C.POINTER(Flags), c_dp, C.c_int64, C.c_int, c_ip,
+                                       c_dp, c_dp, c_dp]),
+    'ms_launch_count': (C.c_int64, [C.c_void_p]),
+    'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
+    'ms_profile_read': (C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int64)]),
+}
+KERNEL_KINDS = ('interp', 'pars', 'phot', 'spec_mlp', 'spec_smooth', 'finalize')
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and attach the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'minesweeper_b200: %s not found. Build it with `python -m minesweeper_b200.build` '
+            '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class MSError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != MS_OK:
+        msg = load().ms_last_error()
+        raise MSError('libmsb200 error %d: %s' % (rc, msg.decode() if msg else ''))

@@ -1,0 +1,156 @@
+// Kernel (1): bracket search + 16-corner gather + N-linear interpolation on the
+// dense MIST grid.  Batched form of GenMIST.getMIST (reference
+// minesweeper/fastMISTmod.py:100-108) with the semantics of params_to_grid
+// (:127-150), linear_weights (:194-213) and weights (:152-170); the KD-tree
+// ball query (:172-192) is replaced by direct addressing of the <= 16 corners
+// that can carry non-zero weight.
+//
+// Layout: table[na][nf][nm][ne][CP] (EEP fastest, so the two EEP corners of a
+// cell are adjacent in memory); a vertex that is absent from the track tables
+// has NaN in column 0.  Axes live in shared memory; theta stays f64 so the
+// brackets equal np.digitize(..., right=False) - 1 bit for bit.
+//
+// HBM-bound: algorithmic bytes per point = 4*8 (theta) + 16*9*sizeof(T) (corners)
+// + 13*8 (derived) -> 712 B (f32 table) / 1288 B (f64 table).
+#include "common.cuh"
+
+namespace {
+
+// number of axis values <= x, minus one  ==  np.digitize([x], g, right=False) - 1.
+// NaN compares false everywhere and lands at n - 1, like NumPy's NaN-last ordering.
+__device__ __forceinline__ int bracket_of(const double *g, int n, double x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (x < g[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo - 1;
+}
+
+template <typename T> struct Row;
+template <> struct Row<float> {
+    static constexpr int CP = MS_CP32;
+    __device__ static void load(const float *p, double *v) {
+        const float4 *q = reinterpret_cast<const float4 *>(p);
+        float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x;
+    }
+};
+template <> struct Row<double> {
+    static constexpr int CP = MS_CP64;
+    __device__ static void load(const double *p, double *v) {
+        const double2 *q = reinterpret_cast<const double2 *>(p);
+        double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x;
+        v[5] = c.y; v[6] = d.x; v[7] = d.y; v[8] = e.x;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int ne, int nm, int nf,
+                   int na, const T *__restrict__ table, int32_t *__restrict__ brackets,
+                   double *__restrict__ derived, uint8_t *__restrict__ okflag) {
+    extern __shared__ double s_axes[];
+    const int ntot = ne + nm + nf + na;
+    for (int i = threadIdx.x; i < ntot; i += blockDim.x) s_axes[i] = axes[i];
+    __syncthreads();
+    const double *g[4] = {s_axes, s_axes + ne, s_axes + ne + nm, s_axes + ne + nm + nf};
+    const int n[4] = {ne, nm, nf, na};
+    constexpr int CP = Row<T>::CP;
+
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < B;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        double x[4];
+        x[0] = theta_get(tv, p, MS_P_EEP);
+        x[1] = theta_get(tv, p, MS_P_INIT_MASS);
+        x[2] = theta_get(tv, p, MS_P_INIT_FEH);
+        x[3] = theta_get(tv, p, MS_P_INIT_AFE);
+        int idx[4];
+        double wl[4], wu[4];
+        bool inside = true;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int i = bracket_of(g[d], n[d], x[d]);
+            idx[d] = i;
+            inside = inside && (i >= 0) && (i <= n[d] - 2);
+            int ic = inside ? i : 0;
+            // same operation order as the reference: frac, i + frac, then dx per corner
+            double frac = (x[d] - g[d][ic]) / (g[d][ic + (n[d] > 1 ? 1 : 0)] - g[d][ic]);
+            double xt = (double)ic + frac;
+            double dl = xt - (double)ic;           // >= 0
+            double du = xt - (double)(ic + 1);     // in [-1, 0)
+            wl[d] = 1.0 - dl;
+            wu[d] = (du > -1.0) ? 1.0 + du : 0.0;
+        }
+        if (brackets) {
+            int4 b4 = make_int4(idx[0], idx[1], idx[2], idx[3]);
+            *reinterpret_cast<int4 *>(brackets + 4 * p) = b4;
+        }
+        double acc[MS_NCOL];
+#pragma unroll
+        for (int c = 0; c < MS_NCOL; ++c) acc[c] = 0.0;
+        double wsum = 0.0;
+        if (inside) {
+            const int64_t sE = CP, sM = (int64_t)ne * CP, sF = (int64_t)nm * sM, sA = (int64_t)nf * sF;
+            const T *base = table + idx[3] * sA + idx[2] * sF + idx[1] * sM + idx[0] * sE;
+            // ascending reference row id = (feh, afe, mass, eep) nesting
+#pragma unroll
+            for (int cf = 0; cf < 2; ++cf)
+#pragma unroll
+                for (int ca = 0; ca < 2; ++ca)
+#pragma unroll
+                    for (int cm = 0; cm < 2; ++cm)
+#pragma unroll
+                        for (int ce = 0; ce < 2; ++ce) {
+                            double w = (ce ? wu[0] : wl[0]);
+                            w = w * (cm ? wu[1] : wl[1]);
+                            w = w * (cf ? wu[2] : wl[2]);
+                            w = w * (ca ? wu[3] : wl[3]);
+                            if (w > 0.0) {
+                                double v[MS_NCOL];
+                                Row<T>::load(base + ca * sA + cf * sF + cm * sM + ce * sE, v);
+                                if (v[0] == v[0]) {      // vertex present
+                                    wsum += w;
+#pragma unroll
+                                    for (int c = 0; c < MS_NCOL; ++c) acc[c] = fma(w, v[c], acc[c]);
+                                }
+                            }
+                        }
+        }
+        const bool ok = inside && (wsum > 0.0);
+        if (okflag) okflag[p] = ok ? 1 : 0;
+        if (derived) {
+            double *o = derived + p * MS_NDERIVED;
+            o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
+            const double inv = ok ? 1.0 / wsum : 0.0;
+#pragma unroll
+            for (int c = 0; c < MS_NCOL; ++c) o[4 + c] = ok ? acc[c] * inv : ms_inf();
+        }
+    }
+}
+
+}  // namespace
+
+int launch_mist_interp(ms_ctx *ctx, const ThetaView &tv, int64_t B, int32_t *brackets,
+                       double *derived, uint8_t *ok, cudaStream_t st) {
+    const GridDev &g = ctx->grid;
+    if (!g.axes) { ms_set_error("MIST grid not configured"); return MS_ESTATE; }
+    if (B <= 0) return MS_OK;
+    KernelTimer timer_(ctx, MS_K_INTERP, st);
+    const int threads = 256;
+    int64_t blocks = (B + threads - 1) / threads;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    size_t smem = (size_t)(g.ne + g.nm + g.nf + g.na) * sizeof(double);
+    if (ctx->precision == MS_PREC_F64)
+        mist_interp_kernel<double><<<(unsigned)blocks, threads, smem, st>>>(
+            tv, B, g.axes, g.ne, g.nm, g.nf, g.na, g.tab64, brackets, derived, ok);
+    else
+        mist_interp_kernel<float><<<(unsigned)blocks, threads, smem, st>>>(
+            tv, B, g.axes, g.ne, g.nm, g.nf, g.na, g.tab32, brackets, derived, ok);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}

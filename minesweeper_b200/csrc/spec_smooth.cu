@@ -1,0 +1,420 @@
+// Kernel (3): rotational + instrumental broadening, resampling onto the observed
+// pixels, blaze polynomial and the spectral chi-square, one CTA per point with
+// the whole spectrum resident in shared memory.  Batched form of
+//   PayneSpecPredict.getspec broadening chain   external Payne (SURVEY.md Appendix B,
+//                                               PARITY UNPINNED; call site genmod.py:80-84)
+//   smoothspec 'vsini' / 'R'    reference minesweeper/smoothing.py:92-114, 131-134
+//   smooth_vsini_fft / smooth_vel_fft            smoothing.py:242-264, 202-240
+//   smooth_fft / smooth_fft_vsini                smoothing.py:517-558
+//   mask_wave / resample_wave                    smoothing.py:560-598
+//   polycalc                                     reference minesweeper/fitutils.py:11-20
+//   likelihood.lnlike spectral chi-square        reference minesweeper/likelihood.py:188-195
+//
+// The reference convolves by FFT on a power-of-two log-uniform resampling of the
+// spectrum; its result is defined by that (circular, band-limited) construction,
+// so this kernel performs the same steps: linear resampling, a real FFT of the
+// resampled spectrum (as a half-length complex FFT held in shared memory,
+// decimation-in-frequency forward / decimation-in-time inverse so that no
+// bit-reversal pass is needed), multiplication by the analytic transfer function,
+// inverse FFT, linear interpolation back.  Because the native wavelength grid is
+// log-uniform and a Doppler shift is a translation in ln(lambda), every
+// resampling position is an affine function of the pixel index; no per-pixel
+// logarithm or exponential is evaluated.
+#include "common.cuh"
+
+#define MS_CKMS 2.998e5            // smoothing.py:14
+#define MS_C_KMS 299792.458        // Payne's Doppler shift (scipy.constants.c / 1000)
+#define MS_ROT_TAB_H (1.0 / 32.0)  // spacing of the rotational-transfer table
+#define MS_ROT_TAB_N 8200
+
+namespace {
+
+template <typename T> struct Cx;
+template <> struct Cx<float> { typedef float2 type; };
+template <> struct Cx<double> { typedef double2 type; };
+
+template <typename T2> __device__ __forceinline__ T2 cadd(T2 a, T2 b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T2> __device__ __forceinline__ T2 csub(T2 a, T2 b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) {
+    return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T2> __device__ __forceinline__ T2 cmulc(T2 a, T2 b) {   // a * conj(b)
+    return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
+}
+
+struct SmoothArgs {
+    const double *pars;            // [B][MS_NPARS] (already offset to the chunk)
+    const void *flux_native;       // [B][npix] T
+    int npix, n1;
+    double lnw0, dlnw, resolution;
+    const double *wave;            // native wavelengths
+    const int *a1_idx, *a2_idx;
+    const void *a1_frac, *a2_frac; // T
+    const void *twiddle;           // T2 [n1/2]: exp(-2 pi i k / n1)
+    const float *rot_tab;          // S(u) on a uniform grid (float mode)
+    // star
+    int n_obs;
+    const double *obs_wave, *obs_lnwave, *obs_flux, *obs_err2, *cheb_x;
+    double ow_min, ow_max;
+    int modpoly, n_pc;
+    double *flux_out;              // [B][n_obs] or nullptr
+    double *chi2;                  // [B] or nullptr
+};
+
+// Transfer function of the rotational profile, smoothing.py:541-548.
+__device__ __forceinline__ double rot_transfer(double u) {
+    if (u == 0.0) return 1.0;
+    double s, c;
+    sincos(u, &s, &c);
+    const double u2 = u * u;
+    return j1(u) / u - 3.0 * c / (2.0 * u2) + 3.0 * s / (2.0 * u2 * u);
+}
+__device__ __forceinline__ float rot_transfer_f(float u, const float *__restrict__ tab) {
+    const float x = u * (float)(1.0 / MS_ROT_TAB_H);
+    int i = (int)x;
+    if (i >= 1 && i < MS_ROT_TAB_N - 3) {          // 4-point Lagrange on the uniform table
+        const float t = x - (float)i;
+        const float p0 = __ldg(tab + i - 1), p1 = __ldg(tab + i), p2 = __ldg(tab + i + 1), p3 = __ldg(tab + i + 2);
+        const float c0 = -t * (t - 1.f) * (t - 2.f) * (1.f / 6.f);
+        const float c1 = (t + 1.f) * (t - 1.f) * (t - 2.f) * 0.5f;
+        const float c2 = -(t + 1.f) * t * (t - 2.f) * 0.5f;
+        const float c3 = (t + 1.f) * t * (t - 1.f) * (1.f / 6.f);
+        return c0 * p0 + c1 * p1 + c2 * p2 + c3 * p3;
+    }
+    if (i < 1) {                                    // series about 0: 1 - u^2/10 + u^4/280
+        const float u2 = u * u;
+        return 1.f - u2 * 0.1f + u2 * u2 * (1.f / 280.f);
+    }
+    float s, c;
+    sincosf(u, &s, &c);
+    const float u2 = u * u;
+    return j1f(u) / u - 3.f * c / (2.f * u2) + 3.f * s / (2.f * u2 * u);
+}
+
+template <typename T> struct Transfer {
+    int kind;            // 0 gaussian, 1 rotation
+    double coef;         // gaussian: 2 pi^2 sigma^2 / (n dv)^2 ; rotation: 2 pi vsini / (n dv)
+    const float *tab;
+    __device__ __forceinline__ T operator()(int k) const;
+};
+template <> __device__ __forceinline__ double Transfer<double>::operator()(int k) const {
+    if (kind == 0) return exp(-coef * (double)k * (double)k);
+    return rot_transfer(coef * (double)k);
+}
+template <> __device__ __forceinline__ float Transfer<float>::operator()(int k) const {
+    if (kind == 0) return expf(-(float)coef * (float)k * (float)k);
+    const double u = coef * (double)k;
+    if (!(u == u)) return __int_as_float(0x7fc00000);
+    return rot_transfer_f((float)u, tab);
+}
+
+// y = irfft(rfft(x) * transfer) for the n real samples stored in z (z[m] = x[2m] + i x[2m+1]).
+template <typename T>
+__device__ void fft_filter(typename Cx<T>::type *z, int n, const Transfer<T> &tf,
+                           const typename Cx<T>::type *__restrict__ tw, int tw_n) {
+    typedef typename Cx<T>::type T2;
+    const int M = n >> 1;
+    const int L = 31 - __clz(M);
+    const int nbf = M >> 1;
+    // forward, decimation in frequency: natural order in, bit-reversed order out
+    for (int s = L - 1; s >= 0; --s) {
+        const int half = 1 << s;
+        const int tstep = tw_n >> (s + 1);            // tw index stride = tw_n / (2 half)
+        for (int t = threadIdx.x; t < nbf; t += blockDim.x) {
+            const int pos = t & (half - 1);
+            const int i0 = ((t >> s) << (s + 1)) + pos;
+            const T2 a = z[i0], b = z[i0 + half];
+            z[i0] = cadd(a, b);
+            z[i0 + half] = cmul(csub(a, b), tw[pos * tstep]);
+        }
+        __syncthreads();
+    }
+    // split into the spectrum of the real sequence, apply the transfer, merge back
+    const int tstepn = tw_n / n;
+    for (int k = threadIdx.x; k <= nbf; k += blockDim.x) {
+        if (k == 0) {
+            const T2 z0 = z[0];
+            const T y0 = tf(0) * (z0.x + z0.y), ym = tf(M) * (z0.x - z0.y);
+            z[0] = {(T)0.5 * (y0 + ym), (T)0.5 * (y0 - ym)};
+        } else {
+            const int pk = __brev((unsigned)k) >> (32 - L);
+            const int pm = __brev((unsigned)(M - k)) >> (32 - L);
+            const T2 A = z[pk];
+            T2 Bc = z[pm]; Bc.y = -Bc.y;
+            const T2 E = {(T)0.5 * (A.x + Bc.x), (T)0.5 * (A.y + Bc.y)};
+            const T2 dif = csub(A, Bc);
+            const T2 O = {(T)0.5 * dif.y, (T)-0.5 * dif.x};          // -i/2 (A - Bc)
+            const T2 w = tw[k * tstepn];
+            const T2 wO = cmul(w, O);
+            const T tk = tf(k), tm = tf(M - k);
+            const T2 Yk = {tk * (E.x + wO.x), tk * (E.y + wO.y)};
+            const T2 Ymc = {tm * (E.x - wO.x), tm * (E.y - wO.y)};   // conj(Y[M-k])
+            const T2 Ep = {(T)0.5 * (Yk.x + Ymc.x), (T)0.5 * (Yk.y + Ymc.y)};
+            const T2 D = {(T)0.5 * (Yk.x - Ymc.x), (T)0.5 * (Yk.y - Ymc.y)};
+            const T2 Op = cmulc(D, w);
+            z[pk] = {Ep.x - Op.y, Ep.y + Op.x};                      // Ep + i Op
+            if (pm != pk) z[pm] = {Ep.x + Op.y, Op.x - Ep.y};        // conj(Ep) + i conj(Op)
+        }
+    }
+    __syncthreads();
+    // inverse, decimation in time: bit-reversed order in, natural order out
+    for (int s = 0; s < L; ++s) {
+        const int half = 1 << s;
+        const int tstep = tw_n >> (s + 1);
+        for (int t = threadIdx.x; t < nbf; t += blockDim.x) {
+            const int pos = t & (half - 1);
+            const int i0 = ((t >> s) << (s + 1)) + pos;
+            const T2 a = z[i0];
+            const T2 b = cmulc(z[i0 + half], tw[pos * tstep]);
+            z[i0] = cadd(a, b);
+            z[i0 + half] = csub(a, b);
+        }
+        __syncthreads();
+    }
+    const T inv = (T)1 / (T)M;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        T2 v = z[m];
+        z[m] = {v.x * inv, v.y * inv};
+    }
+    __syncthreads();
+}
+
+// numpy.polynomial.chebyshev.chebval recurrence (Clenshaw), n coefficients
+__device__ __forceinline__ double cheb_eval(double x, const double *c, int n) {
+    if (n == 1) return c[0];
+    if (n == 2) return c[0] + c[1] * x;
+    const double x2 = 2.0 * x;
+    double c0 = c[n - 2], c1 = c[n - 1];
+    for (int i = 3; i <= n; ++i) {
+        const double tmp = c0;
+        c0 = c[n - i] - c1;
+        c1 = tmp + c1 * x2;
+    }
+    return c0 + c1 * x;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512)
+spec_smooth_kernel(SmoothArgs a, int nB) {
+    typedef typename Cx<T>::type T2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T2 *z = reinterpret_cast<T2 *>(smem_raw);                 // n1/2 complex = n1 reals
+    T *zr = reinterpret_cast<T *>(smem_raw);
+    T *fr = zr + a.n1;                                        // npix
+    __shared__ double red[16];
+    const T *a1f = static_cast<const T *>(a.a1_frac), *a2f = static_cast<const T *>(a.a2_frac);
+    const T2 *tw = static_cast<const T2 *>(a.twiddle);
+    const int npix = a.npix, n1 = a.n1, nobs = a.n_obs;
+
+    for (int p = blockIdx.x; p < nB; p += gridDim.x) {
+        const double *r = a.pars + (size_t)p * MS_NPARS;
+        const bool ok = r[PV_TEFF] != ms_inf();
+        if (!ok) {                                            // uniform across the CTA
+            if (a.flux_out)
+                for (int j = threadIdx.x; j < nobs; j += blockDim.x)
+                    a.flux_out[(size_t)p * nobs + j] = ms_nan();
+            continue;
+        }
+        const double vrad = r[PV_VRAD], vrot = r[PV_VROT];
+        const double inst = 2.355 * r[PV_INSTR];              // genmod.py:74-75
+        const T *frow = static_cast<const T *>(a.flux_native) + (size_t)p * npix;
+        for (int i = threadIdx.x; i < npix; i += blockDim.x) fr[i] = frow[i];
+        __syncthreads();
+
+        // ---- rotational broadening on the full native grid (outwave = None) ----
+        if (vrot != 0.0) {
+            const double sigma = sqrt(vrot * vrot);
+            for (int k = threadIdx.x; k < n1; k += blockDim.x) {
+                const int i = a.a1_idx[k];
+                const T f = a1f[k];
+                zr[k] = fr[i] + (fr[i + 1] - fr[i]) * f;
+            }
+            __syncthreads();
+            const double step1 = (double)(npix - 1) * a.dlnw / (double)(n1 - 1);
+            Transfer<T> tf;
+            tf.kind = 1; tf.tab = a.rot_tab;
+            tf.coef = 2.0 * M_PI * sigma / ((double)n1 * MS_CKMS * step1);
+            fft_filter<T>(z, n1, tf, tw, n1);
+            for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+                const int k = a.a2_idx[i];
+                const T f = a2f[i];
+                fr[i] = zr[k] + (zr[k + 1] - zr[k]) * f;
+            }
+            __syncthreads();
+        }
+
+        // ---- Doppler shift + instrumental broadening + resampling to the observed pixels ----
+        const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
+        const double lnscale = log(scale);
+        int mode;             // 0: FFT-smoothed grid in zr; 1: direct interp of fr; 2: all NaN
+        int i_s = 0, i_e = npix - 1, n2 = 0;
+        double d2 = 0.0;
+        if (inst != 0.0) {
+            const double lo = a.ow_min * (1.0 - 20.0 / inst), hi = a.ow_max * (1.0 + 20.0 / inst);
+            int l = 0, h = npix;                              // first i with wave[i]*scale > lo
+            while (l < h) { int m = (l + h) >> 1; if (a.wave[m] * scale > lo) h = m; else l = m + 1; }
+            i_s = l;
+            l = 0; h = npix;                                  // first i with wave[i]*scale >= hi
+            while (l < h) { int m = (l + h) >> 1; if (a.wave[m] * scale < hi) l = m + 1; else h = m; }
+            i_e = l - 1;
+            const int nmask = i_e - i_s + 1;
+            const double so = MS_CKMS / inst, si = MS_CKMS / a.resolution;
+            const double sigma = sqrt(so * so - si * si);     // NaN when sharper than the net
+            if (nmask < 4 || !(inst == inst)) mode = 2;      // degenerate window: all-NaN model
+            else if (sigma <= 0.0) mode = 1;
+            else {
+                mode = 0;
+                n2 = 1; while (n2 < nmask) n2 <<= 1;
+                const double ratio = (double)(i_e - i_s) / (double)(n2 - 1);
+                d2 = ratio * a.dlnw;
+                const T half_d = (T)(0.5 * a.dlnw);
+                for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+                    const double pos = (double)i_s + (double)k * ratio;
+                    int i = (int)pos;
+                    if (i > i_e - 1) i = i_e - 1;
+                    const T t = (T)(pos - (double)i);
+                    const T f = t * ((T)1 + (t - (T)1) * half_d);     // linear in lambda, not ln(lambda)
+                    zr[k] = fr[i] + (fr[i + 1] - fr[i]) * f;
+                }
+                __syncthreads();
+                Transfer<T> tf;
+                tf.kind = 0; tf.tab = nullptr;
+                const double ndv = (double)n2 * MS_CKMS * d2;
+                tf.coef = 2.0 * M_PI * M_PI * sigma * sigma / (ndv * ndv);
+                fft_filter<T>(z, n2, tf, tw, n1);
+            }
+        } else {
+            mode = 1;
+        }
+
+        double csum = 0.0;
+        const double lnw_s = a.lnw0 + (double)i_s * a.dlnw;
+        for (int j = threadIdx.x; j < nobs; j += blockDim.x) {
+            const double lx = a.obs_lnwave[j] - lnscale;
+            double m;
+            if (mode == 0) {
+                const double q = (lx - lnw_s) / d2;
+                if (q <= 0.0) m = (double)zr[0];
+                else if (q >= (double)(n2 - 1)) m = (double)zr[n2 - 1];
+                else {
+                    const int i = (int)q;
+                    const double t = q - (double)i;
+                    const double f = t * (1.0 + (t - 1.0) * 0.5 * d2);
+                    const double v0 = (double)zr[i], v1 = (double)zr[i + 1];
+                    m = v0 + (v1 - v0) * f;
+                }
+            } else if (mode == 1) {
+                const double q = (lx - a.lnw0) / a.dlnw;
+                const double qlo = (double)i_s, qhi = (double)i_e;
+                if (q < qlo || q > qhi) {
+                    // smoothing branch clamps (np.interp default); plain branch returns NaN outside
+                    m = (inst != 0.0) ? (double)fr[q < qlo ? i_s : i_e] : ms_nan();
+                } else {
+                    int i = (int)q;
+                    if (i > i_e - 1) i = i_e - 1;
+                    const double t = q - (double)i;
+                    const double f = t * (1.0 + (t - 1.0) * 0.5 * a.dlnw);
+                    const double v0 = (double)fr[i], v1 = (double)fr[i + 1];
+                    m = v0 + (v1 - v0) * f;
+                }
+            } else {
+                m = ms_nan();
+            }
+            if (a.modpoly) m *= cheb_eval(a.cheb_x[j], r + PV_PC0, a.n_pc);   // genmod.py:90-93
+            if (a.flux_out) a.flux_out[(size_t)p * nobs + j] = m;
+            if (a.chi2) {
+                const double d = m - a.obs_flux[j];
+                const double t = (d * d) / a.obs_err2[j];
+                if (t == t) csum += t;                        // nansum (likelihood.py:193)
+            }
+        }
+        if (a.chi2) {
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = csum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+                a.chi2[p] += tot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+template <typename T>
+int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux,
+                     const double *d_xmin_scale, cudaStream_t st);
+
+template <typename T>
+static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) {
+    const SpecNetDev &n = ctx->spec;
+    const StarDev &star = ctx->stars[a.star_slot];
+    const int64_t chunk = 1024;
+    const size_t flux_bytes = (size_t)chunk * n.npix * sizeof(T);
+    const size_t hid_bytes = (size_t)chunk * (n.d_in + 2 * n.h) * sizeof(T);
+    if (ctx->scr_flux_bytes < flux_bytes) {
+        if (ctx->scr_flux) cudaFree(ctx->scr_flux);
+        ctx->scr_flux = nullptr; ctx->scr_flux_bytes = 0;
+        MS_CUDA(cudaMalloc(&ctx->scr_flux, flux_bytes));
+        ctx->scr_flux_bytes = flux_bytes;
+    }
+    if (ctx->scr_hid_bytes < hid_bytes) {
+        if (ctx->scr_hid) cudaFree(ctx->scr_hid);
+        ctx->scr_hid = nullptr; ctx->scr_hid_bytes = 0;
+        MS_CUDA(cudaMalloc(&ctx->scr_hid, hid_bytes));
+        ctx->scr_hid_bytes = hid_bytes;
+    }
+    const size_t smem = (size_t)(n.n1 + n.npix) * sizeof(T);
+    if (smem > 226 * 1024) {
+        ms_set_error("spectral net with %d pixels does not fit the shared-memory smoother", n.npix);
+        return MS_EINVAL;
+    }
+    auto kern = spec_smooth_kernel<T>;
+    MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+        const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
+        int rc = spec_mlp_chunk_t<T>(ctx, a.pars + b0 * MS_NPARS, nb, (T *)ctx->scr_hid,
+                                     (T *)ctx->scr_flux, n.xms, st);
+        if (rc) return rc;
+        SmoothArgs sa;
+        sa.pars = a.pars + b0 * MS_NPARS;
+        sa.flux_native = ctx->scr_flux;
+        sa.npix = n.npix; sa.n1 = n.n1; sa.lnw0 = n.lnw0; sa.dlnw = n.dlnw; sa.resolution = n.resolution;
+        sa.wave = n.wave; sa.a1_idx = n.a1_idx; sa.a2_idx = n.a2_idx;
+        if (sizeof(T) == 4) { sa.a1_frac = n.a1_frac; sa.a2_frac = n.a2_frac; sa.twiddle = n.twiddle32; }
+        else { sa.a1_frac = n.a1_fracd; sa.a2_frac = n.a2_fracd; sa.twiddle = n.twiddle64; }
+        sa.rot_tab = n.rot_tab;
+        sa.n_obs = star.n_obs; sa.obs_wave = star.obs_wave; sa.obs_lnwave = star.obs_lnwave;
+        sa.obs_flux = star.obs_flux; sa.obs_err2 = star.obs_err2; sa.cheb_x = star.cheb_x;
+        sa.ow_min = star.wmin; sa.ow_max = star.wmax;
+        sa.modpoly = a.modpoly; sa.n_pc = a.n_pc;
+        sa.flux_out = a.flux ? a.flux + b0 * star.n_obs : nullptr;
+        sa.chi2 = a.chi2 ? a.chi2 + b0 : nullptr;
+        int64_t grid = (int64_t)ctx->sm_count * per_sm;
+        if (grid > nb) grid = nb;
+        {
+            KernelTimer timer_(ctx, MS_K_SPEC_SMOOTH, st);
+            kern<<<(unsigned)grid, 512, smem, st>>>(sa, (int)nb);
+        }
+        ctx->launches++;
+        MS_CUDA(cudaGetLastError());
+    }
+    return MS_OK;
+}
+
+int launch_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) {
+    if (!ctx->spec.w0) { ms_set_error("spectral net not configured"); return MS_ESTATE; }
+    if (a.star_slot < 0 || a.star_slot >= (int)ctx->stars.size() || !ctx->stars[a.star_slot].set ||
+        ctx->stars[a.star_slot].n_obs <= 0) {
+        ms_set_error("star slot %d has no observed spectrum", a.star_slot);
+        return MS_ESTATE;
+    }
+    if (a.modpoly && (a.n_pc < 1 || a.n_pc > MS_MAX_PC)) { ms_set_error("n_pc out of range"); return MS_EINVAL; }
+    if (B <= 0) return MS_OK;
+    if (ctx->precision == MS_PREC_F64) return run_spec<double>(ctx, a, B, st);
+    return run_spec<float>(ctx, a, B, st);
+}

@@ -1,0 +1,62 @@
+"""CPU: the oracle ports against golden vectors written by the reference itself
+(tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import fit_setup, sub
+from oracle import like_port, mist_port, smoothing_port
+from minesweeper_b200 import synth
+
+
+def test_mist_port_matches_reference(g_mist):
+    mist = sub(g_mist, 'mist_')
+    G = mist_port.GenMISTPort(synth.mist_rows(mist), ageweight=True)
+    q = g_mist['theta4']
+    step = 7                                   # per-point port is slow; the dense form below covers all rows
+    for i in range(0, len(q), step):
+        out = G.getMIST(eep=q[i, 0], mass=q[i, 1], feh=q[i, 2], afe=q[i, 3])
+        if g_mist['ok'][i]:
+            np.testing.assert_allclose(out, g_mist['pred'][i], rtol=1e-14, atol=0)
+        else:
+            assert out is None
+
+
+def test_mist_dense_matches_reference(g_mist):
+    mist = sub(g_mist, 'mist_')
+    q = g_mist['theta4']
+    br, pred, ok = mist_port.interp_dense(mist, q[:, 0], q[:, 1], q[:, 2], q[:, 3])
+    assert np.array_equal(br, g_mist['brackets'])              # bit-exact brackets, in and out of grid
+    assert np.array_equal(ok, g_mist['ok'])
+    np.testing.assert_allclose(pred[ok], g_mist['pred'][ok][:, 4:], rtol=1e-13, atol=1e-15)
+    assert g_mist['ok'].sum() > 2000 and (~g_mist['ok']).sum() > 100
+
+
+def test_smoothing_port_matches_reference(g_smooth):
+    w, f, ow = g_smooth['wave'], g_smooth['flux'], g_smooth['outwave']
+    for v, ref in zip(g_smooth['vsini'], g_smooth['vsini_out']):
+        out = smoothing_port.smooth_vsini(w, f, v, outwave=None, inres=0.0)
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-14)
+    ws = w * (1 + float(g_smooth['r_vshift']) / 299792.458)
+    for r, ref in zip(g_smooth['rsigma'], g_smooth['r_out']):
+        out = smoothing_port.smooth_R(ws, f, r, ow, inres=float(g_smooth['r_inres']))
+        np.testing.assert_allclose(out, ref, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize('which', ['phot', 'spec'])
+def test_like_port_matches_reference(which, g_like_phot, g_like_spec):
+    g = g_like_phot if which == 'phot' else g_like_spec
+    fitargs, fitpars, runbools = fit_setup(g)
+    L = like_port.LikelihoodPort(fitargs, fitpars, runbools)
+    assert L.fitpars_i == [str(s) for s in g['fitpars_i']]
+    keys = [str(k) for k in g['parsdict_keys']]
+    n = len(g['theta']) if which == 'phot' else 40
+    for i in range(n):
+        lnl = L.lnlikefn(list(g['theta'][i]))
+        if np.isfinite(g['lnl'][i]):
+            assert abs(lnl - g['lnl'][i]) <= 1e-9 * max(1.0, abs(g['lnl'][i])), i
+            got = np.array([L.parsdict.get(k, np.nan) for k in keys])
+            np.testing.assert_allclose(got, g['parsdict'][i], rtol=1e-13, atol=0)
+        else:
+            assert lnl == g['lnl'][i]
+            assert all(L.parsdict[k] == np.inf for k in like_port.FAIL_KEYS)
+    assert (~np.isfinite(g['lnl'])).sum() >= 2
