@@ -1,13 +1,461 @@
-// Kernel (2), tensor-core form (MS_PREC_TC) -- placeholder until the tcgen05 kernel lands.
+// Kernel (2), tensor-core form (MS_PREC_TC): the photometric MLP stack
+// 6 -> 128 -> 128 -> 1 per band on tcgen05 with TMEM accumulators, fused with
+// the magnitude formula and the photometric chi-square.  Same contract as
+// phot_mlp.cu (GenMod.genphot, reference genmod.py:97-142; FastPayneSEDPredict.sed,
+// external Payne, PARITY UNPINNED; likelihood.lnlike, likelihood.py:204-210).
+//
+// Numerics: every operand is split into two fp16 halves (hi + lo, 22 significant
+// bits) and each GEMM is three kind::f16 MMAs (hi.hi + lo.hi + hi.lo) accumulated
+// in fp32, i.e. fp32-class products at one third of the fp16 tensor rate.  The
+// factor -log2(e) and the layer-1 bias are folded into the packed weights, so the
+// accumulators hold the exponent argument of the sigmoid directly.
+//
+// Structure (one persistent CTA per SM, 320 threads):
+//   warps 0-3 / 4-7  two epilogue warpgroups, each owning one 128-point tile; a thread
+//                    owns one point (= one TMEM lane) for the whole band sweep
+//   warp 8           MMA issuer (one elected lane)
+//   warp 9           weight producer: bulk async copies of the per-band weight image
+//                    (global/L2 -> shared) into a two-deep ring
+// Per tile and band:
+//   D1 = X W1^T            SS MMA, K = 16 (6 inputs + bias column), X tile in shared memory
+//   A1 = sigmoid(D1)       TMEM -> registers -> (ex2, rcp) -> fp16 hi/lo -> TMEM, written
+//                          in place over D1 so the activations never touch shared memory
+//   D2 = A1 W2^T           TS MMA (A operand read from TMEM), K = 128
+//   BC = w3 . sigmoid(D2 + b2) + b3 ; magnitude ; chi-square term     (registers)
+// TMEM: 2 tiles x (128 columns D1/A1 + 128 columns D2) = 512 columns.
+// The two warpgroups keep the MUFU pipe busy while the tensor pipe works on the
+// other tile; the MUFU pipe (one ex2 and half an rcp per activation) is the binder.
 #include "common.cuh"
 
-int phot_tc_prepare(ms_ctx *ctx) {
-    (void)ctx;
-    ms_set_error("MS_PREC_TC photometric kernel not available in this build");
-    return MS_ESTATE;
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int H = 128;             // hidden width this kernel is specialised for
+constexpr int KX = 16;             // padded layer-1 K (d_in <= 6, bias column at 6)
+constexpr int TILE = 128;          // points per tile = TMEM lanes
+constexpr int NTHREADS = 320;
+
+// Per-band weight image in global memory (and in each shared-memory ring slot).
+// Operand images use the K-major no-swizzle core-matrix layout: [k/8][row][k%8] fp16,
+// i.e. 8 rows x 16 B core matrices, SBO = 128 B between 8-row groups, LBO = 2048 B
+// between 8-element K chunks (128 rows).
+constexpr int W1_BYTES = 2 * 128 * 16;                 // K=16: 4096 B
+constexpr int W2_BYTES = 16 * 128 * 16;                // K=128: 32768 B
+constexpr int OFF_W1H = 0;
+constexpr int OFF_W1L = OFF_W1H + W1_BYTES;
+constexpr int OFF_W2H = OFF_W1L + W1_BYTES;
+constexpr int OFF_W2L = OFF_W2H + W2_BYTES;
+constexpr int OFF_CB2 = OFF_W2L + W2_BYTES;            // float[128]: -log2e * b2
+constexpr int OFF_W3 = OFF_CB2 + 512;                  // float[128]
+constexpr int OFF_B3 = OFF_W3 + 512;                   // float[4] (b3 in [0])
+constexpr int BAND_BYTES = OFF_B3 + 128;               // 73,856 B (multiple of 128)
+
+constexpr int X_BYTES = 2 * 128 * 16;                  // one X tile image (hi or lo)
+constexpr int SM_W = 0;                                // 2 ring slots
+constexpr int SM_X = SM_W + 2 * BAND_BYTES;            // 2 tiles x (hi, lo)
+constexpr int SM_BAR = SM_X + 4 * X_BYTES;             // mbarriers
+constexpr int SM_TOTAL = SM_BAR + 256;
+
+// instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_A1 = 8, BAR_D2 = 10, BAR_N = 12 };
+
+// ---- PTX wrappers --------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d), "r"(a), "l"(bdesc), "r"(IDESC), "r"(acc) : "memory");
+}
+// K-major, no swizzle: start address, LBO (K-chunk stride), SBO (8-row group stride), version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+
+#define TMEM_LD32(addr, v)                                                                          \
+    asm volatile(                                                                                   \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                   \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                    \
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                   \
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
+          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),        \
+          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),        \
+          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                             \
+        : "r"(addr))
+
+#define TMEM_ST32(addr, v)                                                                          \
+    asm volatile(                                                                                   \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                             \
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                                   \
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                          \
+        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
+          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),     \
+          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),   \
+          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])    \
+        : "memory")
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// sigmoid of two accumulators that already hold t = -log2(e) * z: 1 / (1 + 2^t), one rcp per pair
+__device__ __forceinline__ void sigmoid_pair(float t0, float t1, float &a0, float &a1) {
+    const float d0 = 1.0f + ex2_approx(fminf(t0, 60.0f));
+    const float d1 = 1.0f + ex2_approx(fminf(t1, 60.0f));
+    const float r = rcp_approx(d0 * d1);
+    a0 = r * d1;
+    a1 = r * d0;
+}
+
+struct TcArgs {
+    const double *pars; const int32_t *star_slot;
+    double *mags; double *chi2;
+    const double *obs_mag, *obs_err2;
+    const unsigned char *wimg;         // [nb][BAND_BYTES]
+    double xmin[8], xscale[8];
+    int nb, d_in;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t s_tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar0 = sbase + SM_BAR;
+    auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(BAR_WFULL + i), 1);
+            mbar_init(bar(BAR_WEMPTY + i), 8);
+            mbar_init(bar(BAR_XFULL + i), 4);
+            mbar_init(bar(BAR_D1 + i), 1);
+            mbar_init(bar(BAR_A1 + i), 4);
+            mbar_init(bar(BAR_D2 + i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {                                   // TMEM: all 512 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+    const int nb = a.nb;
+    int my_pairs = 0;
+    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) ++my_pairs;
+
+    if (warp == 9) {
+        // ===== weight producer =====
+        if (lane == 0) {
+            const int total = my_pairs * nb;
+            for (int g = 0; g < total; ++g) {
+                const int buf = g & 1;
+                mbar_wait(bar(BAR_WEMPTY + buf), ((g >> 1) & 1) ^ 1);
+                mbar_expect_tx(bar(BAR_WFULL + buf), BAND_BYTES);
+                bulk_g2s(sbase + SM_W + buf * BAND_BYTES, a.wimg + (size_t)(g % nb) * BAND_BYTES, BAND_BYTES,
+                         bar(BAR_WFULL + buf));
+            }
+        }
+    } else if (warp == 8) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int g = 0;
+            for (int it = 0; it < my_pairs; ++it) {
+                for (int b = 0; b < nb; ++b, ++g) {
+                    const int buf = g & 1;
+                    const uint32_t wb = sbase + SM_W + buf * BAND_BYTES;
+                    mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);
+                    const uint64_t w1h = make_desc(wb + OFF_W1H, 2048, 128), w1l = make_desc(wb + OFF_W1L, 2048, 128);
+                    for (int T = 0; T < 2; ++T) {
+                        if (b == 0) mbar_wait(bar(BAR_XFULL + T), it & 1);
+                        tc_fence_after();
+                        const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;
+                        const uint64_t xh = make_desc(xb, 2048, 128), xl = make_desc(xb + X_BYTES, 2048, 128);
+                        const uint32_t d1 = tmem + T * 256;
+                        mma_ss(d1, xh, w1h, 0);
+                        mma_ss(d1, xl, w1h, 1);
+                        mma_ss(d1, xh, w1l, 1);
+                        tc_commit(bar(BAR_D1 + T));
+                    }
+                    for (int T = 0; T < 2; ++T) {
+                        mbar_wait(bar(BAR_A1 + T), g & 1);
+                        tc_fence_after();
+                        const uint32_t a1 = tmem + T * 256, d2 = tmem + T * 256 + 128;
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            const uint64_t bh = make_desc(wb + OFF_W2H + s * 4096, 2048, 128);
+                            const uint64_t bl = make_desc(wb + OFF_W2L + s * 4096, 2048, 128);
+                            const uint32_t ah = a1 + 32 * (s >> 1) + 8 * (s & 1), al = ah + 16;
+                            mma_ts(d2, ah, bh, s > 0);
+                            mma_ts(d2, al, bh, 1);
+                            mma_ts(d2, ah, bl, 1);
+                        }
+                        tc_commit(bar(BAR_D2 + T));
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== epilogue warpgroups: tile T, row r =====
+        const int T = warp >> 2;
+        const int r = threadIdx.x & 127;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t t_reg1 = tmem + lane_base + T * 256, t_d2 = t_reg1 + 128;
+        unsigned char *xrow_h = smem + SM_X + T * 2 * X_BYTES, *xrow_l = xrow_h + X_BYTES;
+        int g = 0;
+        for (int it = 0; it < my_pairs; ++it) {
+            const int pr = blockIdx.x + it * gridDim.x;
+            const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + r;
+            const bool live = p < B;
+            bool ok = false;
+            double mag0 = 0.0;
+            float xs[8];
+#pragma unroll
+            for (int d = 0; d < 8; ++d) xs[d] = 0.f;
+            if (live) {
+                const double *q = a.pars + p * MS_NPARS;
+                const double teff = q[PV_TEFF];
+                ok = teff != ms_inf();
+                if (ok) {
+                    const double logt = log10(teff);                     // genmod.py:111-113
+                    const double logl = 2.0 * q[PV_LOGR] + 4.0 * (logt - log10(5770.0));
+                    mag0 = -2.5 * logl + 4.74 + 5.0 * log10(q[PV_DIST]) - 5.0;
+                    const double xin[6] = {pow(10.0, logt), q[PV_LOGG], q[PV_FEH], q[PV_AFE], q[PV_AV], 3.1};
+#pragma unroll
+                    for (int d = 0; d < 6; ++d)
+                        if (d < a.d_in) xs[d] = (float)((xin[d] - a.xmin[d]) * a.xscale[d] - 0.5);
+                }
+            }
+            xs[6] = 1.0f;                                                // bias column
+            {   // X tile row in the core-matrix layout: chunk c (8 k) at c*2048 + r*16
+                __half2 hh[8], ll[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const __half2 h2 = __floats2half2_rn(xs[2 * i], xs[2 * i + 1]);
+                    const float2 back = __half22float2(h2);
+                    hh[i] = h2;
+                    ll[i] = __floats2half2_rn(xs[2 * i] - back.x, xs[2 * i + 1] - back.y);
+                    hh[4 + i] = __floats2half2_rn(0.f, 0.f);
+                    ll[4 + i] = hh[4 + i];
+                }
+                *reinterpret_cast<uint4 *>(xrow_h + r * 16) = *reinterpret_cast<uint4 *>(&hh[0]);
+                *reinterpret_cast<uint4 *>(xrow_h + 2048 + r * 16) = *reinterpret_cast<uint4 *>(&hh[4]);
+                *reinterpret_cast<uint4 *>(xrow_l + r * 16) = *reinterpret_cast<uint4 *>(&ll[0]);
+                *reinterpret_cast<uint4 *>(xrow_l + 2048 + r * 16) = *reinterpret_cast<uint4 *>(&ll[4]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(BAR_XFULL + T));
+            const int slot = (live && a.star_slot) ? a.star_slot[p] : 0;
+            double chi2 = 0.0;
+
+            for (int b = 0; b < nb; ++b, ++g) {
+                const int buf = g & 1;
+                const unsigned char *wb = smem + SM_W + buf * BAND_BYTES;
+                // ---- layer-1 epilogue: sigmoid, fp16 split, written back in place as the TS A operand
+                mbar_wait(bar(BAR_D1 + T), g & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t v[32], o[32];
+                    TMEM_LD32(t_reg1 + 32 * j, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float a0, a1;
+                        sigmoid_pair(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), a0, a1);
+                        const __half2 h2 = __floats2half2_rn(a0, a1);
+                        const float2 back = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn(a0 - back.x, a1 - back.y);
+                        o[i] = *reinterpret_cast<const uint32_t *>(&h2);
+                        o[16 + i] = *reinterpret_cast<const uint32_t *>(&l2);
+                    }
+                    TMEM_ST32(t_reg1 + 32 * j, o);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_A1 + T));
+
+                // ---- layer-2 epilogue: sigmoid, dot with w3, magnitude, chi-square term
+                mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);           // epilogue constants visible
+                const float4 *cb2 = reinterpret_cast<const float4 *>(wb + OFF_CB2);
+                const float4 *w3 = reinterpret_cast<const float4 *>(wb + OFF_W3);
+                float bc0 = 0.f, bc1 = 0.f;
+                mbar_wait(bar(BAR_D2 + T), g & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t v[32];
+                    TMEM_LD32(t_d2 + 32 * j, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 c = cb2[8 * j + i], w = w3[8 * j + i];
+                        float a0, a1, a2, a3;
+                        sigmoid_pair(__uint_as_float(v[4 * i]) + c.x, __uint_as_float(v[4 * i + 1]) + c.y, a0, a1);
+                        sigmoid_pair(__uint_as_float(v[4 * i + 2]) + c.z, __uint_as_float(v[4 * i + 3]) + c.w, a2, a3);
+                        bc0 = fmaf(w.x, a0, bc0); bc1 = fmaf(w.y, a1, bc1);
+                        bc0 = fmaf(w.z, a2, bc0); bc1 = fmaf(w.w, a3, bc1);
+                    }
+                }
+                const float b3 = *reinterpret_cast<const float *>(wb + OFF_B3);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_WEMPTY + buf));       // ring slot free for band g + 2
+                if (ok) {
+                    const double mag = mag0 - (double)(bc0 + bc1 + b3);
+                    if (a.mags) a.mags[p * nb + b] = mag;
+                    if (a.chi2) {
+                        const double o = a.obs_mag[(size_t)slot * nb + b];
+                        const double rr = mag - o;
+                        const double t = (rr * rr) / a.obs_err2[(size_t)slot * nb + b];
+                        if (t == t) chi2 += t;                           // nansum (likelihood.py:207)
+                    }
+                } else if (live && a.mags) {
+                    a.mags[p * nb + b] = ms_nan();
+                }
+            }
+            if (ok && a.chi2) a.chi2[p] += chi2;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// fp16 hi / lo split of a double, returned as raw bits
+void split_f16(double v, uint16_t &hi, uint16_t &lo) {
+    const __half h = __float2half_rn((float)v);
+    const double back = (double)__half2float(h);
+    const __half l = __float2half_rn((float)(v - back));
+    hi = *reinterpret_cast<const uint16_t *>(&h);
+    lo = *reinterpret_cast<const uint16_t *>(&l);
+}
+
+}  // namespace
+
+int phot_tc_prepare(ms_ctx *ctx) {
+    PhotNetDev &P = ctx->phot;
+    if (P.h != H || P.d_in > 6) {
+        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 128 and <= 6 inputs "
+                     "(got h=%d, d_in=%d); use MS_PREC_F32", P.h, P.d_in);
+        return MS_EINVAL;
+    }
+    const int nb = P.nb, D = P.d_in;
+    std::vector<float> w1((size_t)nb * H * D), b1((size_t)nb * H), w2((size_t)nb * H * H), b2((size_t)nb * H),
+        w3((size_t)nb * H), b3(nb);
+    MS_CUDA(cudaMemcpy(w1.data(), P.w1, w1.size() * 4, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(b1.data(), P.b1, b1.size() * 4, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(w2.data(), P.w2, w2.size() * 4, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(b2.data(), P.b2, b2.size() * 4, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(w3.data(), P.w3, w3.size() * 4, cudaMemcpyDeviceToHost));
+    MS_CUDA(cudaMemcpy(b3.data(), P.b3, b3.size() * 4, cudaMemcpyDeviceToHost));
+    const double NL2E = -1.4426950408889634;                      // -log2(e), folded into the weights
+    std::vector<unsigned char> img((size_t)nb * BAND_BYTES, 0);
+    for (int b = 0; b < nb; ++b) {
+        unsigned char *base = img.data() + (size_t)b * BAND_BYTES;
+        uint16_t *w1h = reinterpret_cast<uint16_t *>(base + OFF_W1H), *w1l = reinterpret_cast<uint16_t *>(base + OFF_W1L);
+        uint16_t *w2h = reinterpret_cast<uint16_t *>(base + OFF_W2H), *w2l = reinterpret_cast<uint16_t *>(base + OFF_W2L);
+        float *cb2 = reinterpret_cast<float *>(base + OFF_CB2), *w3o = reinterpret_cast<float *>(base + OFF_W3);
+        float *b3o = reinterpret_cast<float *>(base + OFF_B3);
+        for (int n = 0; n < H; ++n) {
+            for (int k = 0; k < KX; ++k) {
+                double v = 0.0;
+                if (k < D) v = NL2E * (double)w1[((size_t)b * H + n) * D + k];
+                else if (k == 6) v = NL2E * (double)b1[(size_t)b * H + n];
+                if (std::fabs(v) > 6.0e4) { ms_set_error("layer-1 weight exceeds the fp16 range"); return MS_EINVAL; }
+                const size_t at = (size_t)(k / 8) * 1024 + (size_t)n * 8 + (k % 8);   // in fp16 elements
+                split_f16(v, w1h[at], w1l[at]);
+            }
+            for (int k = 0; k < H; ++k) {
+                const double v = NL2E * (double)w2[((size_t)b * H + n) * H + k];
+                if (std::fabs(v) > 6.0e4) { ms_set_error("layer-2 weight exceeds the fp16 range"); return MS_EINVAL; }
+                const size_t at = (size_t)(k / 8) * 1024 + (size_t)n * 8 + (k % 8);
+                split_f16(v, w2h[at], w2l[at]);
+            }
+            cb2[n] = (float)(NL2E * (double)b2[(size_t)b * H + n]);
+            w3o[n] = w3[(size_t)b * H + n];
+        }
+        b3o[0] = b3[b];
+    }
+    MS_CUDA(cudaMalloc(&P.tc_pack, img.size()));
+    MS_CUDA(cudaMemcpy(P.tc_pack, img.data(), img.size(), cudaMemcpyHostToDevice));
+    P.tc_pack_bytes = img.size();
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    return MS_OK;
+}
+
 int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
-    (void)ctx; (void)a; (void)B; (void)st;
-    ms_set_error("MS_PREC_TC photometric kernel not available in this build");
-    return MS_ESTATE;
+    const PhotNetDev &n = ctx->phot;
+    if (!n.tc_pack) { ms_set_error("photometric net not packed for MS_PREC_TC"); return MS_ESTATE; }
+    if (B <= 0) return MS_OK;
+    if (a.chi2 && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
+    TcArgs ka;
+    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2;
+    ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
+    ka.wimg = static_cast<const unsigned char *>(n.tc_pack);
+    for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
+    ka.nb = n.nb; ka.d_in = n.d_in;
+    const int64_t npairs = (B + 2 * TILE - 1) / (2 * TILE);
+    const int grid = (int)(npairs < ctx->sm_count ? npairs : ctx->sm_count);
+    KernelTimer timer_(ctx, MS_K_PHOT, st);
+    phot_mlp_tc_kernel<<<grid, NTHREADS, SM_TOTAL, st>>>(ka, B, (int)npairs);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
 }

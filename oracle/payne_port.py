@@ -71,6 +71,23 @@ class FastPayneSEDPredict(object):
         a2 = _sigmoid(np.einsum('bhk,bk->bh', self.w2, a1) + self.b2)
         return np.einsum('bok,bk->bo', self.w3, a2)[:, 0] + self.b3[:, 0]
 
+    def bolcorr_batch(self, X):
+        """Vectorised ``bolcorr`` for X[B, d_in] (test helper; same arithmetic)."""
+        xs = (np.asarray(X, dtype=np.float64)[:, :self.d_in] - self.xmin) / (self.xmax - self.xmin) - 0.5
+        a1 = _sigmoid(np.einsum('bhd,nd->nbh', self.w1, xs) + self.b1)
+        a2 = _sigmoid(np.einsum('bhk,nbk->nbh', self.w2, a1) + self.b2)
+        return np.einsum('bk,nbk->nb', self.w3[:, 0, :], a2) + self.b3[:, 0]
+
+    def sed_batch(self, photpars):
+        """photpars[B,7] = (Teff, logg, feh, afe, logR, Dist, Av) -> mags[B, nb], following
+        GenMod.genphot (genmod.py:97-142) + ``sed``."""
+        pp = np.asarray(photpars, dtype=np.float64)
+        logt = np.log10(pp[:, 0])
+        logl = 2.0 * pp[:, 4] + 4.0 * (logt - np.log10(5770.0))
+        X = np.stack([10.0 ** logt, pp[:, 1], pp[:, 2], pp[:, 3], pp[:, 6], np.full(len(pp), 3.1)], 1)
+        bc = self.bolcorr_batch(X)
+        return (-2.5 * logl + 4.74 + 5.0 * np.log10(pp[:, 5]) - 5.0)[:, None] - bc
+
     def sed(self, logt=None, logg=None, feh=None, afe=None, logl=0.0, av=0.0,
             rv=3.1, dist=10.0, **extra):
         bc = self.bolcorr([10.0 ** logt, logg, feh, afe, av, rv])
