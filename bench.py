@@ -14,7 +14,6 @@ HBM.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -37,7 +36,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('MS_BENCH_PRECISION', 'f32'))
+    ap.add_argument('--precision', default=os.environ.get('MS_BENCH_PRECISION', 'tc'))
     ap.add_argument('--batch', type=int, default=1 << 20, help='live points per GPU')
     ap.add_argument('--hidden', type=int, default=128)
     ap.add_argument('--small-grid', action='store_true', help='debug: 60x24x7x5 grid')
@@ -79,45 +78,51 @@ def workload_name(args, mist):
 
 
 class ClockSampler(object):
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """Samples SM clock / power / throttle reasons of one GPU through NVML from a
+    thread (every ~2 ms) while the timed region runs."""
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.ok, self.stop_flag = [], False, False
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.ok = True
+            self.t = threading.Thread(target=self._run, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:                     # pragma: no cover
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                                  if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons')
+                                  else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.proc.terminate()
-        try:
-            self.proc.wait(2)
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        hi = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
-        return dict(sm_mhz=float(np.median(hi)) if hi else None, sm_max_mhz=max(mx) if mx else None,
-                    samples=len(sm), reasons=sorted(reasons))
+        if not self.ok:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvml unavailable'])
+        self.stop_flag = True
+        self.t.join(1.0)
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted(k for k, bit in names.items() if any(r[2] & bit for r in self.rows))
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(self.max_mhz),
+                    power_w_max=max((r[1] for r in self.rows), default=None), samples=len(sm),
+                    reasons=reasons)
 
 
 def run_reference(args):
