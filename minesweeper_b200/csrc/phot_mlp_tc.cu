@@ -24,7 +24,8 @@
 //   BC = w3 . sigmoid(D2 + b2) + b3 ; magnitude ; chi-square term     (registers)
 // TMEM: 2 tiles x (128 columns D1/A1 + 128 columns D2) = 512 columns.
 // The two warpgroups keep the MUFU pipe busy while the tensor pipe works on the
-// other tile; the MUFU pipe (one ex2 and half an rcp per activation) is the binder.
+// other tile.  The layer-2 k-steps of a tile are issued chunk by chunk as its activations land
+// in TMEM.  Binder: instruction issue of the sigmoid stream (see sigmoid_quad).
 #include "common.cuh"
 
 #include <cuda_fp16.h>
@@ -60,7 +61,7 @@ constexpr int SM_TOTAL = SM_BAR + 256;
 // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_A1 = 8, BAR_D2 = 10, BAR_N = 12 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR_A1 = 10 /* [tile][chunk] */, BAR_N = 18 };
 
 // ---- PTX wrappers --------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,6 +83,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -146,13 +155,22 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// sigmoid of two accumulators that already hold t = -log2(e) * z: 1 / (1 + 2^t), one rcp per pair
-__device__ __forceinline__ void sigmoid_pair(float t0, float t1, float &a0, float &a1) {
-    const float d0 = 1.0f + ex2_approx(fminf(t0, 60.0f));
-    const float d1 = 1.0f + ex2_approx(fminf(t1, 60.0f));
-    const float r = rcp_approx(d0 * d1);
-    a0 = r * d1;
-    a1 = r * d0;
+// Sigmoid of four accumulators that already hold t = -log2(e) z: 1 / (1 + 2^t) with one rcp
+// shared by the four (1.25 MUFU per activation).  The clamp keeps the product of the four
+// denominators inside the fp32 range (sigmoid error <= 2^-30).  On B200 this code is bound by
+// instruction issue, not by the MUFU pipe alone (tools/mufu_bench.cu: 16 ex2/clk/SM alone, but
+// ~12.9 elements/clk/SM once 7 FP32 instructions accompany each MUFU), so every instruction
+// per activation counts.
+__device__ __forceinline__ void sigmoid_quad(float t0, float t1, float t2, float t3, float &a0, float &a1,
+                                             float &a2, float &a3) {
+    const float d0 = 1.0f + ex2_approx(fminf(t0, 30.0f));
+    const float d1 = 1.0f + ex2_approx(fminf(t1, 30.0f));
+    const float d2 = 1.0f + ex2_approx(fminf(t2, 30.0f));
+    const float d3 = 1.0f + ex2_approx(fminf(t3, 30.0f));
+    const float p01 = d0 * d1, p23 = d2 * d3;
+    const float r = rcp_approx(p01 * p23);
+    const float r01 = r * p23, r23 = r * p01;
+    a0 = r01 * d1; a1 = r01 * d0; a2 = r23 * d3; a3 = r23 * d2;
 }
 
 struct TcArgs {
@@ -179,8 +197,8 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             mbar_init(bar(BAR_WEMPTY + i), 8);
             mbar_init(bar(BAR_XFULL + i), 4);
             mbar_init(bar(BAR_D1 + i), 1);
-            mbar_init(bar(BAR_A1 + i), 4);
             mbar_init(bar(BAR_D2 + i), 1);
+            for (int j = 0; j < 4; ++j) mbar_init(bar(BAR_A1 + 4 * i + j), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -209,18 +227,25 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             }
         }
     } else if (warp == 8) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: one non-blocking state machine per tile =====
+        // stage 0: layer 1 (needs the band's weights, and the X tile on band 0);
+        // stage 1..4: layer-2 k-steps of A1 chunk stage-1, issued as soon as that chunk has
+        // been written back to TMEM by the epilogue (K-pipelined behind the sigmoid).
         if (lane == 0) {
-            int g = 0;
-            for (int it = 0; it < my_pairs; ++it) {
-                for (int b = 0; b < nb; ++b, ++g) {
+            int it[2] = {0, 0}, bnd[2] = {0, 0}, stage[2] = {0, 0};
+            bool done[2] = {my_pairs == 0, my_pairs == 0};
+            while (!(done[0] && done[1])) {
+#pragma unroll
+                for (int T = 0; T < 2; ++T) {
+                    if (done[T]) continue;
+                    const int g = it[T] * nb + bnd[T];
                     const int buf = g & 1;
                     const uint32_t wb = sbase + SM_W + buf * BAND_BYTES;
-                    mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);
-                    const uint64_t w1h = make_desc(wb + OFF_W1H, 2048, 128), w1l = make_desc(wb + OFF_W1L, 2048, 128);
-                    for (int T = 0; T < 2; ++T) {
-                        if (b == 0) mbar_wait(bar(BAR_XFULL + T), it & 1);
+                    if (stage[T] == 0) {
+                        if (!mbar_test(bar(BAR_WFULL + buf), (g >> 1) & 1)) continue;
+                        if (bnd[T] == 0 && !mbar_test(bar(BAR_XFULL + T), it[T] & 1)) continue;
                         tc_fence_after();
+                        const uint64_t w1h = make_desc(wb + OFF_W1H, 2048, 128), w1l = make_desc(wb + OFF_W1L, 2048, 128);
                         const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;
                         const uint64_t xh = make_desc(xb, 2048, 128), xl = make_desc(xb + X_BYTES, 2048, 128);
                         const uint32_t d1 = tmem + T * 256;
@@ -228,21 +253,29 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         mma_ss(d1, xl, w1h, 1);
                         mma_ss(d1, xh, w1l, 1);
                         tc_commit(bar(BAR_D1 + T));
-                    }
-                    for (int T = 0; T < 2; ++T) {
-                        mbar_wait(bar(BAR_A1 + T), g & 1);
+                        stage[T] = 1;
+                    } else {
+                        const int j = stage[T] - 1;
+                        if (!mbar_test(bar(BAR_A1 + 4 * T + j), g & 1)) continue;
                         tc_fence_after();
                         const uint32_t a1 = tmem + T * 256, d2 = tmem + T * 256 + 128;
 #pragma unroll
-                        for (int s = 0; s < 8; ++s) {
+                        for (int s2 = 0; s2 < 2; ++s2) {
+                            const int s = 2 * j + s2;
                             const uint64_t bh = make_desc(wb + OFF_W2H + s * 4096, 2048, 128);
                             const uint64_t bl = make_desc(wb + OFF_W2L + s * 4096, 2048, 128);
-                            const uint32_t ah = a1 + 32 * (s >> 1) + 8 * (s & 1), al = ah + 16;
+                            const uint32_t ah = a1 + 32 * j + 8 * s2, al = ah + 16;
                             mma_ts(d2, ah, bh, s > 0);
                             mma_ts(d2, al, bh, 1);
                             mma_ts(d2, ah, bl, 1);
                         }
-                        tc_commit(bar(BAR_D2 + T));
+                        if (j == 3) {
+                            tc_commit(bar(BAR_D2 + T));
+                            stage[T] = 0;
+                            if (++bnd[T] == nb) { bnd[T] = 0; if (++it[T] == my_pairs) done[T] = true; }
+                        } else {
+                            stage[T] = j + 2;
+                        }
                     }
                 }
             }
@@ -313,21 +346,25 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     TMEM_LD32(t_reg1 + 32 * j, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float a0, a1;
-                        sigmoid_pair(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]), a0, a1);
-                        const __half2 h2 = __floats2half2_rn(a0, a1);
-                        const float2 back = __half22float2(h2);
-                        const __half2 l2 = __floats2half2_rn(a0 - back.x, a1 - back.y);
-                        o[i] = *reinterpret_cast<const uint32_t *>(&h2);
-                        o[16 + i] = *reinterpret_cast<const uint32_t *>(&l2);
+                    for (int i = 0; i < 8; ++i) {
+                        float a0, a1, a2, a3;
+                        sigmoid_quad(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), a0, a1, a2, a3);
+                        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y);
+                        const __half2 l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+                        o[2 * i] = *reinterpret_cast<const uint32_t *>(&h01);
+                        o[2 * i + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+                        o[16 + 2 * i] = *reinterpret_cast<const uint32_t *>(&l01);
+                        o[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                     }
                     TMEM_ST32(t_reg1 + 32 * j, o);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(BAR_A1 + 4 * T + j));   // chunk j usable as TS A operand
                 }
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(BAR_A1 + T));
 
                 // ---- layer-2 epilogue: sigmoid, dot with w3, magnitude, chi-square term
                 mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);           // epilogue constants visible
@@ -345,8 +382,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     for (int i = 0; i < 8; ++i) {
                         const float4 c = cb2[8 * j + i], w = w3[8 * j + i];
                         float a0, a1, a2, a3;
-                        sigmoid_pair(__uint_as_float(v[4 * i]) + c.x, __uint_as_float(v[4 * i + 1]) + c.y, a0, a1);
-                        sigmoid_pair(__uint_as_float(v[4 * i + 2]) + c.z, __uint_as_float(v[4 * i + 3]) + c.w, a2, a3);
+                        sigmoid_quad(__uint_as_float(v[4 * i]) + c.x, __uint_as_float(v[4 * i + 1]) + c.y,
+                                     __uint_as_float(v[4 * i + 2]) + c.z, __uint_as_float(v[4 * i + 3]) + c.w,
+                                     a0, a1, a2, a3);
                         bc0 = fmaf(w.x, a0, bc0); bc1 = fmaf(w.y, a1, bc1);
                         bc0 = fmaf(w.z, a2, bc0); bc1 = fmaf(w.w, a3, bc1);
                     }
