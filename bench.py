@@ -264,7 +264,8 @@ def main():
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get('phot_' + args.precision)
         tbl_b = 4 if args.precision != 'f64' else 8
-        interp_bytes = 4 * 8 + 16 * 9 * tbl_b + 13 * 8
+        # theta row in, 16 corners x 9 columns gathered, 20-double parameter block out (fused kernel)
+        interp_bytes = theta_np.shape[1] * 8 + 16 * 9 * tbl_b + 20 * 8
         out = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,

@@ -451,30 +451,34 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
     }
     int rc;
     const bool iso = tv.col[MS_P_EEP] >= 0 || tv.fixed[MS_P_EEP] == tv.fixed[MS_P_EEP];
-    double *der = nullptr;
-    if (iso) {
-        der = derived;
-        if (!der) {
-            if ((rc = ensure_scratch(&ctx->scr_derived, &ctx->scr_derived_n, (size_t)B * MS_NDERIVED))) return rc;
-            der = ctx->scr_derived;
-        }
-        if ((rc = launch_mist_interp(ctx, tv, B, brackets, der, nullptr, st))) return rc;
-    } else if (derived || brackets) {
+    if (!iso && (derived || brackets)) {
         ms_set_error("derived / brackets requested but EEP is not a parameter");
         return MS_EINVAL;
     }
     if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS))) return rc;
-    if ((rc = ensure_scratch(&ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)B))) return rc;
-    if ((rc = launch_build_pars(ctx, tv, der, flags->mistdif, B, ctx->scr_pars, ctx->scr_chi2, st))) return rc;
+    // chi2 scratch is only needed when a spectrum term precedes the photometry
+    double *chi2 = nullptr;
+    if (flags->spec || !flags->phot) {
+        if ((rc = ensure_scratch(&ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)B))) return rc;
+        chi2 = ctx->scr_chi2;
+    }
+    if (iso) {      // interpolation + parameter assembly in one kernel
+        if ((rc = launch_mist_interp(ctx, tv, B, brackets, derived, nullptr, st, ctx->scr_pars, chi2,
+                                     flags->mistdif))) return rc;
+    } else {
+        if ((rc = launch_build_pars(ctx, tv, nullptr, flags->mistdif, B, ctx->scr_pars, chi2, st))) return rc;
+    }
     if (flags->spec) {
-        SpecArgs sa{ctx->scr_pars, 0, flags->modpoly, flags->n_pc, nullptr, ctx->scr_chi2};
+        SpecArgs sa{ctx->scr_pars, 0, flags->modpoly, flags->n_pc, nullptr, chi2};
         if ((rc = launch_spec(ctx, sa, B, st))) return rc;
     }
-    if (flags->phot) {
-        PhotArgs pa{ctx->scr_pars, star_slot, nullptr, ctx->scr_chi2};
-        if ((rc = run_phot(ctx, pa, B, st))) return rc;
+    const int agew = iso && flags->ageweight;
+    if (flags->phot) {   // photometry is the last term: it also writes lnL
+        PhotArgs pa{ctx->scr_pars, star_slot, nullptr, chi2};
+        pa.lnL = lnL; pa.ageweight = agew;
+        return run_phot(ctx, pa, B, st);
     }
-    return launch_finalize(ctx, ctx->scr_pars, ctx->scr_chi2, iso && flags->ageweight, B, lnL, st);
+    return launch_finalize(ctx, ctx->scr_pars, chi2, agew, B, lnL, st);
 }
 
 extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const double *theta_host,

@@ -128,8 +128,11 @@ struct ThetaView {
     double fixed[MS_NPARAM];       // value when not sampled (NaN = absent)
 };
 
+// pars / chi2 (optional): also emit the per-point parameter block and zero chi2 (fused
+// form of launch_build_pars for isochrone fits)
 int launch_mist_interp(ms_ctx *ctx, const ThetaView &tv, int64_t B, int32_t *brackets,
-                       double *derived, uint8_t *ok, cudaStream_t st);
+                       double *derived, uint8_t *ok, cudaStream_t st, double *pars = nullptr,
+                       double *chi2 = nullptr, int mistdif = 1);
 
 // pars[B][MS_NPARS] from theta / fixed / derived (derived may be nullptr when EEP is
 // not sampled); chi2[B] = 0 for live rows.
@@ -148,6 +151,11 @@ struct PhotArgs {
     const int32_t *star_slot;      // [B] or nullptr
     double *mags;                  // [B][nb] or nullptr
     double *chi2;                  // [B] or nullptr
+    // fused finalisation (likelihood.py:168-176, 219): when lnL is set the kernel writes
+    // lnL = -0.5 (chi2[p] + chi2_phot) + (ageweight ? log Agewgt : 0), -inf for failed rows,
+    // and chi2 is only read
+    double *lnL = nullptr;
+    int ageweight = 0;
 };
 int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
 int phot_tc_prepare(ms_ctx *ctx);          // pack weights for the tensor-core kernel

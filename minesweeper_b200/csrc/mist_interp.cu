@@ -51,7 +51,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int ne, int nm, int nf,
                    int na, const T *__restrict__ table, int32_t *__restrict__ brackets,
-                   double *__restrict__ derived, uint8_t *__restrict__ okflag) {
+                   double *__restrict__ derived, uint8_t *__restrict__ okflag,
+                   double *__restrict__ pars, double *__restrict__ chi2, int mistdif) {
     extern __shared__ double s_axes[];
     const int ntot = ne + nm + nf + na;
     for (int i = threadIdx.x; i < ntot; i += blockDim.x) s_axes[i] = axes[i];
@@ -121,6 +122,28 @@ mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int
         }
         const bool ok = inside && (wsum > 0.0);
         if (okflag) okflag[p] = ok ? 1 : 0;
+        if (pars) {
+            // the per-point parameter block of likelihood.lnlikefn (likelihood.py:121-160),
+            // assembled here so the prediction never makes a round trip through HBM
+            double *o = pars + p * MS_NPARS;
+            const double inv = ok ? 1.0 / wsum : 0.0;
+            const double inf = ms_inf();
+            o[PV_TEFF] = ok ? pow(10.0, acc[4] * inv) : inf;             // likelihood.py:121
+            o[PV_LOGG] = ok ? acc[7] * inv : inf;
+            o[PV_FEH] = ok ? (mistdif ? acc[5] * inv : x[2]) : inf;      // :127-132
+            o[PV_AFE] = ok ? (mistdif ? acc[6] * inv : x[3]) : inf;
+            o[PV_VRAD] = theta_get(tv, p, MS_P_VRAD);
+            o[PV_VROT] = theta_get(tv, p, MS_P_VROT);
+            o[PV_VMIC] = theta_get(tv, p, MS_P_VMIC);
+            o[PV_INSTR] = theta_get(tv, p, MS_P_INST_R);
+            o[PV_LOGR] = ok ? acc[2] * inv : inf;
+            o[PV_DIST] = theta_get(tv, p, MS_P_DIST);
+            o[PV_AV] = theta_get(tv, p, MS_P_AV);
+            o[PV_AGEWGT] = ok ? acc[8] * inv : inf;
+#pragma unroll
+            for (int i = 0; i < MS_MAX_PC; ++i) o[PV_PC0 + i] = theta_get(tv, p, MS_P_PC0 + i);
+            if (chi2) chi2[p] = 0.0;
+        }
         if (derived) {
             double *o = derived + p * MS_NDERIVED;
             o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
@@ -134,7 +157,8 @@ mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int
 }  // namespace
 
 int launch_mist_interp(ms_ctx *ctx, const ThetaView &tv, int64_t B, int32_t *brackets,
-                       double *derived, uint8_t *ok, cudaStream_t st) {
+                       double *derived, uint8_t *ok, cudaStream_t st, double *pars, double *chi2,
+                       int mistdif) {
     const GridDev &g = ctx->grid;
     if (!g.axes) { ms_set_error("MIST grid not configured"); return MS_ESTATE; }
     if (B <= 0) return MS_OK;
@@ -146,10 +170,10 @@ int launch_mist_interp(ms_ctx *ctx, const ThetaView &tv, int64_t B, int32_t *bra
     size_t smem = (size_t)(g.ne + g.nm + g.nf + g.na) * sizeof(double);
     if (ctx->precision == MS_PREC_F64)
         mist_interp_kernel<double><<<(unsigned)blocks, threads, smem, st>>>(
-            tv, B, g.axes, g.ne, g.nm, g.nf, g.na, g.tab64, brackets, derived, ok);
+            tv, B, g.axes, g.ne, g.nm, g.nf, g.na, g.tab64, brackets, derived, ok, pars, chi2, mistdif);
     else
         mist_interp_kernel<float><<<(unsigned)blocks, threads, smem, st>>>(
-            tv, B, g.axes, g.ne, g.nm, g.nf, g.na, g.tab32, brackets, derived, ok);
+            tv, B, g.axes, g.ne, g.nm, g.nf, g.na, g.tab32, brackets, derived, ok, pars, chi2, mistdif);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

@@ -20,7 +20,7 @@ template <> __device__ __forceinline__ double sigmoid_t<double>(double z) { retu
 
 struct PhotKArgs {
     const double *pars; const int32_t *star_slot;
-    double *mags; double *chi2;
+    double *mags; double *chi2; double *lnL; int ageweight;
     const double *obs_mag, *obs_err2;
     const float *w1, *b1, *w2, *b2, *w3, *b3;
     double xmin[8], xscale[8];
@@ -113,7 +113,7 @@ phot_mlp_kernel(PhotKArgs a, int64_t B) {
             if (ok) {
                 const double mag = mag0 - (double)bc;
                 if (a.mags) a.mags[p * a.nb + b] = mag;
-                if (a.chi2) {
+                if (a.chi2 || a.lnL) {
                     const double o = a.obs_mag[(size_t)slot * a.nb + b];
                     const double r = mag - o;
                     const double t = (r * r) / a.obs_err2[(size_t)slot * a.nb + b];
@@ -123,7 +123,16 @@ phot_mlp_kernel(PhotKArgs a, int64_t B) {
                 a.mags[p * a.nb + b] = ms_nan();
             }
         }
-        if (ok && a.chi2) a.chi2[p] += chi2;
+        if (live && a.lnL) {
+            double l = -ms_inf();
+            if (ok) {
+                l = -0.5 * ((a.chi2 ? a.chi2[p] : 0.0) + chi2);
+                if (a.ageweight) l += log(a.pars[p * MS_NPARS + PV_AGEWGT]);
+            }
+            a.lnL[p] = l;
+        } else if (ok && a.chi2) {
+            a.chi2[p] += chi2;
+        }
     }
 }
 
@@ -157,9 +166,9 @@ int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
     const PhotNetDev &n = ctx->phot;
     if (!n.w1) { ms_set_error("photometric net not configured"); return MS_ESTATE; }
     if (B <= 0) return MS_OK;
-    if (a.chi2 && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
+    if ((a.chi2 || a.lnL) && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
     PhotKArgs ka;
-    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2;
+    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2; ka.lnL = a.lnL; ka.ageweight = a.ageweight;
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     ka.w1 = n.w1; ka.b1 = n.b1; ka.w2 = n.w2; ka.b2 = n.b2; ka.w3 = n.w3; ka.b3 = n.b3;
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }

@@ -175,7 +175,7 @@ __device__ __forceinline__ void sigmoid_quad(float t0, float t1, float t2, float
 
 struct TcArgs {
     const double *pars; const int32_t *star_slot;
-    double *mags; double *chi2;
+    double *mags; double *chi2; double *lnL; int ageweight;
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
     double xmin[8], xscale[8];
@@ -396,7 +396,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 if (ok) {
                     const double mag = mag0 - (double)(bc0 + bc1 + b3);
                     if (a.mags) a.mags[p * nb + b] = mag;
-                    if (a.chi2) {
+                    if (a.chi2 || a.lnL) {
                         const double o = a.obs_mag[(size_t)slot * nb + b];
                         const double rr = mag - o;
                         const double t = (rr * rr) / a.obs_err2[(size_t)slot * nb + b];
@@ -406,7 +406,16 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     a.mags[p * nb + b] = ms_nan();
                 }
             }
-            if (ok && a.chi2) a.chi2[p] += chi2;
+            if (live && a.lnL) {
+                double l = -ms_inf();
+                if (ok) {
+                    l = -0.5 * ((a.chi2 ? a.chi2[p] : 0.0) + chi2);
+                    if (a.ageweight) l += log(a.pars[p * MS_NPARS + PV_AGEWGT]);
+                }
+                a.lnL[p] = l;
+            } else if (ok && a.chi2) {
+                a.chi2[p] += chi2;
+            }
         }
     }
     tc_fence_before();
@@ -482,9 +491,9 @@ int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
     const PhotNetDev &n = ctx->phot;
     if (!n.tc_pack) { ms_set_error("photometric net not packed for MS_PREC_TC"); return MS_ESTATE; }
     if (B <= 0) return MS_OK;
-    if (a.chi2 && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
+    if ((a.chi2 || a.lnL) && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
     TcArgs ka;
-    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2;
+    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2; ka.lnL = a.lnL; ka.ageweight = a.ageweight;
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     ka.wimg = static_cast<const unsigned char *>(n.tc_pack);
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
