@@ -1,0 +1,69 @@
+"""Data-parallel sharding of the likelihood path over the GPUs of one box.
+
+The path has no exchange step: every likelihood evaluation and
+every star is independent, so ranks take contiguous blocks of rows (or stars), keep
+the model tables replicated, and the only collective is one gather of fixed-size
+results per batch (``all_gather_into_tensor`` over NCCL/NVLink; gloo in the CPU
+tests).  One process per GPU, launched with torchrun.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank, size):
+    """Contiguous block [lo, hi) of ``n`` items for ``rank``: ceil(n / size) per rank,
+    the tail ranks may be short or empty."""
+    per = -(-n // size) if size > 0 else n
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def gather_rows(local, n_total, group=None):
+    """Concatenate per-rank blocks (made with ``shard_bounds``) of a tensor whose first
+    axis is the sharded one; every rank receives the full result.  Blocks are padded to
+    the common block size so that one ``all_gather_into_tensor`` moves everything."""
+    rank, size = world()
+    if size == 1:
+        return local
+    per = -(-n_total // size)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((size * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    return out[:n_total]
+
+
+def sharded_lnlike(fn, theta, group=None):
+    """Evaluate ``fn(theta_block) -> lnL_block (tensor)`` on this rank's block of rows and
+    gather the full lnL on every rank.  ``fn`` is e.g.
+    ``lambda th: likeobj.lnlike_batch(th, want_derived=False)[0]``."""
+    rank, size = world()
+    n = len(theta)
+    lo, hi = shard_bounds(n, rank, size)
+    block = theta[lo:hi]
+    if hi > lo:
+        lnl = fn(block)
+    else:
+        lnl = None
+    if size == 1:
+        return lnl
+    if lnl is None:
+        dev = theta.device if torch.is_tensor(theta) else torch.device('cpu')
+        lnl = torch.empty((0,), dtype=torch.float64, device=dev)
+    return gather_rows(lnl, n, group=group)
+
+
+def star_blocks(n_stars, rank=None, size=None):
+    """Catalog mode: the block of star indices pinned to this rank's device."""
+    r, s = world()
+    rank = r if rank is None else rank
+    size = s if size is None else size
+    lo, hi = shard_bounds(n_stars, rank, size)
+    return np.arange(lo, hi)
