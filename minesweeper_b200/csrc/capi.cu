@@ -266,7 +266,9 @@ extern "C" int ms_create(ms_ctx **out, int device, int precision, const ms_grid_
     if (grid && (rc = setup_grid(ctx, grid))) { ms_destroy(ctx); return rc; }
     if (phot && (rc = setup_phot(ctx, phot))) { ms_destroy(ctx); return rc; }
     if (spec && (rc = spec_prepare(ctx, spec))) { ms_destroy(ctx); return rc; }
-    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
         ms_destroy(ctx);
         ms_set_error("stream creation failed");
         return MS_ECUDA;
@@ -296,7 +298,10 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(ctx->scr_derived); cudaFree(ctx->scr_pars); cudaFree(ctx->scr_chi2);
     cudaFree(ctx->scr_flux); cudaFree(ctx->scr_hid); cudaFree(ctx->scr_theta); cudaFree(ctx->scr_out);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     delete ctx;
 }
 
@@ -489,13 +494,45 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
     int rc;
     if ((rc = ensure_scratch(&ctx->scr_theta, &ctx->scr_theta_n, (size_t)B * ndim))) return rc;
     if ((rc = ensure_scratch(&ctx->scr_out, &ctx->scr_out_n, (size_t)B * (1 + MS_NDERIVED)))) return rc;
-    cudaStream_t st = ctx->own_stream;
-    MS_CUDA(cudaMemcpyAsync(ctx->scr_theta, theta_host, (size_t)B * ndim * sizeof(double), cudaMemcpyHostToDevice, st));
     double *lnl_d = ctx->scr_out, *der_d = derived_host ? ctx->scr_out + B : nullptr;
-    if ((rc = ms_lnlike_batch(ctx, flags, ctx->scr_theta, nullptr, B, ndim, colmap, fixed, lnl_d, der_d, nullptr, st))) return rc;
-    MS_CUDA(cudaMemcpyAsync(lnL_host, lnl_d, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (derived_host)
-        MS_CUDA(cudaMemcpyAsync(derived_host, der_d, (size_t)B * MS_NDERIVED * sizeof(double), cudaMemcpyDeviceToHost, st));
-    MS_CUDA(cudaStreamSynchronize(st));
+    // Chunked three-stream pipeline: the host->device copy of chunk k+1 and the device->host
+    // copy of chunk k-1 overlap the kernels of chunk k (pinned host buffers make the copies
+    // truly asynchronous; pageable ones still work, serialised by the driver).
+    const int64_t kMaxChunks = 8, kMinChunk = 32768;
+    int64_t chunk = (B + kMaxChunks - 1) / kMaxChunks;
+    if (chunk < kMinChunk) chunk = kMinChunk;
+    {   // whole waves of the persistent phot kernel: one CTA per SM, 256 points per CTA iteration
+        const int64_t wave = (int64_t)ctx->sm_count * 256;
+        chunk = (chunk + wave - 1) / wave * wave;
+    }
+    const int nchunks = (int)((B + chunk - 1) / chunk);
+    while ((int)ctx->ev_pool.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        MS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_pool.push_back(e);
+    }
+    // pre-size the per-batch scratch once so the chunk calls never reallocate mid-pipeline
+    if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)chunk * MS_NPARS))) return rc;
+    if ((rc = ensure_scratch(&ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)chunk))) return rc;
+    for (int k = 0; k < nchunks; ++k) {
+        const int64_t b0 = (int64_t)k * chunk, nb = (B - b0 < chunk) ? B - b0 : chunk;
+        cudaEvent_t up = ctx->ev_pool[2 * k], done = ctx->ev_pool[2 * k + 1];
+        MS_CUDA(cudaMemcpyAsync(ctx->scr_theta + b0 * ndim, theta_host + b0 * ndim,
+                                (size_t)nb * ndim * sizeof(double), cudaMemcpyHostToDevice, ctx->h2d_stream));
+        MS_CUDA(cudaEventRecord(up, ctx->h2d_stream));
+        MS_CUDA(cudaStreamWaitEvent(ctx->own_stream, up, 0));
+        if ((rc = ms_lnlike_batch(ctx, flags, ctx->scr_theta + b0 * ndim, nullptr, nb, ndim, colmap, fixed,
+                                  lnl_d + b0, der_d ? der_d + b0 * MS_NDERIVED : nullptr, nullptr,
+                                  ctx->own_stream))) return rc;
+        MS_CUDA(cudaEventRecord(done, ctx->own_stream));
+        MS_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, done, 0));
+        MS_CUDA(cudaMemcpyAsync(lnL_host + b0, lnl_d + b0, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost,
+                                ctx->d2h_stream));
+        if (derived_host)
+            MS_CUDA(cudaMemcpyAsync(derived_host + b0 * MS_NDERIVED, der_d + b0 * MS_NDERIVED,
+                                    (size_t)nb * MS_NDERIVED * sizeof(double), cudaMemcpyDeviceToHost,
+                                    ctx->d2h_stream));
+    }
+    MS_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
     return MS_OK;
 }

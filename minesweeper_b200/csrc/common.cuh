@@ -89,7 +89,9 @@ struct ms_ctx {
     double *scr_theta = nullptr;   size_t scr_theta_n = 0;     // for the host-buffer entry point
     double *scr_out = nullptr;     size_t scr_out_n = 0;
     int32_t *colmap_dev = nullptr; double *fixed_dev = nullptr;
-    cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream = nullptr;           // compute stream of the host-buffer entry point
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    std::vector<cudaEvent_t> ev_pool;            // chunk pipeline events
     int64_t launches = 0;
     // live timing (ms_profile_*)
     bool prof_on = false;
