@@ -26,6 +26,7 @@
 #define MS_C_KMS 299792.458        // Payne's Doppler shift (scipy.constants.c / 1000)
 #define MS_ROT_TAB_H (1.0 / 32.0)  // spacing of the rotational-transfer table
 #define MS_ROT_TAB_N 8200
+#define SMOOTH_THREADS 512           // one CTA per SM: leaves ~100 KB of L1 for the twiddle / transfer tables
 
 namespace {
 
@@ -40,6 +41,18 @@ template <typename T2> __device__ __forceinline__ T2 cmul(T2 a, T2 b) {
 }
 template <typename T2> __device__ __forceinline__ T2 cmulc(T2 a, T2 b) {   // a * conj(b)
     return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y};
+}
+
+// one-pass data (flux row, resampling maps) is streamed past L1 so that the tables every
+// point re-reads (FFT twiddles, rotational transfer) stay L1-resident
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v; asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+}
+__device__ __forceinline__ int ld_stream(const int *p) {
+    int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
 struct SmoothArgs {
@@ -108,6 +121,77 @@ template <> __device__ __forceinline__ float Transfer<float>::operator()(int k) 
     return rot_transfer_f((float)u, tab);
 }
 
+// ---- in-place FFT passes in shared memory ------------------------------------------------
+// The transform is the textbook radix-2 decimation-in-frequency flow (natural order in,
+// bit-reversed order out) and its decimation-in-time mirror for the inverse, but three
+// consecutive radix-2 stages are fused into one pass: a thread loads the eight elements that
+// interact in stages with half-lengths 4q, 2q, q, does the three stages in registers and
+// stores them back, so a 8192-point transform makes 5 shared-memory passes instead of 13.
+// Twiddles come from the table tw[k] = exp(-2 pi i k / tw_n).
+template <typename T2> __device__ __forceinline__ void bfly_dif(T2 &a, T2 &b, const T2 w) {
+    const T2 d = csub(a, b);
+    a = cadd(a, b);
+    b = cmul(d, w);
+}
+template <typename T2> __device__ __forceinline__ void bfly_dit(T2 &a, T2 &b, const T2 w) {   // w conjugated here
+    const T2 t = cmulc(b, w);
+    b = csub(a, t);
+    a = cadd(a, t);
+}
+template <typename T2> __device__ __forceinline__ T2 mul_w8(const T2 t, int m) {   // t * exp(-2 pi i m / 8), m = 1..3
+    typedef decltype(t.x) T;
+    const T r = (T)0.70710678118654752440;
+    if (m == 1) return {r * (t.x + t.y), r * (t.y - t.x)};
+    if (m == 2) return {t.y, -t.x};
+    return {r * (t.y - t.x), -r * (t.x + t.y)};
+}
+
+template <typename T, bool INVERSE>
+__device__ __forceinline__ void fft_pass8(typename Cx<T>::type *z, int M, int q, int lq,
+                                          const typename Cx<T>::type *__restrict__ tw, int tw_n) {
+    typedef typename Cx<T>::type T2;
+    for (int t = threadIdx.x; t < (M >> 3); t += blockDim.x) {
+        const int posq = t & (q - 1);
+        const int base = ((t >> lq) << (lq + 3)) + posq;
+        const T2 t1 = tw[posq * (tw_n >> (lq + 3))];      // W_{8q}^{posq}
+        const T2 t2 = tw[posq * (tw_n >> (lq + 2))];      // W_{4q}^{posq}
+        const T2 t3 = tw[posq * (tw_n >> (lq + 1))];      // W_{2q}^{posq}
+        T2 x[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) x[m] = z[base + m * q];
+        const T2 wa1 = mul_w8(t1, 1), wa2 = mul_w8(t1, 2), wa3 = mul_w8(t1, 3);
+        const T2 wb1 = mul_w8(t2, 2);
+        if (!INVERSE) {
+            bfly_dif(x[0], x[4], t1); bfly_dif(x[1], x[5], wa1); bfly_dif(x[2], x[6], wa2); bfly_dif(x[3], x[7], wa3);
+            bfly_dif(x[0], x[2], t2); bfly_dif(x[1], x[3], wb1); bfly_dif(x[4], x[6], t2); bfly_dif(x[5], x[7], wb1);
+            bfly_dif(x[0], x[1], t3); bfly_dif(x[2], x[3], t3); bfly_dif(x[4], x[5], t3); bfly_dif(x[6], x[7], t3);
+        } else {
+            bfly_dit(x[0], x[1], t3); bfly_dit(x[2], x[3], t3); bfly_dit(x[4], x[5], t3); bfly_dit(x[6], x[7], t3);
+            bfly_dit(x[0], x[2], t2); bfly_dit(x[1], x[3], wb1); bfly_dit(x[4], x[6], t2); bfly_dit(x[5], x[7], wb1);
+            bfly_dit(x[0], x[4], t1); bfly_dit(x[1], x[5], wa1); bfly_dit(x[2], x[6], wa2); bfly_dit(x[3], x[7], wa3);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) z[base + m * q] = x[m];
+    }
+    __syncthreads();
+}
+
+// one plain radix-2 stage (used for the 1 or 2 stages left over when log2 M is not a multiple of 3)
+template <typename T, bool INVERSE>
+__device__ __forceinline__ void fft_pass2(typename Cx<T>::type *z, int M, int s,
+                                          const typename Cx<T>::type *__restrict__ tw, int tw_n) {
+    typedef typename Cx<T>::type T2;
+    const int half = 1 << s, tstep = tw_n >> (s + 1);
+    for (int t = threadIdx.x; t < (M >> 1); t += blockDim.x) {
+        const int pos = t & (half - 1);
+        const int i0 = ((t >> s) << (s + 1)) + pos;
+        T2 a = z[i0], b = z[i0 + half];
+        if (!INVERSE) bfly_dif(a, b, tw[pos * tstep]); else bfly_dit(a, b, tw[pos * tstep]);
+        z[i0] = a; z[i0 + half] = b;
+    }
+    __syncthreads();
+}
+
 // y = irfft(rfft(x) * transfer) for the n real samples stored in z (z[m] = x[2m] + i x[2m+1]).
 template <typename T>
 __device__ void fft_filter(typename Cx<T>::type *z, int n, const Transfer<T> &tf,
@@ -115,26 +199,19 @@ __device__ void fft_filter(typename Cx<T>::type *z, int n, const Transfer<T> &tf
     typedef typename Cx<T>::type T2;
     const int M = n >> 1;
     const int L = 31 - __clz(M);
+    const int rem = L % 3;
+    // forward: stages L-1 ... 0
+    for (int s = L - 1; s >= rem + 2; s -= 3) fft_pass8<T, false>(z, M, 1 << (s - 2), s - 2, tw, tw_n);
+    for (int s = rem - 1; s >= 0; --s) fft_pass2<T, false>(z, M, s, tw, tw_n);
+    // split into the spectrum of the real sequence, apply the transfer (with the 1/M of the
+    // inverse transform folded in), merge back
     const int nbf = M >> 1;
-    // forward, decimation in frequency: natural order in, bit-reversed order out
-    for (int s = L - 1; s >= 0; --s) {
-        const int half = 1 << s;
-        const int tstep = tw_n >> (s + 1);            // tw index stride = tw_n / (2 half)
-        for (int t = threadIdx.x; t < nbf; t += blockDim.x) {
-            const int pos = t & (half - 1);
-            const int i0 = ((t >> s) << (s + 1)) + pos;
-            const T2 a = z[i0], b = z[i0 + half];
-            z[i0] = cadd(a, b);
-            z[i0 + half] = cmul(csub(a, b), tw[pos * tstep]);
-        }
-        __syncthreads();
-    }
-    // split into the spectrum of the real sequence, apply the transfer, merge back
     const int tstepn = tw_n / n;
+    const T inv = (T)1 / (T)M;
     for (int k = threadIdx.x; k <= nbf; k += blockDim.x) {
         if (k == 0) {
             const T2 z0 = z[0];
-            const T y0 = tf(0) * (z0.x + z0.y), ym = tf(M) * (z0.x - z0.y);
+            const T y0 = inv * tf(0) * (z0.x + z0.y), ym = inv * tf(M) * (z0.x - z0.y);
             z[0] = {(T)0.5 * (y0 + ym), (T)0.5 * (y0 - ym)};
         } else {
             const int pk = __brev((unsigned)k) >> (32 - L);
@@ -146,7 +223,7 @@ __device__ void fft_filter(typename Cx<T>::type *z, int n, const Transfer<T> &tf
             const T2 O = {(T)0.5 * dif.y, (T)-0.5 * dif.x};          // -i/2 (A - Bc)
             const T2 w = tw[k * tstepn];
             const T2 wO = cmul(w, O);
-            const T tk = tf(k), tm = tf(M - k);
+            const T tk = inv * tf(k), tm = inv * tf(M - k);
             const T2 Yk = {tk * (E.x + wO.x), tk * (E.y + wO.y)};
             const T2 Ymc = {tm * (E.x - wO.x), tm * (E.y - wO.y)};   // conj(Y[M-k])
             const T2 Ep = {(T)0.5 * (Yk.x + Ymc.x), (T)0.5 * (Yk.y + Ymc.y)};
@@ -157,26 +234,9 @@ __device__ void fft_filter(typename Cx<T>::type *z, int n, const Transfer<T> &tf
         }
     }
     __syncthreads();
-    // inverse, decimation in time: bit-reversed order in, natural order out
-    for (int s = 0; s < L; ++s) {
-        const int half = 1 << s;
-        const int tstep = tw_n >> (s + 1);
-        for (int t = threadIdx.x; t < nbf; t += blockDim.x) {
-            const int pos = t & (half - 1);
-            const int i0 = ((t >> s) << (s + 1)) + pos;
-            const T2 a = z[i0];
-            const T2 b = cmulc(z[i0 + half], tw[pos * tstep]);
-            z[i0] = cadd(a, b);
-            z[i0 + half] = csub(a, b);
-        }
-        __syncthreads();
-    }
-    const T inv = (T)1 / (T)M;
-    for (int m = threadIdx.x; m < M; m += blockDim.x) {
-        T2 v = z[m];
-        z[m] = {v.x * inv, v.y * inv};
-    }
-    __syncthreads();
+    // inverse: stages 0 ... L-1
+    for (int s = 0; s < rem; ++s) fft_pass2<T, true>(z, M, s, tw, tw_n);
+    for (int s = rem + 2; s <= L - 1; s += 3) fft_pass8<T, true>(z, M, 1 << (s - 2), s - 2, tw, tw_n);
 }
 
 // numpy.polynomial.chebyshev.chebval recurrence (Clenshaw), n coefficients
@@ -194,7 +254,7 @@ __device__ __forceinline__ double cheb_eval(double x, const double *c, int n) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(SMOOTH_THREADS, 1)
 spec_smooth_kernel(SmoothArgs a, int nB) {
     typedef typename Cx<T>::type T2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -218,16 +278,31 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
         const double vrad = r[PV_VRAD], vrot = r[PV_VROT];
         const double inst = 2.355 * r[PV_INSTR];              // genmod.py:74-75
         const T *frow = static_cast<const T *>(a.flux_native) + (size_t)p * npix;
-        for (int i = threadIdx.x; i < npix; i += blockDim.x) fr[i] = frow[i];
+        for (int i0 = threadIdx.x; i0 < npix; i0 += 4 * blockDim.x) {          // 4 loads in flight per thread
+            T v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; v[u] = i < npix ? ld_stream(frow + i) : (T)0; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int i = i0 + u * blockDim.x; if (i < npix) fr[i] = v[u]; }
+        }
         __syncthreads();
 
         // ---- rotational broadening on the full native grid (outwave = None) ----
         if (vrot != 0.0) {
             const double sigma = sqrt(vrot * vrot);
-            for (int k = threadIdx.x; k < n1; k += blockDim.x) {
-                const int i = a.a1_idx[k];
-                const T f = a1f[k];
-                zr[k] = fr[i] + (fr[i + 1] - fr[i]) * f;
+            for (int k0 = threadIdx.x; k0 < n1; k0 += 4 * blockDim.x) {        // n1 is a power of two >= 4 * 512
+                int ii[4]; T ff[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u * blockDim.x;
+                    ii[u] = k < n1 ? ld_stream(a.a1_idx + k) : 0;
+                    ff[u] = k < n1 ? ld_stream(a1f + k) : (T)0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u * blockDim.x;
+                    if (k < n1) zr[k] = fr[ii[u]] + (fr[ii[u] + 1] - fr[ii[u]]) * ff[u];
+                }
             }
             __syncthreads();
             const double step1 = (double)(npix - 1) * a.dlnw / (double)(n1 - 1);
@@ -235,10 +310,19 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
             tf.kind = 1; tf.tab = a.rot_tab;
             tf.coef = 2.0 * M_PI * sigma / ((double)n1 * MS_CKMS * step1);
             fft_filter<T>(z, n1, tf, tw, n1);
-            for (int i = threadIdx.x; i < npix; i += blockDim.x) {
-                const int k = a.a2_idx[i];
-                const T f = a2f[i];
-                fr[i] = zr[k] + (zr[k + 1] - zr[k]) * f;
+            for (int i0 = threadIdx.x; i0 < npix; i0 += 4 * blockDim.x) {
+                int kk[4]; T ff[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * blockDim.x;
+                    kk[u] = i < npix ? ld_stream(a.a2_idx + i) : 0;
+                    ff[u] = i < npix ? ld_stream(a2f + i) : (T)0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < npix) fr[i] = zr[kk[u]] + (zr[kk[u] + 1] - zr[kk[u]]) * ff[u];
+                }
             }
             __syncthreads();
         }
@@ -374,7 +458,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
     }
     auto kern = spec_smooth_kernel<T>;
     MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)((226 * 1024) / (smem + 1024)); if (per_sm < 1) per_sm = 1; if (per_sm > 4) per_sm = 4;
+    const int per_sm = 1;
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
         int rc = spec_mlp_chunk_t<T>(ctx, a.pars + b0 * MS_NPARS, nb, (T *)ctx->scr_hid,
@@ -398,7 +482,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         if (grid > nb) grid = nb;
         {
             KernelTimer timer_(ctx, MS_K_SPEC_SMOOTH, st);
-            kern<<<(unsigned)grid, 512, smem, st>>>(sa, (int)nb);
+            kern<<<(unsigned)grid, SMOOTH_THREADS, smem, st>>>(sa, (int)nb);
         }
         ctx->launches++;
         MS_CUDA(cudaGetLastError());
