@@ -231,6 +231,7 @@ int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d) {
         rt[i] = (float)s;
     }
     if ((rc = upload(&S.rot_tab, rt.data(), rt.size()))) return rc;
+    if (ctx->precision == MS_PREC_TC) return spec_tc_prepare(ctx);
     return MS_OK;
 }
 
@@ -289,7 +290,7 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(S.w0); cudaFree(S.b0); cudaFree(S.w1); cudaFree(S.b1); cudaFree(S.w2); cudaFree(S.b2);
     cudaFree(S.wave); cudaFree(S.a1_idx); cudaFree(S.a2_idx); cudaFree(S.a1_frac); cudaFree(S.a2_frac);
     cudaFree(S.a1_fracd); cudaFree(S.a2_fracd); cudaFree(S.twiddle32); cudaFree(S.twiddle64);
-    cudaFree(S.xms); cudaFree(S.rot_tab); cudaFree(S.tc_pack);
+    cudaFree(S.xms); cudaFree(S.rot_tab); spec_tc_release(ctx);
     cudaFree(ctx->obs_mag); cudaFree(ctx->obs_err2);
     for (StarDev &s : ctx->stars) {
         cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2);

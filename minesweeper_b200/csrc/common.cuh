@@ -172,6 +172,9 @@ struct SpecArgs {
 };
 int launch_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st);
 int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d);
+int spec_tc_prepare(ms_ctx *ctx);           // pack W2 for the tensor-core output GEMM
+void spec_tc_release(ms_ctx *ctx);
+int launch_spec_out_tc(ms_ctx *ctx, const float *h2, int64_t B, float *flux, cudaStream_t st);
 
 
 template <typename T> int ensure_scratch(T **p, size_t *have, size_t need) {

@@ -27,6 +27,7 @@
 // other tile.  The layer-2 k-steps of a tile are issued chunk by chunk as its activations land
 // in TMEM.  Binder: instruction issue of the sigmoid stream (see sigmoid_quad).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
 
@@ -59,91 +60,9 @@ constexpr int SM_BAR = SM_X + 4 * X_BYTES;             // mbarriers
 constexpr int SM_TOTAL = SM_BAR + 256;
 
 // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (0u << 7) | (0u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = make_idesc_f16(128, 128);
 
 enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR_A1 = 10 /* [tile][chunk] */, BAR_N = 18 };
-
-// ---- PTX wrappers --------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(acc) : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d), "r"(a), "l"(bdesc), "r"(IDESC), "r"(acc) : "memory");
-}
-// K-major, no swizzle: start address, LBO (K-chunk stride), SBO (8-row group stride), version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
-}
-
-#define TMEM_LD32(addr, v)                                                                          \
-    asm volatile(                                                                                   \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                   \
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                                    \
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"                   \
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
-          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),        \
-          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),        \
-          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                             \
-        : "r"(addr))
-
-#define TMEM_ST32(addr, v)                                                                          \
-    asm volatile(                                                                                   \
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                             \
-        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                                   \
-        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                          \
-        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), \
-          "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),     \
-          "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),   \
-          "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])    \
-        : "memory")
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -249,9 +168,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;
                         const uint64_t xh = make_desc(xb, 2048, 128), xl = make_desc(xb + X_BYTES, 2048, 128);
                         const uint32_t d1 = tmem + T * 256;
-                        mma_ss(d1, xh, w1h, 0);
-                        mma_ss(d1, xl, w1h, 1);
-                        mma_ss(d1, xh, w1l, 1);
+                        mma_ss(d1, xh, w1h, 0, IDESC);
+                        mma_ss(d1, xl, w1h, 1, IDESC);
+                        mma_ss(d1, xh, w1l, 1, IDESC);
                         tc_commit(bar(BAR_D1 + T));
                         stage[T] = 1;
                     } else {
@@ -265,9 +184,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                             const uint64_t bh = make_desc(wb + OFF_W2H + s * 4096, 2048, 128);
                             const uint64_t bl = make_desc(wb + OFF_W2L + s * 4096, 2048, 128);
                             const uint32_t ah = a1 + 32 * j + 8 * s2, al = ah + 16;
-                            mma_ts(d2, ah, bh, s > 0);
-                            mma_ts(d2, al, bh, 1);
-                            mma_ts(d2, ah, bl, 1);
+                            mma_ts(d2, ah, bh, s > 0, IDESC);
+                            mma_ts(d2, al, bh, 1, IDESC);
+                            mma_ts(d2, ah, bl, 1, IDESC);
                         }
                         if (j == 3) {
                             tc_commit(bar(BAR_D2 + T));

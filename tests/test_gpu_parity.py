@@ -142,7 +142,7 @@ def test_lnprobfn_with_reference_style_prior(g_like_phot):
 
 
 # ---------------------------------------------------------------- kernel (3)
-@pytest.mark.parametrize('prec', PRECS)
+@pytest.mark.parametrize('prec', PRECS + ['tc'])
 def test_spec_model_golden(prec, g_like_spec):
     g = g_like_spec
     eng = _engine(specnet=sub(g, 'spec_'), precision=prec)
@@ -186,7 +186,7 @@ def test_smoothing_kernel_vs_reference_smoothspec(g_smooth):
     f32 = net['b2'].astype(np.float64)
     from oracle import smoothing_port
     ws = w * (1 + float(g_smooth['r_vshift']) / 299792.458)
-    for prec, tol in (('f64', 2e-9), ('f32', 1e-5)):
+    for prec, tol in (('f64', 2e-9), ('f32', 1e-5), ('tc', 1e-5)):
         eng = _engine(specnet=net, precision=prec)
         eng.set_star(0, obs_wave=ow, obs_flux=np.ones_like(ow), obs_eflux=np.ones_like(ow))
         rows = [[5000., 4., 0., 0., float(g_smooth['r_vshift']), 0.0, np.nan, r / 2.355] for r in g_smooth['rsigma']]
@@ -286,3 +286,55 @@ def test_sharded_equals_single_rank(g_like_phot):
             lo, hi = shard_bounds(n, r, size)
             parts.append(L.lnlike_batch(g['theta'][lo:hi])[0].cpu().numpy())
         np.testing.assert_array_equal(np.concatenate(parts), full)
+
+
+def test_lnlike_spec_phot_tc_vs_oracle():
+    """Spectrum + photometry with both MLPs on the tensor cores (spectral output layer and the
+    photometric stack) against the per-point oracle: fluxes 1e-5, lnL bounded by the chi-square
+    sensitivity to 1e-5 model errors."""
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    from oracle.like_port import LikelihoodPort, blaze
+    from oracle.payne_port import PayneSpecPredict
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
+    phot = synth.make_phot_net(h=128, seed=33)
+    spec = synth.make_spec_net(npix=4096, h=300, seed=34, nlines=300)
+    ow = np.linspace(5152.0, 5185.0, 400)
+    _, truth = PayneSpecPredict(nnpath=spec).getspec(Teff=5600.0, logg=4.4, feh=-0.2, afe=0.1, rad_vel=1.2,
+                                                     rot_vel=3.0, inst_R=35000.0 * 2.355, outwave=ow)
+    obs = synth.make_obs_spectrum(spec, n_obs=400, wave_lo=5152.0, wave_hi=5185.0,
+                                  flux=truth * blaze([1.02, 0.03, -0.01, 0.004], ow))
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1', 'pc_2', 'pc_3']
+    on = {'Vrad', 'Vrot', 'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass',
+          'pc_0', 'pc_1', 'pc_2', 'pc_3'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={'Inst_R': 35000.0}, MISTpath=mist, photANNpath=phot,
+                   specANNpath=spec, NNtype='YST1', obs_phot=synth.demo_obs_phot(), obs_wave_fit=obs['obs_wave'],
+                   obs_flux_fit=obs['obs_flux'], obs_eflux_fit=obs['obs_eflux'])
+    runbools = [True, True, True, False, False]
+    rng = np.random.default_rng(9)
+    n = 300
+    base = synth.draw_theta_phot(n, seed=6, frac_out=0.03,
+                                 box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0),
+                                          afe=(-0.2, 0.6), mass=(0.5, 1.25)))
+    th = np.stack([rng.uniform(-5, 5, n), rng.uniform(0, 10, n), base[:, 0], base[:, 1], base[:, 2], base[:, 3],
+                   base[:, 4], base[:, 5], rng.normal(1.0, 0.05, n), rng.normal(0, 0.02, n),
+                   rng.normal(0, 0.01, n), rng.normal(0, 0.005, n)], 1)
+    th[0, 1] = 0.0                                           # Vrot = 0: rotation stage skipped
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', verbose=False)
+    lnl = L.lnlike_batch(th)[0].cpu().numpy()
+    ref = LikelihoodPort(fitargs, fitpars, runbools)
+    for i in range(0, n, 7):
+        want = ref.lnlikefn(list(th[i]))
+        if not np.isfinite(want):
+            assert lnl[i] == want
+            continue
+        sp = [ref.parsdict.get(k, np.nan) for k in ('Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R')]
+        sp += [ref.parsdict[k] for k in L.fitpars_i if 'pc' in k]
+        flux = L.GM.genspec_batch([sp], modpoly=True)[0]
+        _, fref = ref.genspec(sp, outwave=obs['obs_wave'], modpoly=True)
+        np.testing.assert_allclose(flux, fref, rtol=1e-5, atol=1e-5)
+        resid = np.abs(fref - obs['obs_flux']) / obs['obs_eflux'] ** 2
+        tol = np.nansum(resid * 1e-5 * np.abs(fref)) + 1e-3 * abs(want) * 1e-2 + 1e-3
+        assert abs(lnl[i] - want) <= tol, (i, lnl[i], want, tol)
