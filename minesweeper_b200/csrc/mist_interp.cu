@@ -125,9 +125,9 @@ mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int
         if (pars) {
             // the per-point parameter block of likelihood.lnlikefn (likelihood.py:121-160),
             // assembled here so the prediction never makes a round trip through HBM
-            double *o = pars + p * MS_NPARS;
             const double inv = ok ? 1.0 / wsum : 0.0;
             const double inf = ms_inf();
+            double o[MS_NPARS];
             o[PV_TEFF] = ok ? pow(10.0, acc[4] * inv) : inf;             // likelihood.py:121
             o[PV_LOGG] = ok ? acc[7] * inv : inf;
             o[PV_FEH] = ok ? (mistdif ? acc[5] * inv : x[2]) : inf;      // :127-132
@@ -142,6 +142,10 @@ mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int
             o[PV_AGEWGT] = ok ? acc[8] * inv : inf;
 #pragma unroll
             for (int i = 0; i < MS_MAX_PC; ++i) o[PV_PC0 + i] = theta_get(tv, p, MS_P_PC0 + i);
+            // 160-byte row, 16-byte vector stores (each 32-byte sector is touched twice, not four times)
+            double2 *dst = reinterpret_cast<double2 *>(pars + p * MS_NPARS);
+#pragma unroll
+            for (int i = 0; i < MS_NPARS / 2; ++i) dst[i] = make_double2(o[2 * i], o[2 * i + 1]);
             if (chi2) chi2[p] = 0.0;
         }
         if (derived) {

@@ -26,7 +26,8 @@
 #define MS_C_KMS 299792.458        // Payne's Doppler shift (scipy.constants.c / 1000)
 #define MS_ROT_TAB_H (1.0 / 32.0)  // spacing of the rotational-transfer table
 #define MS_ROT_TAB_N 8200
-#define SMOOTH_THREADS 512           // one CTA per SM: leaves ~100 KB of L1 for the twiddle / transfer tables
+// one CTA per SM; 32 warps in f32 (64 registers), 16 in f64 (the f64 kernel needs > 64 registers)
+template <typename T> struct SmoothCfg { static constexpr int THREADS = sizeof(T) == 4 ? 1024 : 512; };
 
 namespace {
 
@@ -254,14 +255,14 @@ __device__ __forceinline__ double cheb_eval(double x, const double *c, int n) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(SMOOTH_THREADS, 1)
+__global__ void __launch_bounds__(SmoothCfg<T>::THREADS, 1)
 spec_smooth_kernel(SmoothArgs a, int nB) {
     typedef typename Cx<T>::type T2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T2 *z = reinterpret_cast<T2 *>(smem_raw);                 // n1/2 complex = n1 reals
     T *zr = reinterpret_cast<T *>(smem_raw);
     T *fr = zr + a.n1;                                        // npix
-    __shared__ double red[16];
+    __shared__ double red[32];
     const T *a1f = static_cast<const T *>(a.a1_frac), *a2f = static_cast<const T *>(a.a2_frac);
     const T2 *tw = static_cast<const T2 *>(a.twiddle);
     const int npix = a.npix, n1 = a.n1, nobs = a.n_obs;
@@ -484,7 +485,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         if (grid > nb) grid = nb;
         {
             KernelTimer timer_(ctx, MS_K_SPEC_SMOOTH, st);
-            kern<<<(unsigned)grid, SMOOTH_THREADS, smem, st>>>(sa, (int)nb);
+            kern<<<(unsigned)grid, SmoothCfg<T>::THREADS, smem, st>>>(sa, (int)nb);
         }
         ctx->launches++;
         MS_CUDA(cudaGetLastError());
