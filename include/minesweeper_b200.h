@@ -157,6 +157,36 @@ int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const double *theta
                          int64_t B, int ndim, const int32_t *colmap, const double *fixed,
                          double *lnL_host, double *derived_host);
 
+/* ---- prior side -------------------------------------------
+ * ms_prior_transform   prior.priortrans                 prior.py:150-385
+ * ms_lnprob_batch      prior.lnpriorfn + fitstar.lnprobfn   prior.py:387-639, fitstar.py:715-727 */
+enum { MS_PRIOR_UNIFORM = 0,     /* p = lo, hi                        pv_uniform / default range */
+       MS_PRIOR_GAUSSIAN,        /* p = loc, scale                    pv_gaussian                */
+       MS_PRIOR_TGAUSSIAN,       /* p = lo, hi, loc, scale            pv_tgaussian, blaze coeffs */
+       MS_PRIOR_EXP,             /* p = loc, scale                    pv_exp                     */
+       MS_PRIOR_LOGUNIFORM };    /* p = a, b                          pv_loguniform              */
+typedef struct { int32_t kind; int32_t pad_; double p[4]; } ms_prior_col;
+
+/* value a prior term applies to: an MS_P_* id (sampled / fixed / isochrone-predicted label) or */
+enum { MS_V_LOGAGE = MS_NPARAM, MS_V_AGE, MS_V_PARALLAX, MS_V_END };
+enum { MS_TERM_UNIFORM = 0,      /* p = lo, hi: -inf outside */
+       MS_TERM_GAUSSIAN,         /* p = mu, sigma            */
+       MS_TERM_TGAUSSIAN,        /* p = lo, hi, mu, sigma (MIST family: bounds and Gaussian) */
+       MS_TERM_TGAUSSIAN_BOUNDS  /* p = lo, hi (spec / phot families apply the bounds only)  */ };
+typedef struct { int32_t value_id; int32_t kind; double p[4]; } ms_prior_term;
+#define MS_MAX_PRIOR_TERMS 32
+
+/* u[B][ndim] in the unit cube -> theta[B][ndim] (device pointers); cols[ndim] host. */
+int ms_prior_transform(ms_ctx *ctx, const double *u, int64_t B, int ndim, const ms_prior_col *cols,
+                       double *theta, void *stream);
+/* out[p] = lnL[p] + lnprior(theta_p, derived_p) with the -inf short circuits of lnprobfn; lnL may
+ * be NULL (then out = lnprior).  derived[B][13] from ms_lnlike_batch (NULL without isochrones);
+ * imf != 0 adds the Kroupa IMF prior on initial_Mass. */
+int ms_lnprob_batch(ms_ctx *ctx, const ms_flags *flags, const double *theta, int64_t B, int ndim,
+                    const int32_t *colmap, const double *fixed, const double *derived,
+                    const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
+                    void *stream);
+
 /* Number of kernel launches issued by this ctx so far (bench bookkeeping). */
 int64_t ms_launch_count(const ms_ctx *ctx);
 

@@ -67,6 +67,19 @@ class Flags(C.Structure):
                 ('ageweight', C.c_int32), ('mistdif', C.c_int32), ('n_pc', C.c_int32)]
 
 
+class PriorCol(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('pad_', C.c_int32), ('p', C.c_double * 4)]
+
+
+class PriorTerm(C.Structure):
+    _fields_ = [('value_id', C.c_int32), ('kind', C.c_int32), ('p', C.c_double * 4)]
+
+
+PRIOR_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'exp': 3, 'loguniform': 4}
+TERM_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'tgaussian_bounds': 3}
+MS_V_LOGAGE, MS_V_AGE, MS_V_PARALLAX = MS_NPARAM, MS_NPARAM + 1, MS_NPARAM + 2
+MS_MAX_PRIOR_TERMS = 32
+
 # every exported symbol of include/minesweeper_b200.h with its prototype
 PROTOTYPES = {
     'ms_version': (C.c_char_p, []),
@@ -86,6 +99,11 @@ PROTOTYPES = {
                                   C.c_void_p]),
     'ms_lnlike_batch_host': (C.c_int, [C.c_void_p, C.POINTER(Flags), c_dp, C.c_int64, C.c_int, c_ip,
                                        c_dp, c_dp, c_dp]),
+    'ms_prior_transform': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.POINTER(PriorCol),
+                                     C.c_void_p, C.c_void_p]),
+    'ms_lnprob_batch': (C.c_int, [C.c_void_p, C.POINTER(Flags), C.c_void_p, C.c_int64, C.c_int, c_ip, c_dp,
+                                  C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
     'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_read': (C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int64)]),

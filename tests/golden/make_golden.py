@@ -190,8 +190,55 @@ def gen_like(spec_on, name, n):
         name, n, np.isfinite(lnl).sum(), np.nanmin(lnl[np.isfinite(lnl)]), np.nanmax(lnl[np.isfinite(lnl)])))
 
 
+def gen_prior():
+    """u -> theta through the reference's prior.priortrans, and lnpriorfn on the parsdict the
+    reference's likelihood leaves behind, for a priordict that exercises every supported kind."""
+    import json
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10, frac_missing=0.04, frac_trunc=0.15)
+    refshim.register_h5('golden://mist', synth.mist_rows(mist))
+    phot = synth.make_phot_net(h=32, seed=11)
+    priordict = {'EEP': {'pv_uniform': [202, 261]},
+                 'initial_Mass': {'pv_tgaussian': [0.5, 1.25, 1.0, 0.2]},
+                 'initial_[Fe/H]': {'pv_gaussian': [-0.3, 0.4]},
+                 'initial_[a/Fe]': {'pv_uniform': [0.6, -0.2], 'gaussian': [0.1, 0.2]},
+                 'Dist': {'pv_loguniform': [1.0, 100.0]},
+                 'Av': {'pv_exp': [0.0, 0.03], 'uniform': [0.0, 0.15]},
+                 'Age': {'tgaussian': [0.5, 14.0, 5.0, 3.0]},
+                 'log(Age)': {'uniform': [8.0, 10.15]},
+                 'Parallax': {'gaussian': [70.7371, 30.0]},
+                 'IMF': {'IMF_type': 'Kroupa'}}
+    inputdict = dict(phot=synth.demo_obs_phot(), photANNpath=phot, MISTpath='golden://mist',
+                     isochrone_prior=True, ageweight=True, priordict=priordict)
+    fs = refshim.build_fit(inputdict)
+    L, P = fs.likeobj, fs.priorobj
+    rng = np.random.default_rng(321)
+    n = 500
+    u = rng.random((n, L.ndim))
+    u[:5] = np.clip(u[:5], 1e-9, 1 - 1e-9)
+    u[0, :] = 1e-12; u[1, :] = 1 - 1e-12
+    theta = np.array([P.priortrans(list(r)) for r in u], dtype=np.float64)
+    lnl = np.empty(n); lnp = np.empty(n); lnprob = np.empty(n)
+    from minesweeper import fitstar
+    for i, th in enumerate(theta):
+        lnl[i] = L.lnlikefn(list(th))
+        lnp[i] = P.lnpriorfn(dict(L.parsdict)) if np.isfinite(lnl[i]) else np.nan
+        lnprob[i] = fitstar.lnprobfn(list(th), L, P)
+    out = dict(u=u, theta=theta, lnl=lnl, lnprior=lnp, lnprob=lnprob, priordict=np.array(json.dumps(priordict)),
+               fitpars_i=np.array(L.fitpars_i), fitpars_all=np.array(fs.fitpars),
+               fitpars_bool=np.array([fs.fitpars_bool[k] for k in fs.fitpars]),
+               runbools=np.array([fs.spec_bool, fs.phot_bool, fs.modpoly_bool, fs.photscale_bool, fs.flux_bool]),
+               obs_phot_bands=np.array(list(fs.fitargs['obs_phot'].keys())),
+               obs_phot=np.array([fs.fitargs['obs_phot'][b] for b in fs.fitargs['obs_phot'].keys()]),
+               fixed_keys=np.array(list(fs.fitargs['fixedpars'].keys()), dtype='<U16'),
+               fixed_vals=np.array([fs.fitargs['fixedpars'][k] for k in fs.fitargs['fixedpars']], dtype=np.float64))
+    out.update(pack('mist_', mist)); out.update(pack('phot_', phot))
+    np.savez_compressed(os.path.join(HERE, 'prior.npz'), **out)
+    print('prior.npz: %d points, %d finite lnl, %d finite lnprob' % (n, np.isfinite(lnl).sum(), np.isfinite(lnprob).sum()))
+
+
 if __name__ == '__main__':
     gen_mist()
     gen_smoothing()
     gen_like(False, 'like_phot.npz', 400)
     gen_like(True, 'like_spec.npz', 120)
+    gen_prior()

@@ -1,0 +1,91 @@
+"""Batched prior transform / ln-prior against golden vectors written by the reference's own
+``prior`` class (tests/golden/prior.npz, make_golden.gen_prior)."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, sub
+
+
+@pytest.fixture(scope='module')
+def g_prior():
+    return load_golden('prior.npz')
+
+
+def _setup(g):
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=sub(g, 'mist_'), photANNpath=sub(g, 'phot_'),
+                   obs_phot={str(b): [float(m), float(e)] for b, (m, e) in zip(g['obs_phot_bands'], g['obs_phot'])})
+    names = [str(n) for n in g['fitpars_all']]
+    fitpars = [names, {n: bool(b) for n, b in zip(names, g['fitpars_bool'])}]
+    runbools = [bool(b) for b in g['runbools']]
+    return fitargs, fitpars, runbools, json.loads(str(g['priordict']))
+
+
+@pytest.mark.gpu
+def test_prior_transform_and_lnprob_golden(g_prior):
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200 import fitstar
+    g = g_prior
+    fitargs, fitpars, runbools, priordict = _setup(g)
+    L = likelihood(fitargs, fitpars, runbools, precision='f64', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    assert P.fitpars_i == [str(s) for s in g['fitpars_i']]
+    # prior transform: uniform (reversed bounds), gaussian, truncated gaussian, exponential, log-uniform
+    theta = P.priortrans_batch(g['u'])
+    np.testing.assert_allclose(theta.cpu().numpy(), g['theta'], rtol=1e-10, atol=1e-12)
+    # lnprob = lnlike + lnprior with the -inf short circuits (fitstar.py:715-727)
+    lnl, der, _ = L.lnlike_batch(g['theta'])
+    lnprob = P.lnprob_batch(g['theta'], lnl, der).cpu().numpy()
+    assert np.array_equal(np.isneginf(lnprob), np.isneginf(g['lnprob']))
+    fin = np.isfinite(g['lnprob'])
+    assert fin.sum() > 300 and (~fin).sum() > 30
+    np.testing.assert_allclose(lnprob[fin], g['lnprob'][fin], rtol=1e-12, atol=1e-6)
+    # ln-prior alone
+    lnp = P.lnprob_batch(g['theta'], None, der).cpu().numpy()
+    ok = np.isfinite(g['lnl'])
+    ref = g['lnprior'][ok]
+    np.testing.assert_allclose(np.where(np.isfinite(lnp[ok]), lnp[ok], -np.inf),
+                               np.where(np.isfinite(ref), ref, -np.inf), rtol=1e-12, atol=1e-9)
+    # scalar API used by the unmodified lnprobfn
+    for i in (3, 50, 200):
+        th = P.priortrans(list(g['u'][i]))
+        np.testing.assert_allclose(th, g['theta'][i], rtol=1e-10, atol=1e-12)
+        v = fitstar.lnprobfn(list(g['theta'][i]), L, P)
+        if np.isfinite(g['lnprob'][i]):
+            assert abs(v - g['lnprob'][i]) <= 1e-6 + 1e-12 * abs(g['lnprob'][i])
+        else:
+            assert v == g['lnprob'][i]
+
+
+def test_priordict_translation_rules():
+    """CPU: column / term tables follow the reference's precedence (no GPU call)."""
+    from minesweeper_b200 import prior as P
+    from minesweeper_b200 import _lib
+
+    class FakeEngine(object):
+        pass
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1']
+    on = {'Vrad', 'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    pd = {'EEP': {'pv_uniform': [300, 200], 'pv_gaussian': [250, 5]},      # uniform wins, bounds sorted
+          'Dist': {'pv_gaussian': [10.0, 1.0], 'pv_loguniform': [1, 100]},
+          'Age': {'uniform': [1, 14]}, 'Parallax': {'gaussian': [70.0, 0.1]}, 'Vrad': {'tgaussian': [-5, 5, 0, 1]},
+          'blaze_coeff': [[1.0, 0.5], [0.0, 0.1]], 'IMF': {'IMF_type': 'Kroupa'}}
+    p = P.prior(dict(fixedpars={'Inst_R': 35000.0}, ageweight=True, mistdif=True), pd, fitpars,
+                [True, True, True, False, False], engine=FakeEngine())
+    cols = {n: p._cols[i] for i, n in enumerate(p.fitpars_i)}
+    assert cols['EEP'].kind == _lib.PRIOR_KINDS['uniform'] and list(cols['EEP'].p)[:2] == [200.0, 300.0]
+    assert cols['Dist'].kind == _lib.PRIOR_KINDS['gaussian']
+    assert cols['Av'].kind == _lib.PRIOR_KINDS['uniform'] and list(cols['Av'].p)[:2] == [0.0, 5.0]      # default range
+    assert cols['pc_1'].kind == _lib.PRIOR_KINDS['tgaussian'] and list(cols['pc_1'].p) == [-0.5, 0.5, 0.0, 0.1]
+    kinds = sorted((t.value_id, t.kind) for t in p._terms_c[:p._nterms])
+    assert (_lib.MS_V_AGE, _lib.TERM_KINDS['uniform']) in kinds
+    assert (_lib.MS_V_PARALLAX, _lib.TERM_KINDS['gaussian']) in kinds
+    assert (_lib.param_id('Vrad'), _lib.TERM_KINDS['tgaussian_bounds']) in kinds       # spec family: bounds only
+    assert p.imf_bool
+    with pytest.raises(NotImplementedError):
+        P.prior(dict(fixedpars={}), {'GAL': {'lb_coords': [0, 0]}}, fitpars, [False, True, False, False, False],
+                engine=FakeEngine())
