@@ -126,6 +126,11 @@ int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, const double 
                 int nb, const double *obs_wave, const double *obs_flux,
                 const double *obs_eflux, int n_obs);
 
+/* Photometry of many stars at once (catalog mode): obs_mag / obs_err[nstars][nb] host arrays go to
+ * slots first_slot .. first_slot + nstars - 1. */
+int ms_set_stars_phot(ms_ctx *ctx, int first_slot, int nstars, const double *obs_mag, const double *obs_err,
+                      int nb);
+
 /* theta4[B][4] = (EEP, initial_Mass, initial_[Fe/H], initial_[a/Fe]) device f64.
  * brackets[B][4] int32 = digitize-1 per axis (may be NULL);
  * derived[B][13] f64 (may be NULL); ok[B] uint8 (may be NULL). */
@@ -186,6 +191,12 @@ int ms_lnprob_batch(ms_ctx *ctx, const ms_flags *flags, const double *theta, int
                     const int32_t *colmap, const double *fixed, const double *derived,
                     const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
                     void *stream);
+/* Same, with a per-star Gaussian parallax prior (catalog mode): star_slot[B] device int32 and
+ * star_plx[nslots][2] = (parallax, error) in mas, device f64; adds -0.5 ((1000/Dist - plx)/err)^2. */
+int ms_lnprob_batch_stars(ms_ctx *ctx, const ms_flags *flags, const double *theta, int64_t B, int ndim,
+                          const int32_t *colmap, const double *fixed, const double *derived,
+                          const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
+                          const int32_t *star_slot, const double *star_plx, void *stream);
 
 /* Number of kernel launches issued by this ctx so far (bench bookkeeping). */
 int64_t ms_launch_count(const ms_ctx *ctx);

@@ -104,6 +104,10 @@ PROTOTYPES = {
     'ms_lnprob_batch': (C.c_int, [C.c_void_p, C.POINTER(Flags), C.c_void_p, C.c_int64, C.c_int, c_ip, c_dp,
                                   C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
+    'ms_lnprob_batch_stars': (C.c_int, [C.c_void_p, C.POINTER(Flags), C.c_void_p, C.c_int64, C.c_int, c_ip, c_dp,
+                                        C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ms_set_stars_phot': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
     'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_read': (C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int64)]),

@@ -391,6 +391,25 @@ extern "C" int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, co
     return MS_OK;
 }
 
+extern "C" int ms_set_stars_phot(ms_ctx *ctx, int first_slot, int nstars, const double *obs_mag,
+                                 const double *obs_err, int nb) {
+    if (!ctx || first_slot < 0 || nstars < 1 || !obs_mag || !obs_err || nb != ctx->phot.nb) {
+        ms_set_error("bad arguments (nb must equal the net's band count)");
+        return MS_EINVAL;
+    }
+    // grow the table through the single-star path, then overwrite the block in two copies
+    int rc = ms_set_star(ctx, first_slot + nstars - 1, obs_mag + (size_t)(nstars - 1) * nb,
+                         obs_err + (size_t)(nstars - 1) * nb, nb, nullptr, nullptr, nullptr, 0);
+    if (rc) return rc;
+    if ((int)ctx->stars.size() < first_slot + nstars) ctx->stars.resize(first_slot + nstars);
+    for (int i = 0; i < nstars; ++i) ctx->stars[first_slot + i].set = true;
+    std::vector<double> e2((size_t)nstars * nb);
+    for (size_t i = 0; i < e2.size(); ++i) e2[i] = obs_err[i] * obs_err[i];
+    MS_CUDA(cudaMemcpy(ctx->obs_mag + (size_t)first_slot * nb, obs_mag, e2.size() * sizeof(double), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemcpy(ctx->obs_err2 + (size_t)first_slot * nb, e2.data(), e2.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return MS_OK;
+}
+
 static void identity_view(ThetaView &tv, const double *theta, int ld) {
     tv.theta = theta; tv.ld = ld;
     for (int i = 0; i < MS_NPARAM; ++i) { tv.col[i] = -1; tv.fixed[i] = std::numeric_limits<double>::quiet_NaN(); }

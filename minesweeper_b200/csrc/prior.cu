@@ -64,6 +64,7 @@ struct LnPriorArgs {
     const double *lnL;              // [B] or nullptr (then out = lnprior)
     double *out;
     int mistdif, nterms, imf;
+    const int32_t *star_slot; const double *star_plx;   // per-star Gaussian parallax prior or nullptr
     ms_prior_term term[MS_MAX_PRIOR_TERMS];
 };
 
@@ -105,6 +106,11 @@ __global__ void lnprior_kernel(LnPriorArgs a, int64_t B) {
             double nlo = pow(mb, 1.0 - al) / (ah - 1.0);
             double nhi = pow(0.08, 1.0 - al) / (al - 1.0) - pow(mb, 1.0 - al) / (al - 1.0);
             lp += v - log(nlo + nhi);
+        }
+        if (a.star_plx) {
+            const double *pe = a.star_plx + 2 * (int64_t)(a.star_slot ? a.star_slot[p] : 0);
+            const double d = 1000.0 / theta_get(a.tv, p, MS_P_DIST) - pe[0];
+            lp += -0.5 * ((d * d) / (pe[1] * pe[1]));
         }
         bool dead = false;
         for (int i = 0; i < a.nterms && !dead; ++i) {
@@ -157,6 +163,14 @@ extern "C" int ms_lnprob_batch(ms_ctx *ctx, const ms_flags *flags, const double 
                                const int32_t *colmap, const double *fixed, const double *derived,
                                const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
                                void *stream) {
+    return ms_lnprob_batch_stars(ctx, flags, theta, B, ndim, colmap, fixed, derived, terms, nterms, imf, lnL, out,
+                                 nullptr, nullptr, stream);
+}
+
+extern "C" int ms_lnprob_batch_stars(ms_ctx *ctx, const ms_flags *flags, const double *theta, int64_t B, int ndim,
+                                     const int32_t *colmap, const double *fixed, const double *derived,
+                                     const ms_prior_term *terms, int nterms, int imf, const double *lnL,
+                                     double *out, const int32_t *star_slot, const double *star_plx, void *stream) {
     if (!ctx || !flags || !theta || !colmap || !out || B < 0 || ndim < 1 || ndim > MS_NPARAM || nterms < 0 ||
         nterms > MS_MAX_PRIOR_TERMS || (nterms && !terms)) { ms_set_error("bad arguments"); return MS_EINVAL; }
     if (B == 0) return MS_OK;
@@ -169,6 +183,7 @@ extern "C" int ms_lnprob_batch(ms_ctx *ctx, const ms_flags *flags, const double 
         a.tv.col[colmap[c]] = c;
     }
     a.derived = derived; a.lnL = lnL; a.out = out; a.mistdif = flags->mistdif; a.nterms = nterms; a.imf = imf;
+    a.star_slot = star_slot; a.star_plx = star_plx;
     for (int i = 0; i < nterms; ++i) {
         if (terms[i].value_id < 0 || terms[i].value_id >= MS_V_END || terms[i].kind < 0 || terms[i].kind > MS_TERM_TGAUSSIAN_BOUNDS) {
             ms_set_error("prior term %d is malformed", i);

@@ -137,6 +137,11 @@ class Engine(object):
                                    _dp(f) if n_obs else None, _dp(e) if n_obs else None, n_obs))
         self.n_obs[int(slot)] = n_obs
 
+    def set_stars_phot(self, obs_mag, obs_err, first_slot=0):
+        """Catalog mode: obs_mag / obs_err[nstars, nb] (NaN = unobserved) into consecutive slots."""
+        m, e = _f64(obs_mag), _f64(obs_err)
+        check(self.lib.ms_set_stars_phot(self._ctx, int(first_slot), m.shape[0], _dp(m), _dp(e), m.shape[1]))
+
     # -- helpers -------------------------------------------------------------
     def _dev(self, a):
         t = torch.as_tensor(a, dtype=torch.float64)

@@ -147,9 +147,11 @@ class prior(object):
                                              theta.data_ptr(), eng._stream()))
         return theta
 
-    def lnprob_batch(self, theta, lnl=None, derived=None, out=None):
+    def lnprob_batch(self, theta, lnl=None, derived=None, out=None, star_slot=None, star_plx=None):
         """lnL + lnprior with lnprobfn's -inf short circuits (fitstar.py:715-727); with
-        ``lnl=None`` the ln-prior alone.  ``derived`` is the [B,13] block of lnlike_batch."""
+        ``lnl=None`` the ln-prior alone.  ``derived`` is the [B,13] block of lnlike_batch.
+        Catalog mode: ``star_slot[B]`` (int32 GPU tensor) and ``star_plx[nslots,2]`` (f64 GPU tensor)
+        add a per-star Gaussian parallax prior."""
         eng = self.engine
         th = eng._dev(theta)
         B = th.shape[0]
@@ -158,12 +160,13 @@ class prior(object):
         if self.iso_bool and derived is None:
             raise ValueError('isochrone fits need the derived block for the ln-prior')
         with torch.cuda.device(eng.device):
-            check(eng.lib.ms_lnprob_batch(
+            check(eng.lib.ms_lnprob_batch_stars(
                 eng._ctx, C.byref(self._flags), th.data_ptr(), B, self.ndim,
                 self._colmap.ctypes.data_as(_lib.c_ip), self._fixed.ctypes.data_as(_lib.c_dp),
                 derived.data_ptr() if derived is not None else None, self._terms_c, self._nterms,
                 int(self.imf_bool), lnl.data_ptr() if lnl is not None else None, out.data_ptr(),
-                eng._stream()))
+                star_slot.data_ptr() if star_slot is not None else None,
+                star_plx.data_ptr() if star_plx is not None else None, eng._stream()))
         return out
 
     # ---- the reference's scalar API ---------------------------------------------------------

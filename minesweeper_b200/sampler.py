@@ -1,0 +1,215 @@
+"""Lock-step batched static nested sampling.
+
+The reference hands ``lnprobfn`` / ``priortrans`` to ``dynesty.NestedSampler`` with the ``rwalk``
+proposal and evaluates one point per call (reference fitstar.py:337-369; settings in
+demo/etc/samplerinfo.dat: static, rwalk, 150 live points, walks 5, dlogz 0.01).  dynesty is not
+available here and cannot feed a GPU one point at a time, so this module runs the same kind of
+sampler for MANY stars at once: every star has its own live set, all stars advance one
+nested-sampling iteration together, and each random-walk step is one batched call of the CUDA
+prior-transform / likelihood / ln-prior kernels over all still-active stars.
+
+Algorithm per star (standard static nested sampling, Skilling 2006, with dynesty-style rwalk):
+  * live points uniform in the unit cube, lnprob = lnL + lnprior from the kernels;
+  * each iteration removes the worst live point (ln X_i = -i / nlive), accumulates ln Z and the
+    information H, and replaces it by the end point of a constrained random walk started from
+    another live point: ``walks`` Gaussian steps in the unit cube, scaled by the live-point
+    spread, reflected at the walls, accepted iff lnprob > lnprob_worst; the step scale adapts to
+    a 0.5 acceptance rate (dynesty's update rule); walks that never moved are extended;
+  * stop when the remaining evidence ln(1 + L_max X / Z) < dlogz; then add the live points.
+The bookkeeping is torch tensor code on the GPU (no host round trip per iteration); all model
+arithmetic is in libmsb200's kernels.  Output: per-star ln Z, its error sqrt(H / nlive), call
+counts, posterior mean / std of theta and of the derived MIST block, and (optionally) the dead
+points with ln weights in the column layout of the reference's samples file
+(fitstar.py:235-242, 392-425).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class BatchedNestedSampler(object):
+    def __init__(self, likeobj, priorobj, nstars=1, nlive=150, walks=5, dlogz=0.01, maxiter=100000,
+                 seed=0, star_plx=None, store_samples=False, max_extend=20):
+        self.L, self.P = likeobj, priorobj
+        self.eng = likeobj.engine
+        self.dev = self.eng.device
+        self.S, self.K, self.walks = int(nstars), int(nlive), int(walks)
+        self.ndim = likeobj.ndim
+        self.dlogz, self.maxiter, self.max_extend = float(dlogz), int(maxiter), int(max_extend)
+        self.gen = torch.Generator(device=self.dev)
+        self.gen.manual_seed(int(seed))
+        self.per_star = self.S > 1 or star_plx is not None
+        self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
+        self.store = bool(store_samples)
+        self.ncall = torch.zeros(self.S, dtype=torch.int64, device=self.dev)
+
+    # one batched evaluation of lnprob for u[N, ndim] belonging to stars slot[N]
+    def _lnprob(self, u, slot):
+        theta = self.P.priortrans_batch(u)
+        slots = slot.to(torch.int32).contiguous() if self.per_star else None
+        lnl, der, _ = self.eng.lnlike_batch(theta, self.L._colmap, self.L._fixed, self.L._flags,
+                                            star_slot=slots if self.S > 1 else None,
+                                            want_derived=self.L.iso_bool)
+        out = self.P.lnprob_batch(theta, lnl, der, star_slot=slots if self.star_plx is not None else None,
+                                  star_plx=self.star_plx)
+        self.ncall.index_add_(0, slot, torch.ones_like(slot))
+        return out, theta, der
+
+    def _rand(self, *shape):
+        return torch.rand(*shape, generator=self.gen, device=self.dev, dtype=torch.float64)
+
+    def _randn(self, *shape):
+        return torch.randn(*shape, generator=self.gen, device=self.dev, dtype=torch.float64)
+
+    def run(self, verbose=False):
+        S, K, nd, dev = self.S, self.K, self.ndim, self.dev
+        f64 = torch.float64
+        star = torch.arange(S, device=dev)
+        # ---- initial live points (redrawn until lnprob is finite) ----
+        U = self._rand(S, K, nd)
+        slot = star.repeat_interleave(K)
+        lp, th, der = self._lnprob(U.reshape(-1, nd), slot)
+        nder = der.shape[1] if der is not None else 0
+        for _ in range(50):
+            bad = ~torch.isfinite(lp)
+            if not bool(bad.any()):
+                break
+            idx = bad.nonzero(as_tuple=True)[0]
+            un = self._rand(len(idx), nd)
+            lpn, thn, dern = self._lnprob(un, slot[idx])
+            U.reshape(-1, nd)[idx] = un
+            lp[idx], th[idx] = lpn, thn
+            if der is not None:
+                der[idx] = dern
+        if bool((~torch.isfinite(lp)).any()):
+            raise RuntimeError('could not draw live points with finite lnprob from the prior')
+        LP = lp.reshape(S, K)
+        TH = th.reshape(S, K, nd)
+        DER = der.reshape(S, K, nder) if der is not None else None
+        ncol = nd + nder
+        logz = torch.full((S,), -float('inf'), dtype=f64, device=dev)
+        hacc = torch.zeros(S, dtype=f64, device=dev)            # sum exp(logwt - logz) * lnL, for H
+        wsum = torch.zeros(S, ncol, dtype=f64, device=dev)      # posterior moments with weights exp(logwt - wmax)
+        wsq = torch.zeros(S, ncol, dtype=f64, device=dev)
+        wmax = torch.full((S,), -float('inf'), dtype=f64, device=dev)
+        wtot = torch.zeros(S, dtype=f64, device=dev)
+        scale = torch.ones(S, dtype=f64, device=dev)
+        active = torch.ones(S, dtype=torch.bool, device=dev)
+        niter = torch.zeros(S, dtype=torch.int64, device=dev)
+        dead = [] if self.store else None
+        lnK = float(np.log(K))
+        log_shrink = float(np.log1p(-np.exp(-1.0 / K)))        # ln(1 - e^{-1/K}): shell width factor
+
+        def accumulate(mask, lnl, logwt, row):
+            """ln Z, H and posterior-moment updates for the stars in ``mask``."""
+            nonlocal logz, hacc, wsum, wsq, wmax, wtot
+            lz_new = torch.logaddexp(logz, logwt)
+            # H bookkeeping: keep S1 = sum w_i lnL_i / Z in rescaled form
+            hacc = torch.where(mask, hacc * torch.exp(logz - lz_new) + torch.exp(logwt - lz_new) * lnl, hacc)
+            logz = torch.where(mask, lz_new, logz)
+            m_new = torch.where(mask, torch.maximum(wmax, logwt), wmax)
+            r_old = torch.exp(wmax - m_new)
+            r_old = torch.where(torch.isfinite(r_old), r_old, torch.zeros_like(r_old))
+            w = torch.where(mask, torch.exp(logwt - m_new), torch.zeros_like(logwt))
+            wsum = wsum * r_old[:, None] + w[:, None] * row
+            wsq = wsq * r_old[:, None] + w[:, None] * row * row
+            wtot = wtot * r_old + w
+            wmax = m_new
+
+        it = 0
+        while bool(active.any()) and it < self.maxiter:
+            it += 1
+            act = active.nonzero(as_tuple=True)[0]
+            A = len(act)
+            # ---- worst live point of every active star ----
+            lmin, w = LP[act].min(dim=1)
+            logvol = -(niter[act].to(f64) + 1.0) / K
+            logwt_full = torch.full((S,), -float('inf'), dtype=f64, device=dev)
+            logwt_full[act] = lmin + (logvol + 1.0 / K + log_shrink)       # lnL_i + ln(X_{i-1} - X_i)
+            row = torch.zeros(S, ncol, dtype=f64, device=dev)
+            rowA = TH[act, w] if DER is None else torch.cat([TH[act, w], DER[act, w]], dim=1)
+            row[act] = torch.where(torch.isfinite(rowA), rowA, torch.zeros_like(rowA))
+            lfull = torch.zeros(S, dtype=f64, device=dev)
+            lfull[act] = lmin
+            accumulate(active, lfull, logwt_full, row)
+            if self.store:
+                dead.append((act.clone(), rowA.clone(), lmin.clone(), logvol.clone(), logwt_full[act].clone()))
+            # ---- constrained random walk from another live point ----
+            j = torch.randint(0, K - 1, (A,), generator=self.gen, device=dev)
+            j = j + (j >= w).to(j.dtype)                                   # any live point but the worst
+            ucur = U[act, j].clone()
+            lcur = LP[act, j].clone()
+            thcur = TH[act, j].clone()
+            dcur = DER[act, j].clone() if DER is not None else None
+            sig = U[act].std(dim=1).clamp_min(1e-12) * scale[act, None]
+            nacc = torch.zeros(A, dtype=torch.int64, device=dev)
+            steps = 0
+            while True:
+                for _ in range(self.walks):
+                    prop = ucur + sig * self._randn(A, nd)
+                    prop = torch.remainder(prop, 2.0)                      # reflect into [0, 1]
+                    prop = torch.where(prop > 1.0, 2.0 - prop, prop)
+                    lpn, thn, dern = self._lnprob(prop, act)
+                    ok = lpn > lmin
+                    ucur = torch.where(ok[:, None], prop, ucur)
+                    lcur = torch.where(ok, lpn, lcur)
+                    thcur = torch.where(ok[:, None], thn, thcur)
+                    if dcur is not None:
+                        dcur = torch.where(ok[:, None], dern, dcur)
+                    nacc += ok
+                steps += self.walks
+                stuck = nacc == 0
+                if not bool(stuck.any()) or steps >= self.walks * self.max_extend:
+                    break
+                sig = torch.where(stuck[:, None], sig * 0.5, sig)          # shrink and keep walking
+            # dynesty's rwalk scale update towards 50 % acceptance
+            facc = nacc.to(f64) / steps
+            scale[act] = (scale[act] * torch.exp((facc - 0.5) / nd / 0.5)).clamp(1e-4, 10.0)
+            U[act, w], LP[act, w], TH[act, w] = ucur, lcur, thcur
+            if DER is not None:
+                DER[act, w] = dcur
+            niter[act] += 1
+            # ---- stopping rule: remaining evidence ----
+            lmax = LP[act].max(dim=1).values
+            dl = torch.logaddexp(logz[act], lmax + logvol) - logz[act]
+            done = dl < self.dlogz
+            active[act[done]] = False
+            if verbose and it % 200 == 0:
+                print('iter %d: %d / %d stars active, median dlogz %.3g' % (it, int(active.sum()), S, float(dl.median())))
+
+        # ---- final live points: each carries X_final / K ----
+        logvol_f = -(niter.to(f64)) / K - lnK
+        allmask = torch.ones(S, dtype=torch.bool, device=dev)
+        for k in range(K):
+            rowk = TH[:, k] if DER is None else torch.cat([TH[:, k], DER[:, k]], dim=1)
+            rowk = torch.where(torch.isfinite(rowk), rowk, torch.zeros_like(rowk))
+            accumulate(allmask, LP[:, k], LP[:, k] + logvol_f, rowk)
+        mean = wsum / wtot[:, None]
+        var = (wsq / wtot[:, None] - mean * mean).clamp_min(0.0)
+        H = hacc - logz                                            # H = sum(w lnL)/Z - ln Z
+        res = dict(logz=logz.cpu().numpy(), logzerr=torch.sqrt(H.clamp_min(0.0) / K).cpu().numpy(),
+                   information=H.cpu().numpy(), niter=niter.cpu().numpy(), ncall=self.ncall.cpu().numpy(),
+                   names=list(self.L.fitpars_i) + (list(_lib.DERIVED_NAMES) if nder else []),
+                   mean=mean.cpu().numpy(), std=torch.sqrt(var).cpu().numpy(),
+                   live_theta=TH.cpu().numpy(), live_lnprob=LP.cpu().numpy(), converged=(~active).cpu().numpy())
+        if self.store:
+            res['dead'] = [tuple(t.cpu().numpy() for t in d) for d in dead]
+        return res
+
+
+def write_samples_file(path, res, star=0):
+    """Dead points of one star in the reference's samples-file layout (header fitstar.py:235-242:
+    ``Iter <pars...> log(lk) log(vol) log(wt) h nc log(z) delta(log(z))``); needs store_samples."""
+    names = res['names']
+    with open(path, 'w') as f:
+        f.write('Iter ' + ' '.join(names) + ' log(lk) log(vol) log(wt) h nc log(z) delta(log(z))\n')
+        it = 0
+        for act, row, lnl, logvol, logwt in res['dead']:
+            k = np.flatnonzero(act == star)
+            if len(k) == 0:
+                continue
+            k = k[0]
+            f.write('%d ' % it + ' '.join('%.10g' % v for v in row[k]) +
+                    ' %.10g %.10g %.10g nan nan nan nan\n' % (lnl[k], logvol[k], logwt[k]))
+            it += 1

@@ -1,0 +1,86 @@
+"""Lock-step batched nested sampler: evidence and posterior moments against brute-force prior
+Monte-Carlo integration through the same kernels, and agreement between independent replicas."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+         'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+
+
+def _problem():
+    from minesweeper_b200 import synth
+    from oracle.payne_port import FastPayneSEDPredict
+    from oracle import mist_port
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10, frac_missing=0.0, frac_trunc=0.0)
+    phot = synth.make_phot_net(h=128, seed=35)
+    truth = dict(EEP=230.3, mass=0.93, feh=-0.4, afe=0.15, dist=14.0, av=0.03)
+    _, pred, ok = mist_port.interp_dense(mist, [truth['EEP']], [truth['mass']], [truth['feh']], [truth['afe']])
+    assert ok[0]
+    p = pred[0]
+    pp = [[10 ** p[4], p[7], p[5], p[6], p[2], truth['dist'], truth['av']]]
+    mags = FastPayneSEDPredict(nnpath=phot).sed_batch(pp)[0]
+    rng = np.random.default_rng(2)
+    err = 0.08
+    obs = {b: [float(m + err * rng.standard_normal()), err] for b, m in zip(synth.DEMO_BANDS, mags)}
+    fitpars = [NAMES, {k: (k in ON) for k in NAMES}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot, obs_phot=obs)
+    runbools = [False, True, False, False, False]
+    priordict = {'EEP': {'pv_uniform': [202, 261]}, 'initial_Mass': {'pv_uniform': [0.5, 1.25]},
+                 'initial_[Fe/H]': {'pv_uniform': [-1.0, 0.2]}, 'initial_[a/Fe]': {'pv_uniform': [-0.2, 0.6]},
+                 'Dist': {'pv_uniform': [8.0, 20.0]}, 'Av': {'pv_uniform': [0.0, 0.1]},
+                 'Parallax': {'gaussian': [1000.0 / 14.0, 3.0]}, 'IMF': {'IMF_type': 'Kroupa'}}
+    return fitargs, fitpars, runbools, priordict
+
+
+def test_nested_sampler_matches_prior_monte_carlo():
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200.sampler import BatchedNestedSampler
+    fitargs, fitpars, runbools, priordict = _problem()
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    # brute force: Z = E_prior[exp(lnprob)], posterior mean = weighted mean
+    gen = torch.Generator(device=L.engine.device).manual_seed(7)
+    lw, ths = [], []
+    for _ in range(8):
+        u = torch.rand(1 << 18, L.ndim, generator=gen, device=L.engine.device, dtype=torch.float64)
+        th = P.priortrans_batch(u)
+        lnl, der, _ = L.lnlike_batch(th)
+        lw.append(P.lnprob_batch(th, lnl, der)); ths.append(th)
+    lw, ths = torch.cat(lw), torch.cat(ths)
+    logz_mc = float(torch.logsumexp(lw, 0) - np.log(len(lw)))
+    w = torch.exp(lw - lw.max()); w = w / w.sum()
+    mean_mc = (w[:, None] * ths).sum(0).cpu().numpy()
+    std_mc = torch.sqrt((w[:, None] * (ths - torch.as_tensor(mean_mc, device=ths.device)) ** 2).sum(0)).cpu().numpy()
+    ess = float(1.0 / (w ** 2).sum())
+    assert ess > 2000, ess
+    # nested sampling: the same star in 6 replicas run in lock step
+    S = 6
+    L.engine.set_stars_phot(np.tile([[fitargs['obs_phot'][b][0] for b in L.engine.bands]], (S, 1)),
+                            np.tile([[fitargs['obs_phot'][b][1] for b in L.engine.bands]], (S, 1)))
+    ns = BatchedNestedSampler(L, P, nstars=S, nlive=150, walks=10, dlogz=0.05, seed=11, store_samples=True)
+    res = ns.run()
+    assert res['converged'].all()
+    assert (res['niter'] > 300).all() and (res['ncall'] > res['niter'] * 10).all()
+    # evidence: replicas agree with brute force within a few sigma of the NS error estimate
+    err = np.maximum(res['logzerr'], 0.05)
+    assert np.all(np.abs(res['logz'] - logz_mc) < 5 * err + 0.15), (res['logz'], logz_mc, err)
+    assert np.std(res['logz']) < 4 * err.mean() + 0.1
+    # posterior means of the sampled parameters
+    nd = L.ndim
+    m_ns = res['mean'][:, :nd].mean(0)
+    assert np.all(np.abs(m_ns - mean_mc) < 0.35 * std_mc + 1e-3), (m_ns, mean_mc, std_mc)
+    s_ns = res['std'][:, :nd].mean(0)
+    assert np.all(np.abs(s_ns / std_mc - 1.0) < 0.35), (s_ns, std_mc)
+    # dead points were recorded in the samples-file layout
+    from minesweeper_b200.sampler import write_samples_file
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, 's.dat')
+        write_samples_file(f, res, star=2)
+        lines = open(f).read().splitlines()
+        assert lines[0].startswith('Iter Dist Av EEP') and len(lines) == res['niter'][2] + 1
