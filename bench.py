@@ -42,6 +42,8 @@ def parse():
     ap.add_argument('--small-grid', action='store_true', help='debug: 60x24x7x5 grid')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--catalog-stars', type=int, default=16384,
+                    help='stars per GPU fitted with the batched nested sampler for the stars/hour figure (0 = skip)')
     return ap.parse_args()
 
 
@@ -252,6 +254,32 @@ def main():
     e2e = B * world * args.steps / float(te.item())
     assert np.array_equal(out_h, lnl.cpu().numpy(), equal_nan=True), 'host and device entry points disagree'
 
+    # ---- auxiliary: stars fitted per hour (BASELINE.json metric, configs[4]) on a small catalog
+    catalog = None
+    if args.catalog_stars > 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tools'))
+            from bench_catalog import make_catalog_sampler, catalog_priordict
+            from minesweeper_b200.prior import prior
+            Pc = prior(fitargs, catalog_priordict(261.0 if args.small_grid else 808.0), fitpars, runbools, likeobj=L)
+            ns, _ = make_catalog_sampler(L, Pc, args.catalog_stars, dev, 150, 5, 0.01, 20000, rank)
+            barrier()
+            tc0 = time.perf_counter()
+            rc = ns.run()
+            torch.cuda.synchronize()
+            tcat = torch.tensor([time.perf_counter() - tc0], dtype=torch.float64, device=dev)
+            ncalls = torch.tensor([float(rc['ncall'].sum())], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tcat, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ncalls)
+            catalog = dict(stars=args.catalog_stars * world, seconds=float(tcat.item()),
+                           stars_per_hour=args.catalog_stars * world / float(tcat.item()) * 3600.0,
+                           loglike_calls=float(ncalls.item()), sampler='lock-step static nested sampling, rwalk',
+                           nlive=150, walks=5, dlogz=0.01, converged_frac=float(rc['converged'].mean()),
+                           note='configs[4] at reduced size: stars per GPU fixed (weak scaling)')
+        except Exception as e:                                           # never lose the main line
+            catalog = dict(error=repr(e))
+
     if rank == 0:
         pk = peaks()
         H, nb = args.hidden, len(eng.bands)
@@ -288,6 +316,7 @@ def main():
                                  frac=(interp_bytes * B * in_n / (in_ms * 1e-3) / 1e9 / pk['hbm']) if in_ms > 0 else 0.0,
                                  ms_per_launch=in_ms / max(in_n, 1)),
             kernel_ms={k: v[0] / args.steps for k, v in prof.items() if v[1]},
+            catalog=catalog,
             cpu_baseline=cpu)
         print(json.dumps(out))
     if world > 1:

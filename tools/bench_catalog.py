@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Config 5 (BASELINE.json configs[4]): a synthetic catalog of stars (10 magnitudes + a Gaia-like
+parallax prior each) fitted with the lock-step batched nested sampler; reports stars fitted per
+hour.  Under torchrun the catalog is sharded over the ranks (contiguous star blocks, no data-path
+collective) and the per-star summaries are gathered once at the end.
+
+    python tools/bench_catalog.py --stars 20000 [--nlive 150 --walks 5 --dlogz 0.01]
+    torchrun --nproc-per-node N tools/bench_catalog.py --stars 100000
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+         'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+
+
+def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed):
+    """Synthetic catalog of S stars on this device (truths from the prior, observations from the
+    model itself, Gaia-like parallaxes) registered with the engine, and a sampler over it.
+    Returns (sampler, truth_theta)."""
+    import torch
+    from minesweeper_b200.sampler import BatchedNestedSampler
+    gen = torch.Generator(device=dev).manual_seed(1000 + seed)
+    truth = None
+    for _ in range(20):                                            # truths with a valid MIST prediction
+        u = torch.rand(2 * S, L.ndim, generator=gen, device=dev, dtype=torch.float64)
+        th = P.priortrans_batch(u)
+        lnl, der, _ = L.lnlike_batch(th)
+        good = torch.isfinite(lnl)
+        th, der = th[good], der[good]
+        truth = (th, der) if truth is None else (torch.cat([truth[0], th]), torch.cat([truth[1], der]))
+        if len(truth[0]) >= S:
+            break
+    th, der = truth[0][:S], truth[1][:S]
+    cols = {n: i for i, n in enumerate(L.fitpars_i)}
+    pp = torch.stack([10 ** der[:, 8], der[:, 11], der[:, 9], der[:, 10], der[:, 6], th[:, cols['Dist']],
+                      th[:, cols['Av']]], 1)
+    mags = L.engine.phot_sed(pp)
+    err = torch.full_like(mags, 0.02)
+    obs = mags + err * torch.randn(mags.shape, generator=gen, device=dev, dtype=torch.float64)
+    plx = 1000.0 / th[:, cols['Dist']]
+    plx_err = 0.05 + 0.02 * plx
+    plx_obs = plx + plx_err * torch.randn(S, generator=gen, device=dev, dtype=torch.float64)
+    L.engine.set_stars_phot(obs.cpu().numpy(), err.cpu().numpy())
+    star_plx = torch.stack([plx_obs, plx_err], 1)
+    ns = BatchedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, dlogz=dlogz, maxiter=maxiter,
+                              seed=5 + seed, star_plx=star_plx)
+    return ns, th
+
+
+def catalog_priordict(eep_hi=808.0):
+    return {'EEP': {'pv_uniform': [202, eep_hi]}, 'initial_Mass': {'pv_uniform': [0.5, 1.25]},
+            'initial_[Fe/H]': {'pv_uniform': [-2.0, 0.4]}, 'initial_[a/Fe]': {'pv_uniform': [-0.2, 0.6]},
+            'Dist': {'pv_uniform': [5.0, 2000.0]}, 'Av': {'pv_uniform': [0.0, 0.5]},
+            'IMF': {'IMF_type': 'Kroupa'}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--stars', type=int, default=20000)
+    ap.add_argument('--nlive', type=int, default=150)
+    ap.add_argument('--walks', type=int, default=5)
+    ap.add_argument('--dlogz', type=float, default=0.01)
+    ap.add_argument('--maxiter', type=int, default=20000)
+    ap.add_argument('--small-grid', action='store_true')
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200.distributed import shard_bounds, gather_rows
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=0) if args.small_grid else synth.make_mist(seed=0)
+    phot = synth.make_phot_net(h=128, seed=1)
+    eep_hi = 261.0 if args.small_grid else 808.0
+    fitpars = [NAMES, {k: (k in ON) for k in NAMES}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot,
+                   obs_phot=synth.demo_obs_phot())
+    runbools = [False, True, False, False, False]
+    priordict = catalog_priordict(eep_hi)
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', device=local, verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    # this rank's block of the catalog
+    lo, hi = shard_bounds(args.stars, rank, world)
+    S = hi - lo
+    ns, th = make_catalog_sampler(L, P, S, dev, args.nlive, args.walks, args.dlogz, args.maxiter, rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = L.engine.launch_count()
+    t0 = time.perf_counter()
+    res = ns.run()
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    summary = torch.from_numpy(np.concatenate([res['logz'][:, None], res['logzerr'][:, None], res['mean'],
+                                               res['std']], 1)).to(dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        summary = gather_rows(summary, args.stars)                 # the only collective: per-star summaries
+    nd = L.ndim
+    zs = (res['mean'][:, :nd] - th.cpu().numpy()) / np.maximum(res['std'][:, :nd], 1e-12)
+    calls = torch.tensor([float(res['ncall'].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(calls)
+    if rank == 0:
+        secs = float(el.item())
+        print(json.dumps(dict(
+            metric='stars_fitted_per_hour', value=args.stars / secs * 3600.0, unit='stars/hour', n_gpus=world,
+            stars=args.stars, seconds=secs, nlive=args.nlive, walks=args.walks, dlogz=args.dlogz,
+            iterations_median=float(np.median(res['niter'])), iterations_max=int(res['niter'].max()),
+            converged_frac=float(res['converged'].mean()),
+            loglike_calls=float(calls.item()), loglike_evals_per_sec=float(calls.item()) / secs,
+            calls_per_star=float(calls.item()) / args.stars,
+            rank0_posterior_z_rms={n: float(np.sqrt(np.mean(zs[:, i] ** 2))) for i, n in enumerate(L.fitpars_i)},
+            rank0_kernel_launches=int(L.engine.launch_count() - l0),
+            summary_shape=list(summary.shape))))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
