@@ -198,6 +198,191 @@ class BatchedNestedSampler(object):
         return res
 
 
+    # ------------------------------------------------------------------------------------------
+    def run_graphed(self, check_every=64, verbose=False, min_compact=512):
+        """Same sampler with one nested-sampling iteration captured in a CUDA graph and replayed.
+
+        Every tensor has a static shape (all stars of the current working set take part in every
+        iteration; finished stars are masked), there is no host synchronisation inside an
+        iteration, and convergence is polled from the host only every ``check_every`` replays.
+        When fewer than half of the working set is still active, the finished stars are retired
+        (their live points are added to the evidence and moments), the state is compacted to the
+        active ones and the graph is captured again, so stragglers do not keep the whole catalog
+        busy.  This removes the launch and Python overhead that bounds ``run`` (about 4 ms per
+        iteration regardless of catalog size).  Differences from ``run``: a walk that never moved
+        is not extended (the start point, a copy of another live point, is kept -- with the
+        adaptive scale this happens in a few per cent of the iterations); dead points are not
+        stored.
+        """
+        S, K, nd, dev = self.S, self.K, self.ndim, self.dev
+        f64 = torch.float64
+        ninf = -float('inf')
+        star0 = torch.arange(S, device=dev)
+        # ---- initial live points, eagerly (redrawn until finite) ----
+        U = self._rand(S, K, nd)
+        slot = star0.repeat_interleave(K)
+        lp, th, der = self._lnprob(U.reshape(-1, nd), slot)
+        nder = der.shape[1] if der is not None else 0
+        for _ in range(50):
+            bad = ~torch.isfinite(lp)
+            if not bool(bad.any()):
+                break
+            idx = bad.nonzero(as_tuple=True)[0]
+            un = self._rand(len(idx), nd)
+            lpn, thn, dern = self._lnprob(un, slot[idx])
+            U.reshape(-1, nd)[idx] = un
+            lp[idx], th[idx] = lpn, thn
+            if der is not None:
+                der[idx] = dern
+        if bool((~torch.isfinite(lp)).any()):
+            raise RuntimeError('could not draw live points with finite lnprob from the prior')
+        ncol = nd + nder
+        st = dict(U=U, LP=lp.reshape(S, K).clone(), TH=th.reshape(S, K, nd).clone(),
+                  logz=torch.full((S,), ninf, dtype=f64, device=dev), hacc=torch.zeros(S, dtype=f64, device=dev),
+                  wsum=torch.zeros(S, ncol, dtype=f64, device=dev), wsq=torch.zeros(S, ncol, dtype=f64, device=dev),
+                  wmax=torch.full((S,), ninf, dtype=f64, device=dev), wtot=torch.zeros(S, dtype=f64, device=dev),
+                  scale=torch.ones(S, dtype=f64, device=dev), active=torch.ones(S, dtype=torch.bool, device=dev),
+                  niter=torch.zeros(S, dtype=torch.int64, device=dev), ncall=self.ncall.clone(),
+                  orig=star0.clone())
+        if der is not None:
+            st['DER'] = der.reshape(S, K, nder).clone()
+        log_shrink = float(np.log1p(-np.exp(-1.0 / K)))
+        per_star = self.S > 1
+        plx = self.star_plx
+        # results for the whole catalog, filled as stars retire
+        out = dict(logz=torch.empty(S, dtype=f64, device=dev), H=torch.empty(S, dtype=f64, device=dev),
+                   niter=torch.zeros(S, dtype=torch.int64, device=dev), ncall=torch.zeros(S, dtype=torch.int64, device=dev),
+                   mean=torch.empty(S, ncol, dtype=f64, device=dev), std=torch.empty(S, ncol, dtype=f64, device=dev),
+                   converged=torch.zeros(S, dtype=torch.bool, device=dev))
+
+        def accumulate(sx, mask, lnl, logwt, row):
+            lz_new = torch.logaddexp(sx['logz'], logwt)
+            h_new = sx['hacc'] * torch.exp(sx['logz'] - lz_new) + torch.exp(logwt - lz_new) * lnl
+            sx['hacc'].copy_(torch.where(mask & torch.isfinite(h_new), h_new, sx['hacc']))
+            sx['logz'].copy_(torch.where(mask, lz_new, sx['logz']))
+            m_new = torch.where(mask, torch.maximum(sx['wmax'], logwt), sx['wmax'])
+            r_old = torch.exp(sx['wmax'] - m_new)
+            r_old = torch.where(torch.isfinite(r_old), r_old, torch.zeros_like(r_old))
+            w = torch.where(mask, torch.exp(logwt - m_new), torch.zeros_like(logwt))
+            w = torch.where(torch.isfinite(w), w, torch.zeros_like(w))
+            sx['wsum'].copy_(sx['wsum'] * r_old[:, None] + w[:, None] * row)
+            sx['wsq'].copy_(sx['wsq'] * r_old[:, None] + w[:, None] * row * row)
+            sx['wtot'].copy_(sx['wtot'] * r_old + w)
+            sx['wmax'].copy_(m_new)
+
+        def retire(idx):
+            """Final live-point contribution and summaries of the stars st[...][idx]."""
+            sx = {k: v[idx].clone() for k, v in st.items()}
+            n = len(idx)
+            logvol_f = -(sx['niter'].to(f64)) / K - float(np.log(K))
+            allm = torch.ones(n, dtype=torch.bool, device=dev)
+            for k in range(K):
+                rowk = sx['TH'][:, k] if 'DER' not in sx else torch.cat([sx['TH'][:, k], sx['DER'][:, k]], dim=1)
+                rowk = torch.where(torch.isfinite(rowk), rowk, torch.zeros_like(rowk))
+                accumulate(sx, allm, sx['LP'][:, k], sx['LP'][:, k] + logvol_f, rowk)
+            mean = sx['wsum'] / sx['wtot'][:, None]
+            var = (sx['wsq'] / sx['wtot'][:, None] - mean * mean).clamp_min(0.0)
+            o = sx['orig']
+            out['logz'][o] = sx['logz']; out['H'][o] = sx['hacc'] - sx['logz']
+            out['niter'][o] = sx['niter']; out['ncall'][o] = sx['ncall']
+            out['mean'][o] = mean; out['std'][o] = torch.sqrt(var)
+            out['converged'][o] = ~sx['active']
+
+        total = 0
+        ncapt = 0
+        while True:
+            Sc = len(st['orig'])
+            star = torch.arange(Sc, device=dev)
+            slot32 = st['orig'].to(torch.int32).contiguous()
+
+            def lnprob_static(u):
+                theta = self.P.priortrans_batch(u)
+                lnl, dr, _ = self.eng.lnlike_batch(theta, self.L._colmap, self.L._fixed, self.L._flags,
+                                                   star_slot=slot32 if per_star else None,
+                                                   want_derived=self.L.iso_bool)
+                o = self.P.lnprob_batch(theta, lnl, dr, star_slot=slot32 if plx is not None else None, star_plx=plx)
+                return o, theta, dr
+
+            def iteration():
+                act = st['active']
+                LP, U_, TH, DER = st['LP'], st['U'], st['TH'], st.get('DER')
+                lmin, w = LP.min(dim=1)
+                logvol = -(st['niter'].to(f64) + 1.0) / K
+                logwt = torch.where(act, lmin + (logvol + 1.0 / K + log_shrink), torch.full_like(lmin, ninf))
+                row = TH[star, w] if DER is None else torch.cat([TH[star, w], DER[star, w]], dim=1)
+                row = torch.where(torch.isfinite(row), row, torch.zeros_like(row))
+                accumulate(st, act, lmin, logwt, row)
+                j = torch.randint(0, K - 1, (Sc,), device=dev)
+                j = j + (j >= w).to(j.dtype)
+                ucur, lcur, thcur = U_[star, j], LP[star, j], TH[star, j]
+                dcur = DER[star, j] if DER is not None else None
+                sig = U_.std(dim=1).clamp_min(1e-12) * st['scale'][:, None]
+                nacc = torch.zeros(Sc, dtype=f64, device=dev)
+                for _ in range(self.walks):
+                    prop = ucur + sig * torch.randn(Sc, nd, device=dev, dtype=f64)
+                    prop = torch.remainder(prop, 2.0)
+                    prop = torch.where(prop > 1.0, 2.0 - prop, prop)
+                    lpn, thn, dern = lnprob_static(prop)
+                    ok = lpn > lmin
+                    ucur = torch.where(ok[:, None], prop, ucur)
+                    lcur = torch.where(ok, lpn, lcur)
+                    thcur = torch.where(ok[:, None], thn, thcur)
+                    if dcur is not None:
+                        dcur = torch.where(ok[:, None], dern, dcur)
+                    nacc = nacc + ok.to(f64)
+                facc = nacc / self.walks
+                st['scale'].copy_(torch.where(act, (st['scale'] * torch.exp((facc - 0.5) / nd / 0.5)).clamp(1e-4, 10.0),
+                                              st['scale']))
+                a2 = act[:, None]
+                U_[star, w] = torch.where(a2, ucur, U_[star, w])
+                LP[star, w] = torch.where(act, lcur, LP[star, w])
+                TH[star, w] = torch.where(a2, thcur, TH[star, w])
+                if DER is not None:
+                    DER[star, w] = torch.where(a2, dcur, DER[star, w])
+                st['niter'] += act.to(torch.int64)
+                st['ncall'] += act.to(torch.int64) * self.walks
+                lmax = LP.max(dim=1).values
+                dl = torch.logaddexp(st['logz'], lmax + logvol) - st['logz']
+                st['active'].copy_(act & ~(dl < self.dlogz) & (st['niter'] < self.maxiter))
+
+            # warm up on a side stream (scratch allocations, lazy initialisation), then capture
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    iteration()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iteration()
+            ncapt += 1
+            total += 3
+            while True:
+                for _ in range(check_every):
+                    graph.replay()
+                total += check_every
+                n_act = int(st['active'].sum().item())
+                if verbose:
+                    print('replays %d: %d / %d stars active (working set %d)' % (total, n_act, S, Sc))
+                if n_act == 0 or (Sc > min_compact and n_act * 2 <= Sc) or total >= self.maxiter + 3 * ncapt:
+                    break
+            del graph
+            done = (~st['active']).nonzero(as_tuple=True)[0]
+            if n_act == 0 or total >= self.maxiter + 3 * ncapt:
+                retire(torch.arange(Sc, device=dev))
+                break
+            retire(done)
+            keep = st['active'].nonzero(as_tuple=True)[0]
+            st = {k: v[keep].clone() for k, v in st.items()}
+        return dict(logz=out['logz'].cpu().numpy(), logzerr=torch.sqrt(out['H'].clamp_min(0.0) / K).cpu().numpy(),
+                    information=out['H'].cpu().numpy(), niter=out['niter'].cpu().numpy(),
+                    ncall=out['ncall'].cpu().numpy(),
+                    names=list(self.L.fitpars_i) + (list(_lib.DERIVED_NAMES) if nder else []),
+                    mean=out['mean'].cpu().numpy(), std=out['std'].cpu().numpy(),
+                    converged=out['converged'].cpu().numpy(), graph_replays=total, graph_captures=ncapt)
+
+
 def write_samples_file(path, res, star=0):
     """Dead points of one star in the reference's samples-file layout (header fitstar.py:235-242:
     ``Iter <pars...> log(lk) log(vol) log(wt) h nc log(z) delta(log(z))``); needs store_samples."""

@@ -84,3 +84,27 @@ def test_nested_sampler_matches_prior_monte_carlo():
         write_samples_file(f, res, star=2)
         lines = open(f).read().splitlines()
         assert lines[0].startswith('Iter Dist Av EEP') and len(lines) == res['niter'][2] + 1
+
+
+def test_graphed_sampler_agrees_with_eager():
+    """The CUDA-graph replay form gives the same evidence and posterior (statistically) as the
+    eager loop."""
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200.sampler import BatchedNestedSampler
+    fitargs, fitpars, runbools, priordict = _problem()
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    S = 8
+    L.engine.set_stars_phot(np.tile([[fitargs['obs_phot'][b][0] for b in L.engine.bands]], (S, 1)),
+                            np.tile([[fitargs['obs_phot'][b][1] for b in L.engine.bands]], (S, 1)))
+    torch.manual_seed(3)
+    eager = BatchedNestedSampler(L, P, nstars=S, nlive=150, walks=10, dlogz=0.05, seed=21).run()
+    graphed = BatchedNestedSampler(L, P, nstars=S, nlive=150, walks=10, dlogz=0.05, seed=22).run_graphed(check_every=32)
+    assert graphed['converged'].all() and eager['converged'].all()
+    err = max(eager['logzerr'].mean(), 0.05)
+    assert abs(graphed['logz'].mean() - eager['logz'].mean()) < 3 * err / np.sqrt(S) + 0.15
+    nd = L.ndim
+    sd = eager['std'][:, :nd].mean(0)
+    assert np.all(np.abs(graphed['mean'][:, :nd].mean(0) - eager['mean'][:, :nd].mean(0)) < 0.3 * sd + 1e-3)
+    assert np.all(np.abs(graphed['std'][:, :nd].mean(0) / sd - 1.0) < 0.3)
