@@ -431,6 +431,7 @@ static int run_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) 
 }
 
 extern "C" int ms_phot_sed(ms_ctx *ctx, const double *photpars, int64_t B, double *mags, void *stream) {
+    if (ctx && B == 0) return MS_OK;
     if (!ctx || !photpars || !mags || B < 0) { ms_set_error("bad arguments"); return MS_EINVAL; }
     MS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -443,6 +444,7 @@ extern "C" int ms_phot_sed(ms_ctx *ctx, const double *photpars, int64_t B, doubl
 
 extern "C" int ms_spec_model(ms_ctx *ctx, int star_slot, const double *specpars, int n_pc, int64_t B,
                              double *flux, void *stream) {
+    if (ctx && B == 0) return MS_OK;
     if (!ctx || !specpars || !flux || B < 0 || n_pc < 0 || n_pc > MS_MAX_PC) { ms_set_error("bad arguments"); return MS_EINVAL; }
     MS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -457,6 +459,7 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
                                const int32_t *star_slot, int64_t B, int ndim, const int32_t *colmap,
                                const double *fixed, double *lnL, double *derived, int32_t *brackets,
                                void *stream) {
+    if (ctx && B == 0) return MS_OK;                       // empty batch: nothing to do, NULL buffers allowed
     if (!ctx || !flags || !theta || !colmap || !lnL || B < 0 || ndim < 1 || ndim > MS_NPARAM) {
         ms_set_error("bad arguments");
         return MS_EINVAL;
@@ -509,6 +512,7 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
 extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const double *theta_host,
                                     int64_t B, int ndim, const int32_t *colmap, const double *fixed,
                                     double *lnL_host, double *derived_host) {
+    if (ctx && B == 0) return MS_OK;
     if (!ctx || !theta_host || !lnL_host || B < 0) { ms_set_error("bad arguments"); return MS_EINVAL; }
     MS_CUDA(cudaSetDevice(ctx->device));
     int rc;

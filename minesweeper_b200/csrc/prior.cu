@@ -141,8 +141,8 @@ __global__ void lnprior_kernel(LnPriorArgs a, int64_t B) {
 
 extern "C" int ms_prior_transform(ms_ctx *ctx, const double *u, int64_t B, int ndim, const ms_prior_col *cols,
                                   double *theta, void *stream) {
+    if (ctx && B == 0) return MS_OK;
     if (!ctx || !u || !theta || !cols || B < 0 || ndim < 1 || ndim > MS_NPARAM) { ms_set_error("bad arguments"); return MS_EINVAL; }
-    if (B == 0) return MS_OK;
     MS_CUDA(cudaSetDevice(ctx->device));
     TransformArgs a;
     a.ndim = ndim;
@@ -171,6 +171,7 @@ extern "C" int ms_lnprob_batch_stars(ms_ctx *ctx, const ms_flags *flags, const d
                                      const int32_t *colmap, const double *fixed, const double *derived,
                                      const ms_prior_term *terms, int nterms, int imf, const double *lnL,
                                      double *out, const int32_t *star_slot, const double *star_plx, void *stream) {
+    if (ctx && B == 0) return MS_OK;
     if (!ctx || !flags || !theta || !colmap || !out || B < 0 || ndim < 1 || ndim > MS_NPARAM || nterms < 0 ||
         nterms > MS_MAX_PRIOR_TERMS || (nterms && !terms)) { ms_set_error("bad arguments"); return MS_EINVAL; }
     if (B == 0) return MS_OK;

@@ -338,3 +338,65 @@ def test_lnlike_spec_phot_tc_vs_oracle():
         resid = np.abs(fref - obs['obs_flux']) / obs['obs_eflux'] ** 2
         tol = np.nansum(resid * 1e-5 * np.abs(fref)) + 1e-3 * abs(want) * 1e-2 + 1e-3
         assert abs(lnl[i] - want) <= tol, (i, lnl[i], want, tol)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_non_isochrone_phot_fit_vs_oracle():
+    """isochrone_prior=False: Teff, log(g), [Fe/H], [a/Fe], log(R), Dist, Av are sampled directly
+    (fitstar.py:187-193 off); no MIST kernel runs, no Agewgt term."""
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    from oracle.like_port import LikelihoodPort
+    phot = synth.make_phot_net(h=128, seed=36)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'log(R)', 'Dist', 'Av'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, photANNpath=phot, obs_phot=synth.demo_obs_phot())
+    runbools = [False, True, False, False, False]
+    th = _rand_photpars(500, 3)[:, [0, 1, 2, 3, 4, 5, 6]]            # fitpars_i order = Teff, logg, feh, afe, logR, Dist, Av
+    ref = LikelihoodPort(dict(fitargs, ageweight=False), fitpars, runbools)
+    for prec, tol in (('f64', 1e-6), ('tc', None)):
+        L = likelihood(dict(fitargs, ageweight=False), fitpars, runbools, precision=prec, verbose=False)
+        assert L.fitpars_i == ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'log(R)', 'Dist', 'Av'] and not L.iso_bool
+        lnl, der, _ = L.lnlike_batch(th)
+        assert der is None
+        lnl = lnl.cpu().numpy()
+        for i in range(0, 500, 11):
+            want = ref.lnlikefn(list(th[i]))
+            if tol is not None:
+                assert abs(lnl[i] - want) <= tol + 1e-12 * abs(want)
+            else:
+                assert abs(lnl[i] - want) <= 2e-4 * abs(want) + 1e-3
+        v = L.lnlikefn(list(th[5]))
+        assert v == lnl[5] and L.parsdict['Teff'] == th[5, 0] and 'log(Age)' not in L.parsdict
+
+
+def test_empty_and_degenerate_batches(g_like_phot):
+    from minesweeper_b200.likelihood import likelihood
+    g = g_like_phot
+    fitargs, fitpars, runbools = fit_setup(g)
+    L = likelihood(fitargs, fitpars, runbools, precision='f32', verbose=False)
+    lnl, der, br = L.lnlike_batch(np.zeros((0, L.ndim)), want_brackets=True)
+    assert lnl.shape == (0,) and der.shape == (0, 13) and br.shape == (0, 4)
+    th = g['theta'][np.isfinite(g['lnl'])][:8].copy()          # in-grid rows
+    th[0, :] = np.nan                                   # NaN everywhere -> out of grid -> -inf, like the reference
+    th[1, L.fitpars_i.index('Dist')] = -5.0             # log10 of a negative distance -> NaN magnitudes -> dropped by nansum
+    th[2, L.fitpars_i.index('initial_Mass')] = np.inf
+    lnl, der, _ = L.lnlike_batch(th)
+    lnl = lnl.cpu().numpy()
+    assert lnl[0] == -np.inf and lnl[2] == -np.inf
+    assert np.isposinf(der.cpu().numpy()[0, 4:]).all()
+    from oracle.like_port import LikelihoodPort
+    ref = LikelihoodPort(fitargs, fitpars, runbools)
+    with np.errstate(all='ignore'):
+        want = ref.lnlikefn(list(th[1]))
+    assert np.isfinite(want) or np.isnan(want)
+    assert (np.isnan(want) and np.isnan(lnl[1])) or abs(lnl[1] - want) <= 1e-3 * abs(want) + 1e-6
+    assert np.isfinite(lnl[3:]).all()
+    # a single row and a ragged size through the host entry point
+    l1, _ = L.lnlike_batch_host(g['theta'][:1])
+    l257, _ = L.lnlike_batch_host(g['theta'][:257])
+    full = L.lnlike_batch(g['theta'][:257])[0].cpu().numpy()
+    np.testing.assert_array_equal(l257, full)
+    np.testing.assert_array_equal(l1, full[:1])
