@@ -240,6 +240,151 @@ __device__ void fft_filter(typename Cx<T>::type *z, int n, const Transfer<T> &tf
     for (int s = rem + 2; s <= L - 1; s += 3) fft_pass8<T, true>(z, M, 1 << (s - 2), s - 2, tw, tw_n);
 }
 
+// ---- Stockham autosort FFT (f32 path) ---------------------------------------------------
+// Out-of-place passes between two shared-memory buffers: a thread reads R inputs at stride
+// M/R (consecutive threads -> consecutive addresses, conflict-free), applies the pass
+// twiddles, does an R-point transform in registers and writes at stride Ns.  Output is in
+// natural order, so the split/merge pass walks k and M-k linearly (conflict-free, and its
+// twiddle / transfer-table reads are coalesced).  Pass schedule: radix 8 while >= 3 bits
+// remain, then radix 4 or 2 (8192 = 8.8.8.8.2).
+template <typename T2, bool INV> __device__ __forceinline__ T2 tw_get(const T2 *__restrict__ tw, int idx) {
+    T2 w = tw[idx];
+    if (INV) w.y = -w.y;
+    return w;
+}
+template <typename T2, bool INV> __device__ __forceinline__ void fft8_reg(T2 (&v)[8]) {
+    typedef decltype(v[0].x) T;
+    const T r = (T)0.70710678118654752440;
+    // stage 1: (m, m+4), twiddle W8^m on the difference
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const T2 a = v[m], b = v[m + 4];
+        v[m] = cadd(a, b);
+        const T2 d = csub(a, b);
+        T2 o;
+        if (m == 0) o = d;
+        else if (m == 1) o = INV ? T2{r * (d.x - d.y), r * (d.x + d.y)} : T2{r * (d.x + d.y), r * (d.y - d.x)};
+        else if (m == 2) o = INV ? T2{-d.y, d.x} : T2{d.y, -d.x};
+        else o = INV ? T2{-r * (d.x + d.y), r * (d.x - d.y)} : T2{r * (d.y - d.x), -r * (d.x + d.y)};
+        v[m + 4] = o;
+    }
+    // stage 2: (m, m+2) inside each half, twiddle W4^m
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+        const T2 a0 = v[h], b0 = v[h + 2], a1 = v[h + 1], b1 = v[h + 3];
+        v[h] = cadd(a0, b0); v[h + 2] = csub(a0, b0);
+        v[h + 1] = cadd(a1, b1);
+        const T2 d = csub(a1, b1);
+        v[h + 3] = INV ? T2{-d.y, d.x} : T2{d.y, -d.x};
+    }
+    // stage 3: (m, m+1)
+#pragma unroll
+    for (int m = 0; m < 8; m += 2) {
+        const T2 a = v[m], b = v[m + 1];
+        v[m] = cadd(a, b); v[m + 1] = csub(a, b);
+    }
+    // v[i] now holds X[bitrev3(i)]
+}
+
+template <typename T, int R, bool INV>
+__device__ __forceinline__ void stockham_pass(const typename Cx<T>::type *__restrict__ in,
+                                              typename Cx<T>::type *__restrict__ out, int M, int lNs,
+                                              const typename Cx<T>::type *__restrict__ tw, int tw_n) {
+    typedef typename Cx<T>::type T2;
+    constexpr int LR = (R == 8) ? 3 : (R == 4 ? 2 : 1);
+    const int nb = M >> LR, Ns = 1 << lNs;
+    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+        const int k = j & (Ns - 1);
+        T2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = in[j + r * nb];
+        if (lNs > 0) {
+            const T2 w1 = tw_get<T2, INV>(tw, k * (tw_n >> (lNs + LR)));      // exp(-+2 pi i k / (Ns R))
+            if (R == 2) {
+                v[1] = cmul(v[1], w1);
+            } else {
+                const T2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                v[1] = cmul(v[1], w1); v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+                if (R == 8) {
+                    const T2 w4 = cmul(w2, w2), w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w6, w1);
+                    v[4] = cmul(v[4], w4); v[5] = cmul(v[5], w5); v[6] = cmul(v[6], w6); v[7] = cmul(v[7], w7);
+                }
+            }
+        }
+        const int j0 = ((j >> lNs) << (lNs + LR)) + k;
+        if (R == 8) {
+            T2 (&v8)[8] = reinterpret_cast<T2 (&)[8]>(v);
+            fft8_reg<T2, INV>(v8);
+            out[j0] = v[0]; out[j0 + Ns] = v[4]; out[j0 + 2 * Ns] = v[2]; out[j0 + 3 * Ns] = v[6];
+            out[j0 + 4 * Ns] = v[1]; out[j0 + 5 * Ns] = v[5]; out[j0 + 6 * Ns] = v[3]; out[j0 + 7 * Ns] = v[7];
+        } else if (R == 4) {
+            const T2 a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]), b0 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+            const T2 b1 = INV ? T2{-d.y, d.x} : T2{d.y, -d.x};
+            out[j0] = cadd(a0, b0); out[j0 + Ns] = cadd(a1, b1); out[j0 + 2 * Ns] = csub(a0, b0); out[j0 + 3 * Ns] = csub(a1, b1);
+        } else {
+            out[j0] = cadd(v[0], v[1]); out[j0 + Ns] = csub(v[0], v[1]);
+        }
+    }
+    __syncthreads();
+}
+
+// runs all passes of an M-point transform from buffer a to ... ; returns which buffer holds the result
+template <typename T, bool INV>
+__device__ __forceinline__ int stockham_fft(typename Cx<T>::type *b0, typename Cx<T>::type *b1, int src, int M, int L,
+                                            const typename Cx<T>::type *__restrict__ tw, int tw_n) {
+    typedef typename Cx<T>::type T2;
+    int lNs = 0, rem = L;
+    while (rem > 0) {
+        const T2 *in = src ? b1 : b0;
+        T2 *out = src ? b0 : b1;
+        if (rem >= 3) { stockham_pass<T, 8, INV>(in, out, M, lNs, tw, tw_n); lNs += 3; rem -= 3; }
+        else if (rem == 2) { stockham_pass<T, 4, INV>(in, out, M, lNs, tw, tw_n); lNs += 2; rem -= 2; }
+        else { stockham_pass<T, 2, INV>(in, out, M, lNs, tw, tw_n); lNs += 1; rem -= 1; }
+        src ^= 1;
+    }
+    return src;
+}
+
+// y = irfft(rfft(x) * transfer): input reals in z0 (z0[m] = x[2m] + i x[2m+1]), result back in z0;
+// z1 is the ping-pong buffer.  Natural-order data throughout.
+template <typename T>
+__device__ void fft_filter_stockham(typename Cx<T>::type *z0, typename Cx<T>::type *z1, int n, const Transfer<T> &tf,
+                                    const typename Cx<T>::type *__restrict__ tw, int tw_n) {
+    typedef typename Cx<T>::type T2;
+    const int M = n >> 1;
+    const int L = 31 - __clz(M);
+    const int where = stockham_fft<T, false>(z0, z1, 0, M, L, tw, tw_n);
+    T2 *z = where ? z1 : z0;
+    const int nbf = M >> 1, tstepn = tw_n / n;
+    const T inv = (T)1 / (T)M;
+    for (int k = threadIdx.x; k <= nbf; k += blockDim.x) {
+        if (k == 0) {
+            const T2 zz = z[0];
+            const T y0 = inv * tf(0) * (zz.x + zz.y), ym = inv * tf(M) * (zz.x - zz.y);
+            z[0] = {(T)0.5 * (y0 + ym), (T)0.5 * (y0 - ym)};
+        } else {
+            const int pm = M - k;
+            const T2 A = z[k];
+            T2 Bc = z[pm]; Bc.y = -Bc.y;
+            const T2 E = {(T)0.5 * (A.x + Bc.x), (T)0.5 * (A.y + Bc.y)};
+            const T2 dif = csub(A, Bc);
+            const T2 O = {(T)0.5 * dif.y, (T)-0.5 * dif.x};
+            const T2 w = tw[k * tstepn];
+            const T2 wO = cmul(w, O);
+            const T tk = inv * tf(k), tm = inv * tf(pm);
+            const T2 Yk = {tk * (E.x + wO.x), tk * (E.y + wO.y)};
+            const T2 Ymc = {tm * (E.x - wO.x), tm * (E.y - wO.y)};
+            const T2 Ep = {(T)0.5 * (Yk.x + Ymc.x), (T)0.5 * (Yk.y + Ymc.y)};
+            const T2 D = {(T)0.5 * (Yk.x - Ymc.x), (T)0.5 * (Yk.y - Ymc.y)};
+            const T2 Op = cmulc(D, w);
+            z[k] = {Ep.x - Op.y, Ep.y + Op.x};
+            if (pm != k) z[pm] = {Ep.x + Op.y, Op.x - Ep.y};
+        }
+    }
+    __syncthreads();
+    stockham_fft<T, true>(z0, z1, where, M, L, tw, tw_n);     // same number of passes -> ends in z0
+}
+
 // numpy.polynomial.chebyshev.chebval recurrence (Clenshaw), n coefficients
 __device__ __forceinline__ double cheb_eval(double x, const double *c, int n) {
     if (n == 1) return c[0];
@@ -259,9 +404,11 @@ __global__ void __launch_bounds__(SmoothCfg<T>::THREADS, 1)
 spec_smooth_kernel(SmoothArgs a, int nB) {
     typedef typename Cx<T>::type T2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool kStockham = sizeof(T) == 4;                // f32: ping-pong Stockham FFT; f64: in-place
     T2 *z = reinterpret_cast<T2 *>(smem_raw);                 // n1/2 complex = n1 reals
     T *zr = reinterpret_cast<T *>(smem_raw);
-    T *fr = zr + a.n1;                                        // npix
+    T2 *z1 = z + (a.n1 >> 1);                                 // second FFT buffer (f32 only)
+    T *fr = zr + (kStockham ? 2 * a.n1 : a.n1);               // npix
     __shared__ double red[32];
     const T *a1f = static_cast<const T *>(a.a1_frac), *a2f = static_cast<const T *>(a.a2_frac);
     const T2 *tw = static_cast<const T2 *>(a.twiddle);
@@ -310,7 +457,7 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
             Transfer<T> tf;
             tf.kind = 1; tf.tab = a.rot_tab;
             tf.coef = 2.0 * M_PI * sigma / ((double)n1 * MS_CKMS * step1);
-            fft_filter<T>(z, n1, tf, tw, n1);
+            if (kStockham) fft_filter_stockham<T>(z, z1, n1, tf, tw, n1); else fft_filter<T>(z, n1, tf, tw, n1);
             for (int i0 = threadIdx.x; i0 < npix; i0 += 4 * blockDim.x) {
                 int kk[4]; T ff[4];
 #pragma unroll
@@ -366,7 +513,7 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
                 tf.kind = 0; tf.tab = nullptr;
                 const double ndv = (double)n2 * MS_CKMS * d2;
                 tf.coef = 2.0 * M_PI * M_PI * sigma * sigma / (ndv * ndv);
-                fft_filter<T>(z, n2, tf, tw, n1);
+                if (kStockham) fft_filter_stockham<T>(z, z1, n2, tf, tw, n1); else fft_filter<T>(z, n2, tf, tw, n1);
             }
         } else {
             mode = 1;
@@ -454,7 +601,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         MS_CUDA(cudaMalloc(&ctx->scr_hid, hid_bytes));
         ctx->scr_hid_bytes = hid_bytes;
     }
-    const size_t smem = (size_t)(n.n1 + n.npix) * sizeof(T);
+    const size_t smem = (size_t)((sizeof(T) == 4 ? 2 : 1) * n.n1 + n.npix) * sizeof(T);
     if (smem > 226 * 1024) {
         ms_set_error("spectral net with %d pixels does not fit the shared-memory smoother", n.npix);
         return MS_EINVAL;
