@@ -198,6 +198,32 @@ int ms_lnprob_batch_stars(ms_ctx *ctx, const ms_flags *flags, const double *thet
                           const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
                           const int32_t *star_slot, const double *star_plx, void *stream);
 
+/* ---- nested-sampling bookkeeping ---------------------------
+ * Replaces the sequential part of dynesty's static sampler as driven by fitstar._runsampler
+ * (fitstar.py:337-369): S stars x Q queued random-walk walkers, K live points per star.  All
+ * pointers are device memory owned by the caller (see minesweeper_b200/sampler.py). */
+typedef struct {
+    int32_t S, K, Q, nd, nder, walks;
+    int64_t maxiter, dead_cap;
+    double dlogz;
+    double *live_u, *live_lp, *live_row;              /* [S][K][nd], [S][K], [S][K][nd+nder]         */
+    double *cur_u, *cur_lp, *cur_row, *prop_u;        /* walkers: [S*Q][nd], [S*Q], [S*Q][nd+nder]   */
+    const double *prop_lp, *prop_theta, *prop_der;    /* outputs of the batched lnprob at prop_u     */
+    int32_t *nacc;                                    /* [S*Q] accepted steps this round             */
+    double *lmin, *sigma, *scale;                     /* [S], [S][nd], [S]                           */
+    double *logz, *hacc, *wmax, *wtot, *wsum, *wsq;   /* evidence / information / posterior moments  */
+    int64_t *niter, *ncall;                           /* [S] iterations, likelihood calls            */
+    int32_t *done;                                    /* [S]                                         */
+    double *dead;                                     /* [S][dead_cap][nd+nder+3] or NULL            */
+    uint64_t *rng_round;                              /* device counter of completed rounds (graph-replay safe RNG stream) */
+} ms_ns_state;
+/* step = walk step inside the current round (0 .. walks-1); the round number is read from rng_round */
+int ms_ns_propose(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t step, void *stream);
+int ms_ns_accept(ms_ctx *ctx, const ms_ns_state *s, void *stream);
+/* consumes the queue, prepares the next round and advances rng_round */
+int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, void *stream);
+int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
+
 /* Number of kernel launches issued by this ctx so far (bench bookkeeping). */
 int64_t ms_launch_count(const ms_ctx *ctx);
 

@@ -80,6 +80,15 @@ TERM_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'tgaussian_bounds': 3
 MS_V_LOGAGE, MS_V_AGE, MS_V_PARALLAX = MS_NPARAM, MS_NPARAM + 1, MS_NPARAM + 2
 MS_MAX_PRIOR_TERMS = 32
 
+class NsState(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ('S', 'K', 'Q', 'nd', 'nder', 'walks')] +
+                [('maxiter', C.c_int64), ('dead_cap', C.c_int64), ('dlogz', C.c_double)] +
+                [(n, C.c_void_p) for n in ('live_u', 'live_lp', 'live_row', 'cur_u', 'cur_lp', 'cur_row', 'prop_u',
+                                           'prop_lp', 'prop_theta', 'prop_der', 'nacc', 'lmin', 'sigma', 'scale',
+                                           'logz', 'hacc', 'wmax', 'wtot', 'wsum', 'wsq', 'niter', 'ncall', 'done', 'dead',
+                                           'rng_round')])
+
+
 # every exported symbol of include/minesweeper_b200.h with its prototype
 PROTOTYPES = {
     'ms_version': (C.c_char_p, []),
@@ -108,6 +117,10 @@ PROTOTYPES = {
                                         C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     'ms_set_stars_phot': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int]),
+    'ms_ns_propose': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_uint64, C.c_void_p]),
+    'ms_ns_accept': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
+    'ms_ns_consume': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_void_p]),
+    'ms_ns_finalize': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
     'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_read': (C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int64)]),

@@ -1,0 +1,287 @@
+// Nested-sampling bookkeeping kernels: the sequential part of a
+// static nested-sampling run with a proposal queue, one CTA per star.
+//
+// The reference drives dynesty's static sampler with the `rwalk` proposal, one likelihood call at
+// a time (reference fitstar.py:337-369; demo/etc/samplerinfo.dat).  Here every star owns Q
+// random-walk walkers that are advanced together (one batched prior-transform / likelihood /
+// ln-prior call per walk step over all stars x walkers); their end points form a queue that
+// `ns_consume_kernel` uses up in order: each accepted candidate replaces the current worst live
+// point (ln X_i = -i / K), provided it still lies above the rising likelihood threshold --
+// exactly dynesty's `queue_size` logic: a point uniform in {L > L_a} that also satisfies
+// L > L_b >= L_a is uniform in {L > L_b}.
+//   ns_propose_kernel   Gaussian step in the unit cube, reflected at the walls (Philox)
+//   ns_accept_kernel    accept iff lnprob > threshold of the round; carries theta / derived along
+//   ns_consume_kernel   worst point, ln Z / H / posterior moments, replacement, stopping rule,
+//                       live-point spread, step-scale adaptation, restart points of the next round
+//   ns_finalize_kernel  contribution of the remaining live points
+#include "common.cuh"
+
+#include <curand_kernel.h>
+
+namespace {
+
+__device__ __forceinline__ double logaddexp_d(double a, double b) {
+    if (a == -ms_inf()) return b;
+    if (b == -ms_inf()) return a;
+    const double m = fmax(a, b);
+    return m + log1p(exp(-fabs(a - b)));
+}
+
+__global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
+    const int64_t n = (int64_t)s.S * s.Q;
+    for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < n; wk += (int64_t)gridDim.x * blockDim.x) {
+        const int star = (int)(wk / s.Q);
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed, (unsigned long long)wk, (*s.rng_round * (uint64_t)s.walks + step) * 32ull, &st);
+        const double sc = s.scale[star];
+        for (int d = 0; d < s.nd; d += 2) {
+            const double2 g = curand_normal2_double(&st);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (d + e >= s.nd) break;
+                double v = s.cur_u[wk * s.nd + d + e] + sc * s.sigma[(int64_t)star * s.nd + d + e] * (e ? g.y : g.x);
+                v = fmod(v, 2.0);                       // reflect into [0, 1]
+                if (v < 0.0) v += 2.0;
+                if (v > 1.0) v = 2.0 - v;
+                s.prop_u[wk * s.nd + d + e] = v;
+            }
+        }
+    }
+}
+
+__global__ void ns_accept_kernel(ms_ns_state s) {
+    const int64_t n = (int64_t)s.S * s.Q;
+    const int ncol = s.nd + s.nder;
+    for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < n; wk += (int64_t)gridDim.x * blockDim.x) {
+        const int star = (int)(wk / s.Q);
+        const double lp = s.prop_lp[wk];
+        if (lp > s.lmin[star]) {
+            s.cur_lp[wk] = lp;
+            for (int d = 0; d < s.nd; ++d) {
+                s.cur_u[wk * s.nd + d] = s.prop_u[wk * s.nd + d];
+                s.cur_row[wk * ncol + d] = s.prop_theta[wk * s.nd + d];
+            }
+            for (int d = 0; d < s.nder; ++d) s.cur_row[wk * ncol + s.nd + d] = s.prop_der[wk * s.nder + d];
+            s.nacc[wk] += 1;
+        }
+    }
+}
+
+// update of ln Z, H and the weighted posterior moments of one star with a point of ln weight logwt
+__device__ __forceinline__ void ns_accumulate(const ms_ns_state &s, int star, double lnl, double logwt,
+                                              const double *row, int ncol, double *sh) {
+    // sh[0] = r_old, sh[1] = w  (broadcast from thread 0)
+    if (threadIdx.x == 0) {
+        const double lz = s.logz[star], lz_new = logaddexp_d(lz, logwt);
+        double h = s.hacc[star] * exp(lz - lz_new) + exp(logwt - lz_new) * lnl;
+        if (lz == -ms_inf()) h = exp(logwt - lz_new) * lnl;
+        s.hacc[star] = h;
+        s.logz[star] = lz_new;
+        const double m_old = s.wmax[star], m_new = fmax(m_old, logwt);
+        const double r_old = (m_old == -ms_inf()) ? 0.0 : exp(m_old - m_new);
+        const double w = exp(logwt - m_new);
+        s.wmax[star] = m_new;
+        s.wtot[star] = s.wtot[star] * r_old + w;
+        sh[0] = r_old; sh[1] = w;
+    }
+    __syncthreads();
+    const double r_old = sh[0], w = sh[1];
+    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+        double v = row[c];
+        if (!(fabs(v) < 1e300)) v = 0.0;
+        const int64_t at = (int64_t)star * ncol + c;
+        s.wsum[at] = s.wsum[at] * r_old + w * v;
+        s.wsq[at] = s.wsq[at] * r_old + w * v * v;
+    }
+    __syncthreads();
+}
+
+// block-wide arg-min and max of lp[0..K)
+__device__ __forceinline__ void ns_minmax(const double *lp, int K, double *sv, int *si, double &vmin, int &imin, double &vmax) {
+    double mn = ms_inf(), mx = -ms_inf();
+    int im = 0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const double v = lp[k];
+        if (v < mn) { mn = v; im = k; }
+        mx = fmax(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double omn = __shfl_xor_sync(0xffffffffu, mn, o);
+        const int oim = __shfl_xor_sync(0xffffffffu, im, o);
+        const double omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        if (omn < mn || (omn == mn && oim < im)) { mn = omn; im = oim; }
+        mx = fmax(mx, omx);
+    }
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sv[w] = mn; si[w] = im; sv[32 + w] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < nw; ++i) {
+            if (sv[i] < sv[0] || (sv[i] == sv[0] && si[i] < si[0])) { sv[0] = sv[i]; si[0] = si[i]; }
+            sv[32] = fmax(sv[32], sv[32 + i]);
+        }
+    }
+    __syncthreads();
+    vmin = sv[0]; imin = si[0]; vmax = sv[32];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(128)
+ns_consume_kernel(ms_ns_state s, uint64_t seed) {
+    extern __shared__ double sm[];
+    const int star = blockIdx.x;
+    const uint64_t round = *s.rng_round;
+    const int K = s.K, Q = s.Q, nd = s.nd, ncol = s.nd + s.nder;
+    double *lp = sm;                       // K live ln-probabilities
+    double *sv = lp + K;                   // 64 reduction slots
+    double *sh = sv + 64;                  // 4 broadcast slots
+    int *si = reinterpret_cast<int *>(sh + 4);
+    const int64_t lbase = (int64_t)star * K;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) lp[k] = s.live_lp[lbase + k];
+    __syncthreads();
+    const double log_shrink = log1p(-exp(-1.0 / K));
+    bool done = s.done[star] != 0;
+    int nacc_tot = 0;
+    if (!done) {
+        if (threadIdx.x == 0 && round > 0) s.ncall[star] += (int64_t)Q * s.walks;     // the walk steps of this round
+        for (int q = 0; q < Q; ++q) {
+            const int64_t wk = (int64_t)star * Q + q;
+            nacc_tot += s.nacc[wk];
+            double lmin, lmax; int w;
+            ns_minmax(lp, K, sv, si, lmin, w, lmax);
+            const double lpq = s.cur_lp[wk];
+            if (!(s.nacc[wk] > 0 && lpq > lmin)) continue;          // never moved, or overtaken by the threshold
+            const int64_t it = s.niter[star];
+            const double logvol = -((double)it + 1.0) / K;
+            const double logwt = lmin + (logvol + 1.0 / K + log_shrink);
+            const double *row_w = s.live_row + (lbase + w) * ncol;
+            if (s.dead && it < s.dead_cap) {                        // optional dead-point record
+                double *o = s.dead + ((int64_t)star * s.dead_cap + it) * (ncol + 3);
+                for (int c = threadIdx.x; c < ncol; c += blockDim.x) o[c] = row_w[c];
+                if (threadIdx.x == 0) { o[ncol] = lmin; o[ncol + 1] = logvol; o[ncol + 2] = logwt; }
+            }
+            ns_accumulate(s, star, lmin, logwt, row_w, ncol, sh);
+            // the candidate replaces the worst live point
+            for (int c = threadIdx.x; c < ncol; c += blockDim.x) s.live_row[(lbase + w) * ncol + c] = s.cur_row[wk * ncol + c];
+            for (int d = threadIdx.x; d < nd; d += blockDim.x) s.live_u[(lbase + w) * nd + d] = s.cur_u[wk * nd + d];
+            if (threadIdx.x == 0) { lp[w] = lpq; s.live_lp[lbase + w] = lpq; s.niter[star] = it + 1; }
+            __syncthreads();
+            lmax = fmax(lmax, lpq);
+            const double lz = s.logz[star];
+            const double dl = logaddexp_d(lz, lmax + logvol) - lz;
+            if (dl < s.dlogz || it + 1 >= s.maxiter) { done = true; break; }
+        }
+        if (threadIdx.x == 0) {
+            s.done[star] = done ? 1 : 0;
+            // dynesty's rwalk scale update towards 50 % acceptance
+            const double facc = (double)nacc_tot / ((double)Q * s.walks);
+            double sc = s.scale[star] * exp((facc - 0.5) / nd / 0.5);
+            s.scale[star] = fmin(fmax(sc, 1e-4), 10.0);
+        }
+    }
+    __syncthreads();
+    // live-point spread per dimension (step size of the next round)
+    for (int d = 0; d < nd; ++d) {
+        double a = 0.0, b = 0.0;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) { const double v = s.live_u[(lbase + k) * nd + d]; a += v; b += v * v; }
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = a; sv[32 + (threadIdx.x >> 5)] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { sv[0] += sv[i]; sv[32] += sv[32 + i]; }
+            const double mean = sv[0] / K;
+            const double var = fmax((sv[32] - K * mean * mean) / (K - 1), 0.0);
+            s.sigma[(int64_t)star * nd + d] = fmax(sqrt(var), 1e-12);
+        }
+        __syncthreads();
+    }
+    // threshold and restart points of the next round: random live points other than the worst
+    double lmin, lmax; int w;
+    ns_minmax(lp, K, sv, si, lmin, w, lmax);
+    if (threadIdx.x == 0) s.lmin[star] = lmin;
+    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+        const int64_t wk = (int64_t)star * Q + q;
+        curandStatePhilox4_32_10_t st;
+        curand_init(seed ^ 0x9e3779b97f4a7c15ull, (unsigned long long)wk, round * 4ull, &st);
+        int j = (int)(curand(&st) % (unsigned)(K - 1));
+        if (j >= w) ++j;
+        s.cur_lp[wk] = lp[j];
+        s.nacc[wk] = 0;
+        for (int d = 0; d < nd; ++d) s.cur_u[wk * nd + d] = s.live_u[(lbase + j) * nd + d];
+        for (int c = 0; c < ncol; ++c) s.cur_row[wk * ncol + c] = s.live_row[(lbase + j) * ncol + c];
+    }
+}
+
+__global__ void ns_tick_kernel(uint64_t *counter) { *counter += 1; }
+
+__global__ void __launch_bounds__(128)
+ns_finalize_kernel(ms_ns_state s) {
+    __shared__ double sh[4];
+    const int star = blockIdx.x;
+    const int K = s.K, ncol = s.nd + s.nder;
+    const double logvol_f = -((double)s.niter[star]) / K - log((double)K);
+    for (int k = 0; k < K; ++k) {
+        const double l = s.live_lp[(int64_t)star * K + k];
+        ns_accumulate(s, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, sh);
+    }
+}
+
+int check_state(const ms_ns_state *s) {
+    if (!s || s->S < 1 || s->K < 2 || s->Q < 1 || s->nd < 1 || s->nd > MS_NPARAM || s->nder < 0 || s->walks < 1 ||
+        !s->live_u || !s->live_lp || !s->live_row || !s->cur_u || !s->cur_lp || !s->cur_row || !s->prop_u ||
+        !s->prop_lp || !s->prop_theta || !s->nacc || !s->lmin || !s->sigma || !s->scale || !s->logz || !s->hacc ||
+        !s->wmax || !s->wtot || !s->wsum || !s->wsq || !s->niter || !s->ncall || !s->done || !s->rng_round ||
+        (s->nder && !s->prop_der)) {
+        ms_set_error("ms_ns_state is incomplete");
+        return MS_EINVAL;
+    }
+    return MS_OK;
+}
+
+}  // namespace
+
+extern "C" int ms_ns_propose(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t step, void *stream) {
+    int rc = check_state(s);
+    if (rc || !ctx) return rc ? rc : MS_EINVAL;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = (int64_t)s->S * s->Q;
+    int64_t blocks = (n + 127) / 128, cap = (int64_t)ctx->sm_count * 16;
+    ns_propose_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(*s, seed, step);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_ns_accept(ms_ctx *ctx, const ms_ns_state *s, void *stream) {
+    int rc = check_state(s);
+    if (rc || !ctx) return rc ? rc : MS_EINVAL;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = (int64_t)s->S * s->Q;
+    int64_t blocks = (n + 127) / 128, cap = (int64_t)ctx->sm_count * 16;
+    ns_accept_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(*s);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, void *stream) {
+    int rc = check_state(s);
+    if (rc || !ctx) return rc ? rc : MS_EINVAL;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)(s->K + 64 + 4) * sizeof(double) + 64 * sizeof(int);
+    ns_consume_kernel<<<(unsigned)s->S, 128, smem, (cudaStream_t)stream>>>(*s, seed);
+    ns_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s->rng_round);
+    ctx->launches += 2;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream) {
+    int rc = check_state(s);
+    if (rc || !ctx) return rc ? rc : MS_EINVAL;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    ns_finalize_kernel<<<(unsigned)s->S, 128, 0, (cudaStream_t)stream>>>(*s);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}

@@ -203,14 +203,15 @@ class Engine(object):
         return Flags(int(spec), int(phot), int(modpoly), int(ageweight), int(mistdif), int(n_pc))
 
     def lnlike_batch(self, theta, colmap, fixed, flags, star_slot=None, want_derived=True,
-                     want_brackets=False, out=None):
+                     want_brackets=False, out=None, derived_out=None):
         """theta[B,ndim] (GPU f64 tensor or array) -> (lnL[B], derived[B,13] | None, brackets | None)."""
         th = self._dev(theta)
         B, ndim = th.shape
         lnl = out if out is not None else torch.empty((B,), dtype=torch.float64, device=self.device)
         iso = _lib.PARAM_IDS['EEP'] in list(colmap) or not np.isnan(fixed[_lib.PARAM_IDS['EEP']])
-        der = torch.empty((B, _lib.MS_NDERIVED), dtype=torch.float64, device=self.device) \
-            if (want_derived and iso) else None
+        der = derived_out if derived_out is not None else (
+            torch.empty((B, _lib.MS_NDERIVED), dtype=torch.float64, device=self.device)
+            if (want_derived and iso) else None)
         br = torch.empty((B, 4), dtype=torch.int32, device=self.device) if (want_brackets and iso) else None
         slots = None
         if star_slot is not None:

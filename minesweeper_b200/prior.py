@@ -136,12 +136,12 @@ class prior(object):
         return out
 
     # ---- batched entry points --------------------------------------------------------------
-    def priortrans_batch(self, u):
+    def priortrans_batch(self, u, out=None):
         """u[B, ndim] in the unit cube (GPU tensor or array) -> theta[B, ndim] GPU tensor."""
         eng = self.engine
         ut = eng._dev(u)
         B = ut.shape[0]
-        theta = torch.empty_like(ut)
+        theta = out if out is not None else torch.empty_like(ut)
         with torch.cuda.device(eng.device):
             check(eng.lib.ms_prior_transform(eng._ctx, ut.data_ptr(), B, self.ndim, self._cols,
                                              theta.data_ptr(), eng._stream()))

@@ -383,6 +383,138 @@ class BatchedNestedSampler(object):
                     converged=out['converged'].cpu().numpy(), graph_replays=total, graph_captures=ncapt)
 
 
+class QueuedNestedSampler(object):
+    """Static nested sampling with a proposal queue, bookkeeping in CUDA kernels (csrc/sampler.cu).
+
+    Each star owns ``queue`` random-walk walkers; a round advances all walkers of all stars by
+    ``walks`` steps (one batched prior-transform / likelihood / ln-prior call per step) and then
+    ``ns_consume_kernel`` (one CTA per star) uses the walkers' end points in order, each one
+    replacing the then-worst live point if it is still above the threshold -- dynesty's
+    ``queue_size`` scheme.  ``queue > 1`` is what makes a *single* star fast on a GPU (the
+    sequential depth drops from ~niter to ~niter / queue rounds); ``queue = 1`` with many stars is
+    the catalog mode.  One round is captured in a CUDA graph and replayed; the RNG stream is
+    driven by a device-side round counter so replays draw fresh numbers.
+    """
+
+    def __init__(self, likeobj, priorobj, nstars=1, nlive=150, walks=5, queue=32, dlogz=0.01, maxiter=100000,
+                 seed=0, star_plx=None, store_samples=False, dead_cap=20000):
+        if not likeobj.iso_bool:
+            raise NotImplementedError('the queued sampler tracks the derived MIST block (isochrone fits)')
+        self.L, self.P = likeobj, priorobj
+        self.eng = likeobj.engine
+        self.dev = self.eng.device
+        self.S, self.K, self.Q, self.walks = int(nstars), int(nlive), int(queue), int(walks)
+        self.nd, self.nder = likeobj.ndim, _lib.MS_NDERIVED
+        self.dlogz, self.maxiter, self.seed = float(dlogz), int(maxiter), int(seed)
+        self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
+        self.store, self.dead_cap = bool(store_samples), int(dead_cap)
+
+    def run(self, check_every=4, verbose=False):
+        import ctypes as C
+        S, K, Q, nd, nder, dev = self.S, self.K, self.Q, self.nd, self.nder, self.dev
+        ncol = nd + nder
+        f64 = torch.float64
+        eng, lib = self.eng, self.eng.lib
+        gen = torch.Generator(device=dev).manual_seed(self.seed)
+        z = lambda *shape, dt=f64: torch.zeros(*shape, dtype=dt, device=dev)
+        # ---- initial live points (eager; redrawn until lnprob is finite) ----
+        star_k = torch.arange(S, device=dev, dtype=torch.int32).repeat_interleave(K)
+        per_star = S > 1
+
+        def lnprob_eager(u, slots):
+            th = self.P.priortrans_batch(u)
+            lnl, der, _ = eng.lnlike_batch(th, self.L._colmap, self.L._fixed, self.L._flags,
+                                           star_slot=slots if per_star else None, want_derived=True)
+            lp = self.P.lnprob_batch(th, lnl, der, star_slot=slots if self.star_plx is not None else None,
+                                     star_plx=self.star_plx)
+            return lp, th, der
+        U = torch.rand(S * K, nd, generator=gen, device=dev, dtype=f64)
+        lp, th, der = lnprob_eager(U, star_k)
+        for _ in range(50):
+            bad = ~torch.isfinite(lp)
+            if not bool(bad.any()):
+                break
+            idx = bad.nonzero(as_tuple=True)[0]
+            un = torch.rand(len(idx), nd, generator=gen, device=dev, dtype=f64)
+            lpn, thn, dern = lnprob_eager(un, star_k[idx])
+            U[idx], lp[idx], th[idx], der[idx] = un, lpn, thn, dern
+        if bool((~torch.isfinite(lp)).any()):
+            raise RuntimeError('could not draw live points with finite lnprob from the prior')
+        t = dict(live_u=U.contiguous(), live_lp=lp.contiguous(), live_row=torch.cat([th, der], 1).contiguous(),
+                 cur_u=z(S * Q, nd), cur_lp=z(S * Q), cur_row=z(S * Q, ncol), prop_u=z(S * Q, nd),
+                 prop_lp=z(S * Q), prop_theta=z(S * Q, nd), prop_der=z(S * Q, nder), lnl=z(S * Q),
+                 nacc=z(S * Q, dt=torch.int32), lmin=z(S), sigma=z(S, nd), scale=torch.ones(S, dtype=f64, device=dev),
+                 logz=torch.full((S,), -float('inf'), dtype=f64, device=dev), hacc=z(S),
+                 wmax=torch.full((S,), -float('inf'), dtype=f64, device=dev), wtot=z(S), wsum=z(S, ncol), wsq=z(S, ncol),
+                 niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), done=z(S, dt=torch.int32),
+                 rng_round=z(1, dt=torch.int64))
+        if self.store:
+            t['dead'] = z(S, self.dead_cap, ncol + 3)
+        st = _lib.NsState()
+        st.S, st.K, st.Q, st.nd, st.nder, st.walks = S, K, Q, nd, nder, self.walks
+        st.maxiter, st.dead_cap, st.dlogz = self.maxiter, self.dead_cap if self.store else 0, self.dlogz
+        for name, _ in _lib.NsState._fields_[9:]:
+            setattr(st, name, t[name].data_ptr() if name in t else None)
+        walker_slot = torch.arange(S, device=dev, dtype=torch.int32).repeat_interleave(Q).contiguous()
+        seed = C.c_uint64(self.seed * 7919 + 17)
+        stream = lambda: eng._stream()
+
+        def consume():
+            _lib.check(lib.ms_ns_consume(eng._ctx, C.byref(st), seed, stream()))
+
+        def round_():
+            for step in range(self.walks):
+                _lib.check(lib.ms_ns_propose(eng._ctx, C.byref(st), seed, C.c_uint64(step), stream()))
+                self.P.priortrans_batch(t['prop_u'], out=t['prop_theta'])
+                eng.lnlike_batch(t['prop_theta'], self.L._colmap, self.L._fixed, self.L._flags,
+                                 star_slot=walker_slot if per_star else None, want_derived=True,
+                                 out=t['lnl'], derived_out=t['prop_der'])
+                self.P.lnprob_batch(t['prop_theta'], t['lnl'], t['prop_der'], out=t['prop_lp'],
+                                    star_slot=walker_slot if self.star_plx is not None else None,
+                                    star_plx=self.star_plx)
+                _lib.check(lib.ms_ns_accept(eng._ctx, C.byref(st), stream()))
+            consume()
+
+        with torch.cuda.device(dev):
+            consume()                                     # bootstrap: spread, threshold, first restart points
+            t['scale'].fill_(1.0)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                round_()                                  # warm-up (scratch allocation), a real round
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                round_()
+            rounds = 2
+            max_rounds = self.maxiter + 16
+            while rounds < max_rounds:
+                for _ in range(check_every):
+                    graph.replay()
+                rounds += check_every
+                ndone = int(t['done'].sum().item())
+                if verbose:
+                    print('round %d: %d / %d stars done' % (rounds, ndone, S))
+                if ndone == S:
+                    break
+            _lib.check(lib.ms_ns_finalize(eng._ctx, C.byref(st), stream()))
+            torch.cuda.synchronize(dev)
+        mean = t['wsum'] / t['wtot'][:, None]
+        var = (t['wsq'] / t['wtot'][:, None] - mean * mean).clamp_min(0.0)
+        H = t['hacc'] - t['logz']
+        res = dict(logz=t['logz'].cpu().numpy(), logzerr=torch.sqrt(H.clamp_min(0.0) / K).cpu().numpy(),
+                   information=H.cpu().numpy(), niter=t['niter'].cpu().numpy(), ncall=t['ncall'].cpu().numpy(),
+                   names=list(self.L.fitpars_i) + list(_lib.DERIVED_NAMES), mean=mean.cpu().numpy(),
+                   std=torch.sqrt(var).cpu().numpy(), converged=(t['done'] != 0).cpu().numpy(), rounds=rounds,
+                   live_theta=t['live_row'].reshape(S, K, ncol)[:, :, :nd].cpu().numpy(),
+                   live_lnprob=t['live_lp'].reshape(S, K).cpu().numpy())
+        if self.store:
+            d = t['dead'].cpu().numpy()
+            res['dead'] = [d[s_, :min(int(res['niter'][s_]), self.dead_cap)] for s_ in range(S)]
+        return res
+
+
 def write_samples_file(path, res, star=0):
     """Dead points of one star in the reference's samples-file layout (header fitstar.py:235-242:
     ``Iter <pars...> log(lk) log(vol) log(wt) h nc log(z) delta(log(z))``); needs store_samples."""

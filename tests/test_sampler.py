@@ -108,3 +108,46 @@ def test_graphed_sampler_agrees_with_eager():
     sd = eager['std'][:, :nd].mean(0)
     assert np.all(np.abs(graphed['mean'][:, :nd].mean(0) - eager['mean'][:, :nd].mean(0)) < 0.3 * sd + 1e-3)
     assert np.all(np.abs(graphed['std'][:, :nd].mean(0) / sd - 1.0) < 0.3)
+
+
+def test_queued_sampler_single_star_matches_monte_carlo():
+    """Proposal-queue sampler (bookkeeping in CUDA kernels, one CTA per star) on a single star
+    and on replicas: evidence vs brute-force prior Monte-Carlo, posterior moments, dead points."""
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200.sampler import QueuedNestedSampler
+    fitargs, fitpars, runbools, priordict = _problem()
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    gen = torch.Generator(device=L.engine.device).manual_seed(7)
+    lw, ths = [], []
+    for _ in range(8):
+        u = torch.rand(1 << 18, L.ndim, generator=gen, device=L.engine.device, dtype=torch.float64)
+        th = P.priortrans_batch(u)
+        lnl, der, _ = L.lnlike_batch(th)
+        lw.append(P.lnprob_batch(th, lnl, der)); ths.append(th)
+    lw, ths = torch.cat(lw), torch.cat(ths)
+    logz_mc = float(torch.logsumexp(lw, 0) - np.log(len(lw)))
+    w = torch.exp(lw - lw.max()); w = w / w.sum()
+    mean_mc = (w[:, None] * ths).sum(0).cpu().numpy()
+    std_mc = torch.sqrt((w[:, None] * (ths - torch.as_tensor(mean_mc, device=ths.device)) ** 2).sum(0)).cpu().numpy()
+    nd = L.ndim
+    # one star, 32 queued walkers
+    one = QueuedNestedSampler(L, P, nstars=1, nlive=150, walks=10, queue=32, dlogz=0.05, seed=3, store_samples=True).run()
+    assert one['converged'].all() and one['niter'][0] > 300
+    assert abs(one['logz'][0] - logz_mc) < 5 * max(one['logzerr'][0], 0.05) + 0.2, (one['logz'], logz_mc)
+    assert one['rounds'] < one['niter'][0] / 4                      # the queue cut the sequential depth
+    dead = one['dead'][0]
+    assert dead.shape == (one['niter'][0], nd + 13 + 3)
+    assert np.all(np.diff(dead[:, nd + 13]) >= 0)                  # dead-point lnprob is non-decreasing
+    # replicas in lock step
+    S = 8
+    L.engine.set_stars_phot(np.tile([[fitargs['obs_phot'][b][0] for b in L.engine.bands]], (S, 1)),
+                            np.tile([[fitargs['obs_phot'][b][1] for b in L.engine.bands]], (S, 1)))
+    res = QueuedNestedSampler(L, P, nstars=S, nlive=150, walks=10, queue=8, dlogz=0.05, seed=4).run()
+    assert res['converged'].all()
+    err = np.maximum(res['logzerr'], 0.05)
+    assert np.all(np.abs(res['logz'] - logz_mc) < 5 * err + 0.2), (res['logz'], logz_mc)
+    m_ns = res['mean'][:, :nd].mean(0)
+    assert np.all(np.abs(m_ns - mean_mc) < 0.35 * std_mc + 1e-3), (m_ns, mean_mc, std_mc)
+    assert np.all(np.abs(res['std'][:, :nd].mean(0) / std_mc - 1.0) < 0.35)

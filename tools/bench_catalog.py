@@ -73,6 +73,7 @@ def main():
     ap.add_argument('--maxiter', type=int, default=20000)
     ap.add_argument('--small-grid', action='store_true')
     ap.add_argument('--eager', action='store_true', help='use the eager sampler loop instead of the CUDA-graph one')
+    ap.add_argument('--queued', type=int, default=0, help='use the kernel-bookkeeping sampler with this queue size')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -105,7 +106,15 @@ def main():
     torch.cuda.synchronize()
     l0 = L.engine.launch_count()
     t0 = time.perf_counter()
-    res = ns.run() if args.eager else ns.run_graphed()
+    if args.queued:
+        from minesweeper_b200.sampler import QueuedNestedSampler
+        ns = QueuedNestedSampler(L, P, nstars=S, nlive=args.nlive, walks=args.walks, queue=args.queued,
+                                 dlogz=args.dlogz, maxiter=args.maxiter, seed=5 + rank, star_plx=ns.star_plx)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = ns.run(check_every=64)
+    else:
+        res = ns.run() if args.eager else ns.run_graphed()
     torch.cuda.synchronize()
     el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     summary = torch.from_numpy(np.concatenate([res['logz'][:, None], res['logzerr'][:, None], res['mean'],
@@ -124,7 +133,7 @@ def main():
             metric='stars_fitted_per_hour', value=args.stars / secs * 3600.0, unit='stars/hour', n_gpus=world,
             stars=args.stars, seconds=secs, nlive=args.nlive, walks=args.walks, dlogz=args.dlogz,
             iterations_median=float(np.median(res['niter'])), iterations_max=int(res['niter'].max()),
-            converged_frac=float(res['converged'].mean()), mode='eager' if args.eager else 'cuda-graph',
+            converged_frac=float(res['converged'].mean()), mode=('queued-%d' % args.queued) if args.queued else ('eager' if args.eager else 'cuda-graph'),
             loglike_calls=float(calls.item()), loglike_evals_per_sec=float(calls.item()) / secs,
             calls_per_star=float(calls.item()) / args.stars,
             rank0_posterior_z_rms={n: float(np.sqrt(np.mean(zs[:, i] ** 2))) for i, n in enumerate(L.fitpars_i)},
