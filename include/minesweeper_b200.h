@@ -213,7 +213,7 @@ typedef struct {
     double *lmin, *sigma, *scale;                     /* [S], [S][nd], [S]                           */
     double *logz, *hacc, *wmax, *wtot, *wsum, *wsq;   /* evidence / information / posterior moments  */
     int64_t *niter, *ncall;                           /* [S] iterations, likelihood calls            */
-    int32_t *done;                                    /* [S]                                         */
+    int32_t *done;                                    /* [S] 0 running, 1 converged, 2 finalised     */
     double *dead;                                     /* [S][dead_cap][nd+nder+3] or NULL            */
     uint64_t *rng_round;                              /* device counter of completed rounds (graph-replay safe RNG stream) */
 } ms_ns_state;
@@ -222,6 +222,7 @@ int ms_ns_propose(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t ste
 int ms_ns_accept(ms_ctx *ctx, const ms_ns_state *s, void *stream);
 /* consumes the queue, prepares the next round and advances rng_round */
 int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, void *stream);
+/* adds the remaining live points of every star with done == 1 and marks it 2 */
 int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
 
 /* Number of kernel launches issued by this ctx so far (bench bookkeeping). */

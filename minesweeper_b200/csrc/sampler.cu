@@ -141,6 +141,7 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
     __syncthreads();
     const double log_shrink = log1p(-exp(-1.0 / K));
     bool done = s.done[star] != 0;
+    const int done_in = s.done[star];
     int nacc_tot = 0;
     if (!done) {
         if (threadIdx.x == 0 && round > 0) s.ncall[star] += (int64_t)Q * s.walks;     // the walk steps of this round
@@ -173,6 +174,7 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
         }
         if (threadIdx.x == 0) {
             s.done[star] = done ? 1 : 0;
+            (void)done_in;
             // dynesty's rwalk scale update towards 50 % acceptance
             const double facc = (double)nacc_tot / ((double)Q * s.walks);
             double sc = s.scale[star] * exp((facc - 0.5) / nd / 0.5);
@@ -218,12 +220,14 @@ __global__ void __launch_bounds__(128)
 ns_finalize_kernel(ms_ns_state s) {
     __shared__ double sh[4];
     const int star = blockIdx.x;
+    if (s.done[star] != 1) return;                     // only stars that finished and are not yet finalised
     const int K = s.K, ncol = s.nd + s.nder;
     const double logvol_f = -((double)s.niter[star]) / K - log((double)K);
     for (int k = 0; k < K; ++k) {
         const double l = s.live_lp[(int64_t)star * K + k];
         ns_accumulate(s, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, sh);
     }
+    if (threadIdx.x == 0) s.done[star] = 2;
 }
 
 int check_state(const ms_ns_state *s) {

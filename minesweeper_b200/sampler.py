@@ -409,7 +409,7 @@ class QueuedNestedSampler(object):
         self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
         self.store, self.dead_cap = bool(store_samples), int(dead_cap)
 
-    def run(self, check_every=4, verbose=False):
+    def run(self, check_every=4, verbose=False, min_compact=512):
         import ctypes as C
         S, K, Q, nd, nder, dev = self.S, self.K, self.Q, self.nd, self.nder, self.dev
         ncol = nd + nder
@@ -450,66 +450,109 @@ class QueuedNestedSampler(object):
                  rng_round=z(1, dt=torch.int64))
         if self.store:
             t['dead'] = z(S, self.dead_cap, ncol + 3)
-        st = _lib.NsState()
-        st.S, st.K, st.Q, st.nd, st.nder, st.walks = S, K, Q, nd, nder, self.walks
-        st.maxiter, st.dead_cap, st.dlogz = self.maxiter, self.dead_cap if self.store else 0, self.dlogz
-        for name, _ in _lib.NsState._fields_[9:]:
-            setattr(st, name, t[name].data_ptr() if name in t else None)
-        walker_slot = torch.arange(S, device=dev, dtype=torch.int32).repeat_interleave(Q).contiguous()
+        orig = torch.arange(S, device=dev)
+        out = dict(logz=z(S), H=z(S), niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), mean=z(S, ncol),
+                   std=z(S, ncol), converged=z(S, dt=torch.bool))
         seed = C.c_uint64(self.seed * 7919 + 17)
         stream = lambda: eng._stream()
+        per_star_keys = ('live_u', 'live_lp', 'live_row', 'lmin', 'sigma', 'scale', 'logz', 'hacc', 'wmax', 'wtot',
+                         'wsum', 'wsq', 'niter', 'ncall', 'done', 'dead')
+        walker_keys = ('cur_u', 'cur_lp', 'cur_row', 'prop_u', 'prop_lp', 'prop_theta', 'prop_der', 'lnl', 'nacc')
 
-        def consume():
-            _lib.check(lib.ms_ns_consume(eng._ctx, C.byref(st), seed, stream()))
+        def harvest(mask):
+            """Copy the summaries of the (finalised) stars in ``mask`` to the catalog-wide outputs."""
+            o = orig[mask]
+            mean = t['wsum'][mask] / t['wtot'][mask][:, None]
+            var = (t['wsq'][mask] / t['wtot'][mask][:, None] - mean * mean).clamp_min(0.0)
+            out['logz'][o] = t['logz'][mask]; out['H'][o] = t['hacc'][mask] - t['logz'][mask]
+            out['niter'][o] = t['niter'][mask]; out['ncall'][o] = t['ncall'][mask]
+            out['mean'][o] = mean; out['std'][o] = torch.sqrt(var)
 
-        def round_():
-            for step in range(self.walks):
-                _lib.check(lib.ms_ns_propose(eng._ctx, C.byref(st), seed, C.c_uint64(step), stream()))
-                self.P.priortrans_batch(t['prop_u'], out=t['prop_theta'])
-                eng.lnlike_batch(t['prop_theta'], self.L._colmap, self.L._fixed, self.L._flags,
-                                 star_slot=walker_slot if per_star else None, want_derived=True,
-                                 out=t['lnl'], derived_out=t['prop_der'])
-                self.P.lnprob_batch(t['prop_theta'], t['lnl'], t['prop_der'], out=t['prop_lp'],
-                                    star_slot=walker_slot if self.star_plx is not None else None,
-                                    star_plx=self.star_plx)
-                _lib.check(lib.ms_ns_accept(eng._ctx, C.byref(st), stream()))
-            consume()
-
+        rounds, captures = 0, 0
+        bootstrap = True
         with torch.cuda.device(dev):
-            consume()                                     # bootstrap: spread, threshold, first restart points
-            t['scale'].fill_(1.0)
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                round_()                                  # warm-up (scratch allocation), a real round
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                round_()
-            rounds = 2
-            max_rounds = self.maxiter + 16
-            while rounds < max_rounds:
-                for _ in range(check_every):
-                    graph.replay()
-                rounds += check_every
-                ndone = int(t['done'].sum().item())
-                if verbose:
-                    print('round %d: %d / %d stars done' % (rounds, ndone, S))
-                if ndone == S:
+            while True:
+                Sc = len(orig)
+                st = _lib.NsState()
+                st.S, st.K, st.Q, st.nd, st.nder, st.walks = Sc, K, Q, nd, nder, self.walks
+                st.maxiter, st.dead_cap, st.dlogz = self.maxiter, self.dead_cap if self.store else 0, self.dlogz
+                for name, _ in _lib.NsState._fields_[9:]:
+                    setattr(st, name, t[name].data_ptr() if name in t else None)
+                walker_slot = orig.to(torch.int32).repeat_interleave(Q).contiguous()
+
+                def consume():
+                    _lib.check(lib.ms_ns_consume(eng._ctx, C.byref(st), seed, stream()))
+
+                def round_():
+                    for step in range(self.walks):
+                        _lib.check(lib.ms_ns_propose(eng._ctx, C.byref(st), seed, C.c_uint64(step), stream()))
+                        self.P.priortrans_batch(t['prop_u'], out=t['prop_theta'])
+                        eng.lnlike_batch(t['prop_theta'], self.L._colmap, self.L._fixed, self.L._flags,
+                                         star_slot=walker_slot if per_star else None, want_derived=True,
+                                         out=t['lnl'], derived_out=t['prop_der'])
+                        self.P.lnprob_batch(t['prop_theta'], t['lnl'], t['prop_der'], out=t['prop_lp'],
+                                            star_slot=walker_slot if self.star_plx is not None else None,
+                                            star_plx=self.star_plx)
+                        _lib.check(lib.ms_ns_accept(eng._ctx, C.byref(st), stream()))
+                    consume()
+
+                if bootstrap:                             # spread, threshold, first restart points
+                    consume()
+                    t['scale'].fill_(1.0)
+                    bootstrap = False
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    round_()                              # warm-up (scratch allocation), a real round
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    round_()
+                rounds += 2
+                captures += 1
+                while True:
+                    for _ in range(check_every):
+                        graph.replay()
+                    rounds += check_every
+                    nrun = int((t['done'] == 0).sum().item())
+                    if verbose:
+                        print('round %d: %d / %d stars running (working set %d)' % (rounds, nrun, S, Sc))
+                    if nrun == 0 or (Sc > min_compact and nrun * 2 <= Sc) or rounds >= self.maxiter + 16:
+                        break
+                del graph
+                if rounds >= self.maxiter + 16:
+                    t['done'].clamp_(min=1)               # give up on the rest: finalise as they are
+                    nrun = 0
+                out['converged'][orig[t['done'] != 0]] = rounds < self.maxiter + 16
+                _lib.check(lib.ms_ns_finalize(eng._ctx, C.byref(st), stream()))
+                fin = t['done'] == 2
+                harvest(fin)
+                if self.store and 'dead' in t:
+                    pass                                  # dead points are read back below (single working set)
+                if nrun == 0:
                     break
-            _lib.check(lib.ms_ns_finalize(eng._ctx, C.byref(st), stream()))
+                keep = (t['done'] == 0).nonzero(as_tuple=True)[0]
+                nk = len(keep)
+                for kname in ('live_u', 'live_lp', 'live_row'):          # [S*K, ...] blocks of K rows per star
+                    v = t[kname]
+                    t[kname] = v.reshape((Sc, K) + tuple(v.shape[1:]))[keep].reshape((nk * K,) + tuple(v.shape[1:])).contiguous()
+                for kname in walker_keys:                                 # [S*Q, ...] blocks of Q rows per star
+                    v = t[kname]
+                    t[kname] = v.reshape((Sc, Q) + tuple(v.shape[1:]))[keep].reshape((nk * Q,) + tuple(v.shape[1:])).contiguous()
+                for kname in per_star_keys:                               # [S, ...]
+                    if kname in t and not kname.startswith('live'):
+                        t[kname] = t[kname][keep].contiguous()
+                orig = orig[keep]
             torch.cuda.synchronize(dev)
-        mean = t['wsum'] / t['wtot'][:, None]
-        var = (t['wsq'] / t['wtot'][:, None] - mean * mean).clamp_min(0.0)
-        H = t['hacc'] - t['logz']
-        res = dict(logz=t['logz'].cpu().numpy(), logzerr=torch.sqrt(H.clamp_min(0.0) / K).cpu().numpy(),
-                   information=H.cpu().numpy(), niter=t['niter'].cpu().numpy(), ncall=t['ncall'].cpu().numpy(),
-                   names=list(self.L.fitpars_i) + list(_lib.DERIVED_NAMES), mean=mean.cpu().numpy(),
-                   std=torch.sqrt(var).cpu().numpy(), converged=(t['done'] != 0).cpu().numpy(), rounds=rounds,
-                   live_theta=t['live_row'].reshape(S, K, ncol)[:, :, :nd].cpu().numpy(),
-                   live_lnprob=t['live_lp'].reshape(S, K).cpu().numpy())
+        res = dict(logz=out['logz'].cpu().numpy(), logzerr=torch.sqrt(out['H'].clamp_min(0.0) / K).cpu().numpy(),
+                   information=out['H'].cpu().numpy(), niter=out['niter'].cpu().numpy(), ncall=out['ncall'].cpu().numpy(),
+                   names=list(self.L.fitpars_i) + list(_lib.DERIVED_NAMES), mean=out['mean'].cpu().numpy(),
+                   std=out['std'].cpu().numpy(), converged=out['converged'].cpu().numpy(), rounds=rounds,
+                   graph_captures=captures)
         if self.store:
+            if captures > 1:
+                raise RuntimeError('store_samples needs min_compact >= nstars (no compaction)')
             d = t['dead'].cpu().numpy()
             res['dead'] = [d[s_, :min(int(res['niter'][s_]), self.dead_cap)] for s_ in range(S)]
         return res

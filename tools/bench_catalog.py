@@ -23,12 +23,12 @@ NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R',
 ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
 
 
-def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed):
+def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed, queued=1):
     """Synthetic catalog of S stars on this device (truths from the prior, observations from the
     model itself, Gaia-like parallaxes) registered with the engine, and a sampler over it.
     Returns (sampler, truth_theta)."""
     import torch
-    from minesweeper_b200.sampler import BatchedNestedSampler
+    from minesweeper_b200.sampler import BatchedNestedSampler, QueuedNestedSampler
     gen = torch.Generator(device=dev).manual_seed(1000 + seed)
     truth = None
     for _ in range(20):                                            # truths with a valid MIST prediction
@@ -52,8 +52,12 @@ def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed):
     plx_obs = plx + plx_err * torch.randn(S, generator=gen, device=dev, dtype=torch.float64)
     L.engine.set_stars_phot(obs.cpu().numpy(), err.cpu().numpy())
     star_plx = torch.stack([plx_obs, plx_err], 1)
-    ns = BatchedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, dlogz=dlogz, maxiter=maxiter,
-                              seed=5 + seed, star_plx=star_plx)
+    if queued:       # bookkeeping in CUDA kernels (csrc/sampler.cu), proposal queue of `queued` walkers per star
+        ns = QueuedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, queue=queued, dlogz=dlogz,
+                                 maxiter=maxiter, seed=5 + seed, star_plx=star_plx)
+    else:            # torch-tensor bookkeeping (reference implementation of the same sampler)
+        ns = BatchedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, dlogz=dlogz, maxiter=maxiter,
+                                  seed=5 + seed, star_plx=star_plx)
     return ns, th
 
 
@@ -73,7 +77,8 @@ def main():
     ap.add_argument('--maxiter', type=int, default=20000)
     ap.add_argument('--small-grid', action='store_true')
     ap.add_argument('--eager', action='store_true', help='use the eager sampler loop instead of the CUDA-graph one')
-    ap.add_argument('--queued', type=int, default=0, help='use the kernel-bookkeeping sampler with this queue size')
+    ap.add_argument('--queued', type=int, default=1,
+                    help='walkers per star of the kernel-bookkeeping sampler; 0 = torch-tensor sampler')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -100,18 +105,14 @@ def main():
     # this rank's block of the catalog
     lo, hi = shard_bounds(args.stars, rank, world)
     S = hi - lo
-    ns, th = make_catalog_sampler(L, P, S, dev, args.nlive, args.walks, args.dlogz, args.maxiter, rank)
+    ns, th = make_catalog_sampler(L, P, S, dev, args.nlive, args.walks, args.dlogz, args.maxiter, rank,
+                                  queued=args.queued)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     l0 = L.engine.launch_count()
     t0 = time.perf_counter()
     if args.queued:
-        from minesweeper_b200.sampler import QueuedNestedSampler
-        ns = QueuedNestedSampler(L, P, nstars=S, nlive=args.nlive, walks=args.walks, queue=args.queued,
-                                 dlogz=args.dlogz, maxiter=args.maxiter, seed=5 + rank, star_plx=ns.star_plx)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         res = ns.run(check_every=64)
     else:
         res = ns.run() if args.eager else ns.run_graphed()
