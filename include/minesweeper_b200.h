@@ -210,7 +210,7 @@ typedef struct {
     double *cur_u, *cur_lp, *cur_row, *prop_u;        /* walkers: [S*Q][nd], [S*Q], [S*Q][nd+nder]   */
     const double *prop_lp, *prop_theta, *prop_der;    /* outputs of the batched lnprob at prop_u     */
     int32_t *nacc;                                    /* [S*Q] accepted steps this round             */
-    double *lmin, *sigma, *scale;                     /* [S], [S][nd], [S]                           */
+    double *lmin, *sigma, *scale;                     /* [S], [S][nd][nd] Cholesky factor of the live-point covariance, [S] */
     double *logz, *hacc, *wmax, *wtot, *wsum, *wsq;   /* evidence / information / posterior moments  */
     int64_t *niter, *ncall;                           /* [S] iterations, likelihood calls            */
     int32_t *done;                                    /* [S] 0 running, 1 converged, 2 finalised     */

@@ -34,17 +34,23 @@ __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
         curandStatePhilox4_32_10_t st;
         curand_init(seed, (unsigned long long)wk, (*s.rng_round * (uint64_t)s.walks + step) * 32ull, &st);
         const double sc = s.scale[star];
+        // step = scale * L z with L the Cholesky factor of the live-point covariance (the analogue of
+        // dynesty's rwalk proposing along the axes of the bounding ellipsoid)
+        double zv[MS_NPARAM];
         for (int d = 0; d < s.nd; d += 2) {
             const double2 g = curand_normal2_double(&st);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (d + e >= s.nd) break;
-                double v = s.cur_u[wk * s.nd + d + e] + sc * s.sigma[(int64_t)star * s.nd + d + e] * (e ? g.y : g.x);
-                v = fmod(v, 2.0);                       // reflect into [0, 1]
-                if (v < 0.0) v += 2.0;
-                if (v > 1.0) v = 2.0 - v;
-                s.prop_u[wk * s.nd + d + e] = v;
-            }
+            zv[d] = g.x;
+            if (d + 1 < s.nd) zv[d + 1] = g.y;
+        }
+        const double *Lc = s.sigma + (int64_t)star * s.nd * s.nd;
+        for (int d = 0; d < s.nd; ++d) {
+            double step = 0.0;
+            for (int e = 0; e <= d; ++e) step = fma(Lc[d * s.nd + e], zv[e], step);
+            double v = s.cur_u[wk * s.nd + d] + sc * step;
+            v = fmod(v, 2.0);                       // reflect into [0, 1]
+            if (v < 0.0) v += 2.0;
+            if (v > 1.0) v = 2.0 - v;
+            s.prop_u[wk * s.nd + d] = v;
         }
     }
 }
@@ -135,7 +141,7 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
     double *lp = sm;                       // K live ln-probabilities
     double *sv = lp + K;                   // 64 reduction slots
     double *sh = sv + 64;                  // 4 broadcast slots
-    int *si = reinterpret_cast<int *>(sh + 4);
+    int *si = reinterpret_cast<int *>(sh + 4);             // 64 ints = 32 doubles
     const int64_t lbase = (int64_t)star * K;
     for (int k = threadIdx.x; k < K; k += blockDim.x) lp[k] = s.live_lp[lbase + k];
     __syncthreads();
@@ -182,18 +188,46 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
         }
     }
     __syncthreads();
-    // live-point spread per dimension (step size of the next round)
-    for (int d = 0; d < nd; ++d) {
-        double a = 0.0, b = 0.0;
-        for (int k = threadIdx.x; k < K; k += blockDim.x) { const double v = s.live_u[(lbase + k) * nd + d]; a += v; b += v * v; }
-        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-        if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = a; sv[32 + (threadIdx.x >> 5)] = b; }
+    // covariance of the live points and its Cholesky factor (proposal shape of the next rounds);
+    // at most Q of the K live points change per round, so it is refreshed every ~16 replacements
+    const uint64_t cov_every = (uint64_t)(Q >= 16 ? 1 : 16 / Q);
+    if (round % cov_every == 0) {
+        double *mean = sv;                                   // nd <= 24 < 64 slots
+        double *cov = sm + (K + 64 + 4 + 32);                // nd * nd, after lp / sv / sh / si
+        double *lu = cov + nd * nd + nd;                     // K * nd: this star's live points, staged once
+        for (int i = threadIdx.x; i < K * nd; i += blockDim.x) lu[i] = s.live_u[lbase * nd + i];
         __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { sv[0] += sv[i]; sv[32] += sv[32 + i]; }
-            const double mean = sv[0] / K;
-            const double var = fmax((sv[32] - K * mean * mean) / (K - 1), 0.0);
-            s.sigma[(int64_t)star * nd + d] = fmax(sqrt(var), 1e-12);
+        for (int d = threadIdx.x; d < nd; d += blockDim.x) {
+            double a = 0.0;
+            for (int k = 0; k < K; ++k) a += lu[k * nd + d];
+            mean[d] = a / K;
+        }
+        __syncthreads();
+        for (int pe = threadIdx.x; pe < nd * nd; pe += blockDim.x) {
+            const int d = pe / nd, e = pe - d * nd;
+            if (e > d) { cov[pe] = 0.0; continue; }
+            double a = 0.0;
+            for (int k = 0; k < K; ++k) a += (lu[k * nd + d] - mean[d]) * (lu[k * nd + e] - mean[e]);
+            cov[pe] = a / (K - 1);
+        }
+        __syncthreads();
+        double *diag = sm + (K + 64 + 4 + 32 + nd * nd);     // variances, kept for the degenerate fallback
+        for (int d = threadIdx.x; d < nd; d += blockDim.x) diag[d] = cov[d * nd + d];
+        __syncthreads();
+        if (threadIdx.x == 0) {                              // in-place Cholesky, row by row, lower triangle
+            bool ok = true;
+            for (int i = 0; i < nd && ok; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    double a = cov[i * nd + j] + (i == j ? 1e-14 : 0.0);
+                    for (int k = 0; k < j; ++k) a -= cov[i * nd + k] * cov[j * nd + k];
+                    if (i == j) { if (!(a > 0.0)) { ok = false; break; } cov[i * nd + i] = sqrt(a); }
+                    else cov[i * nd + j] = a / cov[j * nd + j];
+                }
+            double *out = s.sigma + (int64_t)star * nd * nd;
+            for (int i = 0; i < nd; ++i)
+                for (int j = 0; j < nd; ++j)
+                    out[i * nd + j] = ok ? (j <= i ? cov[i * nd + j] : 0.0)
+                                         : (i == j ? sqrt(fmax(diag[i], 1e-24)) : 0.0);   // degenerate: diagonal
         }
         __syncthreads();
     }
@@ -272,7 +306,7 @@ extern "C" int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, v
     int rc = check_state(s);
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)(s->K + 64 + 4) * sizeof(double) + 64 * sizeof(int);
+    const size_t smem = (size_t)(s->K + 64 + 4 + 32 + s->nd * s->nd + s->nd + s->K * s->nd) * sizeof(double);   // lp, reductions, broadcast, int slots, covariance, variances, live points
     ns_consume_kernel<<<(unsigned)s->S, 128, smem, (cudaStream_t)stream>>>(*s, seed);
     ns_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s->rng_round);
     ctx->launches += 2;

@@ -28,6 +28,17 @@ import torch
 from . import _lib
 
 
+def _chol_cov(U):
+    """Cholesky factors [S, nd, nd] of the covariance of the live points U[S, K, nd] (the shape of
+    the random-walk proposal, as dynesty's rwalk uses the bounding ellipsoid)."""
+    d = U - U.mean(dim=1, keepdim=True)
+    cov = torch.matmul(d.transpose(1, 2), d) / (U.shape[1] - 1)
+    eye = torch.eye(U.shape[2], dtype=U.dtype, device=U.device)
+    L, info = torch.linalg.cholesky_ex(cov + 1e-14 * eye)
+    diag = torch.diag_embed(torch.sqrt(torch.diagonal(cov, dim1=1, dim2=2).clamp_min(1e-24)))
+    return torch.where((info == 0)[:, None, None], L, diag)
+
+
 class BatchedNestedSampler(object):
     def __init__(self, likeobj, priorobj, nstars=1, nlive=150, walks=5, dlogz=0.01, maxiter=100000,
                  seed=0, star_plx=None, store_samples=False, max_extend=20):
@@ -142,12 +153,12 @@ class BatchedNestedSampler(object):
             lcur = LP[act, j].clone()
             thcur = TH[act, j].clone()
             dcur = DER[act, j].clone() if DER is not None else None
-            sig = U[act].std(dim=1).clamp_min(1e-12) * scale[act, None]
+            sig = _chol_cov(U[act]) * scale[act, None, None]
             nacc = torch.zeros(A, dtype=torch.int64, device=dev)
             steps = 0
             while True:
                 for _ in range(self.walks):
-                    prop = ucur + sig * self._randn(A, nd)
+                    prop = ucur + torch.bmm(sig, self._randn(A, nd, 1)).squeeze(2)
                     prop = torch.remainder(prop, 2.0)                      # reflect into [0, 1]
                     prop = torch.where(prop > 1.0, 2.0 - prop, prop)
                     lpn, thn, dern = self._lnprob(prop, act)
@@ -162,7 +173,7 @@ class BatchedNestedSampler(object):
                 stuck = nacc == 0
                 if not bool(stuck.any()) or steps >= self.walks * self.max_extend:
                     break
-                sig = torch.where(stuck[:, None], sig * 0.5, sig)          # shrink and keep walking
+                sig = torch.where(stuck[:, None, None], sig * 0.5, sig)    # shrink and keep walking
             # dynesty's rwalk scale update towards 50 % acceptance
             facc = nacc.to(f64) / steps
             scale[act] = (scale[act] * torch.exp((facc - 0.5) / nd / 0.5)).clamp(1e-4, 10.0)
@@ -316,10 +327,10 @@ class BatchedNestedSampler(object):
                 j = j + (j >= w).to(j.dtype)
                 ucur, lcur, thcur = U_[star, j], LP[star, j], TH[star, j]
                 dcur = DER[star, j] if DER is not None else None
-                sig = U_.std(dim=1).clamp_min(1e-12) * st['scale'][:, None]
+                sig = _chol_cov(U_) * st['scale'][:, None, None]
                 nacc = torch.zeros(Sc, dtype=f64, device=dev)
                 for _ in range(self.walks):
-                    prop = ucur + sig * torch.randn(Sc, nd, device=dev, dtype=f64)
+                    prop = ucur + torch.bmm(sig, torch.randn(Sc, nd, 1, device=dev, dtype=f64)).squeeze(2)
                     prop = torch.remainder(prop, 2.0)
                     prop = torch.where(prop > 1.0, 2.0 - prop, prop)
                     lpn, thn, dern = lnprob_static(prop)
@@ -443,7 +454,7 @@ class QueuedNestedSampler(object):
         t = dict(live_u=U.contiguous(), live_lp=lp.contiguous(), live_row=torch.cat([th, der], 1).contiguous(),
                  cur_u=z(S * Q, nd), cur_lp=z(S * Q), cur_row=z(S * Q, ncol), prop_u=z(S * Q, nd),
                  prop_lp=z(S * Q), prop_theta=z(S * Q, nd), prop_der=z(S * Q, nder), lnl=z(S * Q),
-                 nacc=z(S * Q, dt=torch.int32), lmin=z(S), sigma=z(S, nd), scale=torch.ones(S, dtype=f64, device=dev),
+                 nacc=z(S * Q, dt=torch.int32), lmin=z(S), sigma=z(S, nd * nd), scale=torch.ones(S, dtype=f64, device=dev),
                  logz=torch.full((S,), -float('inf'), dtype=f64, device=dev), hacc=z(S),
                  wmax=torch.full((S,), -float('inf'), dtype=f64, device=dev), wtot=z(S), wsum=z(S, ncol), wsq=z(S, ncol),
                  niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), done=z(S, dt=torch.int32),
