@@ -27,6 +27,8 @@
  *   - out-of-grid / no-corner / zero-weight points follow the reference:
  *     lnL = -inf and the nine derived MIST values = +inf (likelihood.py:107-119);
  *     NaN residuals are dropped from the chi-square (nansum, :193,207).
+ *   - a ctx owns per-batch scratch buffers: use it from one host thread and one stream at a
+ *     time (calls on one stream are ordered; create one ctx per stream / thread for concurrency).
  *   - there is no CPU fallback: without a CUDA device ms_create fails with
  *     MS_ENODEV.
  */
