@@ -53,3 +53,40 @@ def test_product_does_not_import_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, flags=re.M), f
+
+
+def _build_c_smoke(tmp_path):
+    import subprocess
+    exe = str(tmp_path / 'abi_smoke')
+    libdir = os.path.join(ROOT, 'minesweeper_b200')
+    cmd = ['gcc', '-O1', '-o', exe, os.path.join(ROOT, 'tests', 'c', 'abi_smoke.c'), '-L' + libdir, '-lmsb200',
+           '-Wl,-rpath,' + libdir, '-lm']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_program_links_against_the_abi(tmp_path):
+    """A C program with nothing but include/minesweeper_b200.h compiles and links; without a GPU it
+    gets MS_ENODEV (exit code 3) instead of a fallback."""
+    import subprocess
+    import torch
+    from minesweeper_b200 import _lib
+    _lib.load()
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert 'lnL[0]' in r.stdout and 'lnL[2] = -inf' in r.stdout
+    else:
+        assert r.returncode == 3, r.stdout + r.stderr
+        assert 'no CPU fallback' in r.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_program_runs_on_gpu(tmp_path):
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'lnL[2] = -inf' in r.stdout and 'launches = 2' in r.stdout
