@@ -216,6 +216,17 @@ int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d) {
     S.twiddle_n = n1;
     if ((rc = upload(&S.twiddle64, tw.data(), tw.size()))) return rc;
     if ((rc = upload(&S.twiddle32, twf.data(), twf.size()))) return rc;
+    {   // compact per-level tables for the Stockham passes (unit-stride reads, small L1 footprint)
+        int lmax = 0;
+        while ((1 << lmax) < n1) ++lmax;
+        std::vector<float2> lev((size_t)1 << lmax, make_float2(1.f, 0.f));
+        for (int l = 1; l <= lmax; ++l)
+            for (int k = 0; k < (1 << (l - 1)); ++k) {
+                const double a = -2.0 * M_PI * (double)k / (double)(1 << l);
+                lev[((size_t)1 << (l - 1)) + k] = make_float2((float)std::cos(a), (float)std::sin(a));
+            }
+        if ((rc = upload(&S.twlev32, lev.data(), lev.size()))) return rc;
+    }
     // rotational transfer S(u) = J1(u)/u - 3 cos u / (2 u^2) + 3 sin u / (2 u^3) on u = i/32
     const int NT = 8200;
     std::vector<float> rt(NT);
@@ -290,7 +301,7 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(S.w0); cudaFree(S.b0); cudaFree(S.w1); cudaFree(S.b1); cudaFree(S.w2); cudaFree(S.b2);
     cudaFree(S.wave); cudaFree(S.a1_idx); cudaFree(S.a2_idx); cudaFree(S.a1_frac); cudaFree(S.a2_frac);
     cudaFree(S.a1_fracd); cudaFree(S.a2_fracd); cudaFree(S.twiddle32); cudaFree(S.twiddle64);
-    cudaFree(S.xms); cudaFree(S.rot_tab); spec_tc_release(ctx);
+    cudaFree(S.xms); cudaFree(S.rot_tab); cudaFree(S.twlev32); spec_tc_release(ctx);
     cudaFree(ctx->obs_mag); cudaFree(ctx->obs_err2);
     for (StarDev &s : ctx->stars) {
         cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2);

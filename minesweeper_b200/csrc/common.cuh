@@ -58,6 +58,7 @@ struct SpecNetDev {
     float2 *twiddle32 = nullptr;   // exp(-2 pi i k / n1), k < n1/2
     double2 *twiddle64 = nullptr;
     int twiddle_n = 0;
+    float2 *twlev32 = nullptr;     // per-level compact tables: level l at offset 2^(l-1), entry k = exp(-2 pi i k / 2^l), k < 2^(l-1)
     void *tc_pack = nullptr;
 };
 

@@ -65,6 +65,7 @@ struct SmoothArgs {
     const int *a1_idx, *a2_idx;
     const void *a1_frac, *a2_frac; // T
     const void *twiddle;           // T2 [n1/2]: exp(-2 pi i k / n1)
+    const void *twlev;             // float2 per-level compact tables (Stockham path)
     const float *rot_tab;          // S(u) on a uniform grid (float mode)
     // star
     int n_obs;
@@ -299,7 +300,7 @@ __device__ __forceinline__ void stockham_pass(const typename Cx<T>::type *__rest
 #pragma unroll
         for (int r = 0; r < R; ++r) v[r] = in[j + r * nb];
         if (lNs > 0) {
-            const T2 w1 = tw_get<T2, INV>(tw, k * (tw_n >> (lNs + LR)));      // exp(-+2 pi i k / (Ns R))
+            const T2 w1 = tw_get<T2, INV>(tw, (1 << (lNs + LR - 1)) + k);      // level table: exp(-+2 pi i k / (Ns R))
             if (R == 2) {
                 v[1] = cmul(v[1], w1);
             } else {
@@ -334,13 +335,15 @@ __device__ __forceinline__ int stockham_fft(typename Cx<T>::type *b0, typename C
                                             const typename Cx<T>::type *__restrict__ tw, int tw_n) {
     typedef typename Cx<T>::type T2;
     int lNs = 0, rem = L;
+    // leftover bits first (Ns = 1: no twiddles), so the last and largest radix-8 pass needs only
+    // M / 8 distinct twiddles
+    if (rem % 3 == 2) {
+        stockham_pass<T, 4, INV>(src ? b1 : b0, src ? b0 : b1, M, lNs, tw, tw_n); lNs += 2; rem -= 2; src ^= 1;
+    } else if (rem % 3 == 1) {
+        stockham_pass<T, 2, INV>(src ? b1 : b0, src ? b0 : b1, M, lNs, tw, tw_n); lNs += 1; rem -= 1; src ^= 1;
+    }
     while (rem > 0) {
-        const T2 *in = src ? b1 : b0;
-        T2 *out = src ? b0 : b1;
-        if (rem >= 3) { stockham_pass<T, 8, INV>(in, out, M, lNs, tw, tw_n); lNs += 3; rem -= 3; }
-        else if (rem == 2) { stockham_pass<T, 4, INV>(in, out, M, lNs, tw, tw_n); lNs += 2; rem -= 2; }
-        else { stockham_pass<T, 2, INV>(in, out, M, lNs, tw, tw_n); lNs += 1; rem -= 1; }
-        src ^= 1;
+        stockham_pass<T, 8, INV>(src ? b1 : b0, src ? b0 : b1, M, lNs, tw, tw_n); lNs += 3; rem -= 3; src ^= 1;
     }
     return src;
 }
@@ -355,7 +358,8 @@ __device__ void fft_filter_stockham(typename Cx<T>::type *z0, typename Cx<T>::ty
     const int L = 31 - __clz(M);
     const int where = stockham_fft<T, false>(z0, z1, 0, M, L, tw, tw_n);
     T2 *z = where ? z1 : z0;
-    const int nbf = M >> 1, tstepn = tw_n / n;
+    const int nbf = M >> 1;
+    const T2 *twn = tw + (n >> 1);                            // level log2(n): exp(-2 pi i k / n), k < n / 2
     const T inv = (T)1 / (T)M;
     for (int k = threadIdx.x; k <= nbf; k += blockDim.x) {
         if (k == 0) {
@@ -369,7 +373,7 @@ __device__ void fft_filter_stockham(typename Cx<T>::type *z0, typename Cx<T>::ty
             const T2 E = {(T)0.5 * (A.x + Bc.x), (T)0.5 * (A.y + Bc.y)};
             const T2 dif = csub(A, Bc);
             const T2 O = {(T)0.5 * dif.y, (T)-0.5 * dif.x};
-            const T2 w = tw[k * tstepn];
+            const T2 w = twn[k];
             const T2 wO = cmul(w, O);
             const T tk = inv * tf(k), tm = inv * tf(pm);
             const T2 Yk = {tk * (E.x + wO.x), tk * (E.y + wO.y)};
@@ -457,7 +461,7 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
             Transfer<T> tf;
             tf.kind = 1; tf.tab = a.rot_tab;
             tf.coef = 2.0 * M_PI * sigma / ((double)n1 * MS_CKMS * step1);
-            if (kStockham) fft_filter_stockham<T>(z, z1, n1, tf, tw, n1); else fft_filter<T>(z, n1, tf, tw, n1);
+            if (kStockham) fft_filter_stockham<T>(z, z1, n1, tf, static_cast<const T2 *>(a.twlev), n1); else fft_filter<T>(z, n1, tf, tw, n1);
             for (int i0 = threadIdx.x; i0 < npix; i0 += 4 * blockDim.x) {
                 int kk[4]; T ff[4];
 #pragma unroll
@@ -513,7 +517,7 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
                 tf.kind = 0; tf.tab = nullptr;
                 const double ndv = (double)n2 * MS_CKMS * d2;
                 tf.coef = 2.0 * M_PI * M_PI * sigma * sigma / (ndv * ndv);
-                if (kStockham) fft_filter_stockham<T>(z, z1, n2, tf, tw, n1); else fft_filter<T>(z, n2, tf, tw, n1);
+                if (kStockham) fft_filter_stockham<T>(z, z1, n2, tf, static_cast<const T2 *>(a.twlev), n1); else fft_filter<T>(z, n2, tf, tw, n1);
             }
         } else {
             mode = 1;
@@ -621,7 +625,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         sa.wave = n.wave; sa.a1_idx = n.a1_idx; sa.a2_idx = n.a2_idx;
         if (sizeof(T) == 4) { sa.a1_frac = n.a1_frac; sa.a2_frac = n.a2_frac; sa.twiddle = n.twiddle32; }
         else { sa.a1_frac = n.a1_fracd; sa.a2_frac = n.a2_fracd; sa.twiddle = n.twiddle64; }
-        sa.rot_tab = n.rot_tab;
+        sa.rot_tab = n.rot_tab; sa.twlev = n.twlev32;
         sa.n_obs = star.n_obs; sa.obs_wave = star.obs_wave; sa.obs_lnwave = star.obs_lnwave;
         sa.obs_flux = star.obs_flux; sa.obs_err2 = star.obs_err2; sa.cheb_x = star.cheb_x;
         sa.ow_min = star.wmin; sa.ow_max = star.wmax;
