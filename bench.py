@@ -22,6 +22,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tools'))
 
 METRIC = 'phot_loglike_evals_per_sec'
 UNIT = 'evals/s'
@@ -42,6 +43,8 @@ def parse():
     ap.add_argument('--small-grid', action='store_true', help='debug: 60x24x7x5 grid')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
+    ap.add_argument('--spec-batch', type=int, default=65536,
+                    help='points per GPU of the auxiliary spectrum + photometry measurement (0 = skip)')
     ap.add_argument('--catalog-stars', type=int, default=65536,
                     help='stars per GPU fitted with the batched nested sampler for the stars/hour figure (0 = skip)')
     return ap.parse_args()
@@ -258,7 +261,6 @@ def main():
     catalog = None
     if args.catalog_stars > 0:
         try:
-            sys.path.insert(0, os.path.join(ROOT, 'tools'))
             from bench_catalog import make_catalog_sampler, catalog_priordict
             from minesweeper_b200.prior import prior
             Pc = prior(fitargs, catalog_priordict(261.0 if args.small_grid else 808.0), fitpars, runbools, likeobj=L)
@@ -279,6 +281,23 @@ def main():
                            note='configs[4] at reduced size: stars per GPU fixed (weak scaling)')
         except Exception as e:                                           # never lose the main line
             catalog = dict(error=repr(e))
+
+    # ---- auxiliary: spectrum + photometry likelihood (BASELINE.json metric, configs[2])
+    specblk = None
+    if args.spec_batch > 0:
+        try:
+            from bench_spec import run_spec_bench
+            r = run_spec_bench(fitargs['MISTpath'], fitargs['photANNpath'], batch=args.spec_batch, nobs=1536,
+                               precision=args.precision if args.precision != 'f64' else 'f32', steps=3, device=local,
+                               seed=rank)
+            tsp = torch.tensor([r['ms_per_step']], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tsp, op=dist.ReduceOp.MAX)
+            specblk = dict(value=args.spec_batch * world / (float(tsp.item()) * 1e-3), unit='evals/s',
+                           ms_per_step=float(tsp.item()), batch_per_gpu=args.spec_batch, workload=r['workload'],
+                           kernel_ms=r['kernel_ms'], spec_mlp_tflops=r['spec_mlp_tflops'])
+        except Exception as e:
+            specblk = dict(error=repr(e))
 
     if rank == 0:
         pk = peaks()
@@ -317,6 +336,7 @@ def main():
                                  ms_per_launch=in_ms / max(in_n, 1)),
             kernel_ms={k: v[0] / args.steps for k, v in prof.items() if v[1]},
             catalog=catalog,
+            spec_phot=specblk,
             cpu_baseline=cpu)
         print(json.dumps(out))
     if world > 1:

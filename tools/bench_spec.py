@@ -17,6 +17,70 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc', steps=3, device=None,
+                   cpu_points=0, seed=0):
+    """Times spectrum + photometry lnL over `batch` points resident on the GPU; returns a dict."""
+    import torch
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    spec = synth.make_spec_net(npix=npix, h=300, seed=2)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1', 'pc_2', 'pc_3']
+    on = {'Vrad', 'Vrot', 'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass',
+          'pc_0', 'pc_1', 'pc_2', 'pc_3'}
+    fitpars = [names, {n: (n in on) for n in names}]
+    obs = synth.make_obs_spectrum(spec, n_obs=nobs, seed=4)
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={'Inst_R': 35000.0}, MISTpath=mist,
+                   photANNpath=phot, specANNpath=spec, NNtype='YST1', obs_phot=synth.demo_obs_phot(),
+                   obs_wave_fit=obs['obs_wave'], obs_flux_fit=obs['obs_flux'], obs_eflux_fit=obs['obs_eflux'])
+    runbools = [True, True, True, False, False]
+    rng = np.random.default_rng(4 + seed)
+    B = batch
+    small = len(mist['eep']) < 100
+    box = dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0), afe=(-0.2, 0.6),
+               mass=(0.5, 1.25)) if small else None
+    base = synth.draw_theta_phot(B, seed=3 + seed, box=box)            # Dist, Av, EEP, feh, afe, mass
+    th = np.stack([rng.uniform(-5, 5, B), rng.uniform(0, 10, B), base[:, 0], base[:, 1], base[:, 2], base[:, 3],
+                   base[:, 4], base[:, 5], rng.normal(1.0, 0.05, B), rng.normal(0, 0.02, B),
+                   rng.normal(0, 0.01, B), rng.normal(0, 0.005, B)], 1)
+    cpu = None
+    if cpu_points:
+        from oracle.like_port import LikelihoodPort
+        ref = LikelihoodPort(fitargs, fitpars, runbools)
+        t0 = time.perf_counter()
+        for i in range(cpu_points):
+            ref.lnlikefn(list(th[i]))
+        cpu = cpu_points / (time.perf_counter() - t0)
+    L = likelihood(fitargs, fitpars, runbools, precision=precision, device=device, verbose=False)
+    assert L.fitpars_i == [n for n in names if n in on]
+    eng = L.engine
+    theta = torch.from_numpy(th).to(eng.device)
+    out = torch.empty(B, dtype=torch.float64, device=eng.device)
+    for _ in range(2):
+        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=out)
+    torch.cuda.synchronize(eng.device)
+    eng.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=out)
+    e1.record()
+    torch.cuda.synchronize(eng.device)
+    ms = e0.elapsed_time(e1) / steps
+    prof = eng.profile_read()
+    eng.profile(False)
+    flop = 2.0 * (4 * 300 + 300 * 300 + 300 * npix)
+    res = dict(metric='spec_phot_loglike_evals_per_sec', value=B / (ms * 1e-3), unit='evals/s', ms_per_step=ms,
+               batch=B, n_obs=nobs, npix=npix, precision=precision,
+               kernel_ms={k: v[0] / steps for k, v in prof.items() if v[1]},
+               spec_mlp_tflops=flop * B / (prof['spec_mlp'][0] / steps * 1e-3) / 1e12,
+               finite=int(torch.isfinite(out).sum().item()), cpu_evals_per_sec_1core=cpu,
+               workload='configs[2]: spectrum + photometry loglike, spectral ANN 4-300-300-%d px, vsini + Doppler + '
+                        'R smoothing, %d observed pixels, batch %d' % (npix, nobs, B))
+    eng.close()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=65536)
@@ -26,60 +90,11 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--cpu-points', type=int, default=0, help='also time the per-point oracle on N points')
     args = ap.parse_args()
-    import torch
     from minesweeper_b200 import synth
-    from minesweeper_b200.likelihood import likelihood
     mist = synth.make_mist(seed=0)
     phot = synth.make_phot_net(h=128, seed=1)
-    spec = synth.make_spec_net(npix=args.npix, h=300, seed=2)
-    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
-             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1', 'pc_2', 'pc_3']
-    on = {'Vrad', 'Vrot', 'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass',
-          'pc_0', 'pc_1', 'pc_2', 'pc_3'}
-    fitpars = [names, {n: (n in on) for n in names}]
-    obs = synth.make_obs_spectrum(spec, n_obs=args.nobs, seed=4)
-    fitargs = dict(ageweight=True, mistdif=True, fixedpars={'Inst_R': 35000.0}, MISTpath=mist,
-                   photANNpath=phot, specANNpath=spec, NNtype='YST1', obs_phot=synth.demo_obs_phot(),
-                   obs_wave_fit=obs['obs_wave'], obs_flux_fit=obs['obs_flux'], obs_eflux_fit=obs['obs_eflux'])
-    runbools = [True, True, True, False, False]
-    rng = np.random.default_rng(4)
-    B = args.batch
-    base = synth.draw_theta_phot(B, seed=3)            # Dist, Av, EEP, feh, afe, mass
-    th = np.stack([rng.uniform(-5, 5, B), rng.uniform(0, 10, B), base[:, 0], base[:, 1], base[:, 2], base[:, 3],
-                   base[:, 4], base[:, 5], rng.normal(1.0, 0.05, B), rng.normal(0, 0.02, B),
-                   rng.normal(0, 0.01, B), rng.normal(0, 0.005, B)], 1)
-    cpu = None
-    if args.cpu_points:
-        from oracle.like_port import LikelihoodPort
-        ref = LikelihoodPort(fitargs, fitpars, runbools)
-        t0 = time.perf_counter()
-        for i in range(args.cpu_points):
-            ref.lnlikefn(list(th[i]))
-        cpu = args.cpu_points / (time.perf_counter() - t0)
-    prec = 'f32' if args.precision == 'tc' else args.precision
-    L = likelihood(fitargs, fitpars, runbools, precision=args.precision, verbose=False)
-    assert L.fitpars_i == [n for n in names if n in on]
-    theta = torch.from_numpy(th).cuda()
-    out = torch.empty(B, dtype=torch.float64, device='cuda')
-    eng = L.engine
-    for _ in range(2):
-        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=out)
-    torch.cuda.synchronize()
-    eng.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    prof = eng.profile_read()
-    flop = 2.0 * (4 * 300 + 300 * 300 + 300 * args.npix)
-    print(json.dumps(dict(metric='spec_phot_loglike_evals_per_sec', value=B / (ms * 1e-3), ms_per_step=ms,
-                          batch=B, n_obs=args.nobs, npix=args.npix, precision=args.precision,
-                          kernel_ms={k: v[0] / args.steps for k, v in prof.items() if v[1]},
-                          spec_mlp_tflops=flop * B / (prof['spec_mlp'][0] / args.steps * 1e-3) / 1e12,
-                          finite=int(torch.isfinite(out).sum().item()), cpu_evals_per_sec_1core=cpu)))
+    print(json.dumps(run_spec_bench(mist, phot, args.batch, args.nobs, args.npix, args.precision, args.steps,
+                                    cpu_points=args.cpu_points)))
 
 
 if __name__ == '__main__':
