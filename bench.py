@@ -316,7 +316,8 @@ def main():
         out = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-            dtype={'f64': 'f64', 'f32': 'f32', 'tc': 'bf16x3'}[args.precision], data='synthetic',
+            dtype={'f64': 'f64', 'f32': 'f32', 'tc': 'f16x3 (split fp16, fp32 accumulate)',
+                   'tc16': 'f16 (fp32 accumulate)'}[args.precision], data='synthetic',
             config=dict(workload=workload_name(args, fitargs['MISTpath']), precision=args.precision,
                         l2='flushed between steps (256 MiB memset outside the timed events)',
                         collective='all_gather_into_tensor(lnL) per step' if world > 1 else 'none',

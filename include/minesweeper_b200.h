@@ -52,7 +52,9 @@ extern "C" {
  * chi-square epilogue and lnL are IEEE f64 in every mode. */
 #define MS_PREC_F64   0  /* f64 table + f64 MLP/FFT on CUDA cores: validation grade */
 #define MS_PREC_F32   1  /* f32 table, f32 MLP/FFT on CUDA cores */
-#define MS_PREC_TC    2  /* f32 table, MLP layers on tcgen05 tensor cores (split-bf16, fp32 accumulate) */
+#define MS_PREC_TC    2  /* f32 table, MLP layers on tcgen05 tensor cores (split-fp16 x3, fp32 accumulate: fp32-class) */
+#define MS_PREC_TC16  3  /* as MS_PREC_TC, but the photometric MLP uses single fp16 activations and tanh.approx
+                            (the "bf16-class" mode: magnitudes to a stated ~1e-3 mag, about twice the throughput) */
 
 /* canonical parameter ids for `colmap` (theta column -> parameter);
  * order = fitstar.py:50-67 */

@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libmsb200.so')
 
 MS_OK, MS_EINVAL, MS_ENODEV, MS_ECUDA, MS_ENOMEM, MS_ESTATE = 0, -1, -2, -3, -4, -5
-MS_PREC_F64, MS_PREC_F32, MS_PREC_TC = 0, 1, 2
-PRECISIONS = {'f64': MS_PREC_F64, 'f32': MS_PREC_F32, 'tc': MS_PREC_TC}
+MS_PREC_F64, MS_PREC_F32, MS_PREC_TC, MS_PREC_TC16 = 0, 1, 2, 3
+PRECISIONS = {'f64': MS_PREC_F64, 'f32': MS_PREC_F32, 'tc': MS_PREC_TC, 'tc16': MS_PREC_TC16}
 
 # canonical parameter ids (fitstar.py:50-67 order)
 PARAM_IDS = {

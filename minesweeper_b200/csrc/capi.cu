@@ -119,7 +119,7 @@ int setup_phot(ms_ctx *ctx, const ms_phot_net_desc *d) {
         P.xmin[i] = d->xmin[i];
         P.xscale[i] = 1.0 / (d->xmax[i] - d->xmin[i]);
     }
-    if (ctx->precision == MS_PREC_TC) return phot_tc_prepare(ctx);
+    if (ctx->precision >= MS_PREC_TC) return phot_tc_prepare(ctx);
     return MS_OK;
 }
 
@@ -242,7 +242,7 @@ int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d) {
         rt[i] = (float)s;
     }
     if ((rc = upload(&S.rot_tab, rt.data(), rt.size()))) return rc;
-    if (ctx->precision == MS_PREC_TC) return spec_tc_prepare(ctx);
+    if (ctx->precision >= MS_PREC_TC) return spec_tc_prepare(ctx);
     return MS_OK;
 }
 
@@ -250,7 +250,7 @@ extern "C" int ms_create(ms_ctx **out, int device, int precision, const ms_grid_
                          const ms_phot_net_desc *phot, const ms_spec_net_desc *spec) {
     if (!out) { ms_set_error("out is NULL"); return MS_EINVAL; }
     *out = nullptr;
-    if (precision != MS_PREC_F64 && precision != MS_PREC_F32 && precision != MS_PREC_TC) {
+    if (precision < MS_PREC_F64 || precision > MS_PREC_TC16) {
         ms_set_error("unknown precision %d", precision);
         return MS_EINVAL;
     }
@@ -437,7 +437,7 @@ extern "C" int ms_mist_interp(ms_ctx *ctx, const double *theta4, int64_t B, int3
 }
 
 static int run_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
-    if (ctx->precision == MS_PREC_TC) return launch_phot_tc(ctx, a, B, st);
+    if (ctx->precision >= MS_PREC_TC) return launch_phot_tc(ctx, a, B, st);
     return launch_phot(ctx, a, B, st);
 }
 

@@ -10,11 +10,11 @@
 // factor -log2(e) and the layer-1 bias are folded into the packed weights, so the
 // accumulators hold the exponent argument of the sigmoid directly.
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Structure (one persistent CTA per SM, 352 threads):
 //   warps 0-3 / 4-7  two epilogue warpgroups, each owning one 128-point tile; a thread
 //                    owns one point (= one TMEM lane) for the whole band sweep
-//   warp 8           MMA issuer (one elected lane)
-//   warp 9           weight producer: bulk async copies of the per-band weight image
+//   warps 8, 9       MMA issuers, one per tile (one elected lane each, blocking on that tile's barriers)
+//   warp 10          weight producer: bulk async copies of the per-band weight image
 //                    (global/L2 -> shared) into a two-deep ring
 // Per tile and band:
 //   D1 = X W1^T            SS MMA, K = 16 (6 inputs + bias column), X tile in shared memory
@@ -36,7 +36,7 @@ namespace {
 constexpr int H = 128;             // hidden width this kernel is specialised for
 constexpr int KX = 16;             // padded layer-1 K (d_in <= 6, bias column at 6)
 constexpr int TILE = 128;          // points per tile = TMEM lanes
-constexpr int NTHREADS = 320;
+constexpr int NTHREADS = 352;
 
 // Per-band weight image in global memory (and in each shared-memory ring slot).
 // Operand images use the K-major no-swizzle core-matrix layout: [k/8][row][k%8] fp16,
@@ -92,6 +92,27 @@ __device__ __forceinline__ void sigmoid_quad(float t0, float t1, float t2, float
     a0 = r01 * d1; a1 = r01 * d0; a2 = r23 * d3; a3 = r23 * d2;
 }
 
+// a - (float)h for both halves of a packed fp16 pair, one mixed-precision FMA each (FHFMA)
+__device__ __forceinline__ void sub_half2(float a0, float a1, __half2 h, float &l0, float &l1) {
+    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h);
+    unsigned short lo, hi;
+    asm("mov.b32 {%0,%1}, %2;" : "=h"(lo), "=h"(hi) : "r"(hb));
+    const unsigned short m1 = 0xbc00;                  // -1.0h
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l0) : "h"(lo), "h"(m1), "f"(a0));
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(l1) : "h"(hi), "h"(m1), "f"(a1));
+}
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    uint32_t p;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(hi), "f"(lo));
+    return p;
+}
+
 struct TcArgs {
     const double *pars; const int32_t *star_slot;
     double *mags; double *chi2; double *lnL; int ageweight;
@@ -101,6 +122,10 @@ struct TcArgs {
     int nb, d_in;
 };
 
+// FAST = MS_PREC_TC16: sigmoid(z) = 1/2 + tanh(z/2)/2 with the affine part folded into the next
+// layer's packed weights, tanh.approx.f32 (one MUFU per activation), activations handed to layer 2 as
+// single fp16 values (weights stay hi + lo).  Stated tolerance instead of fp32-class results.
+template <bool FAST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -133,7 +158,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     int my_pairs = 0;
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) ++my_pairs;
 
-    if (warp == 9) {
+    if (warp == 10) {
         // ===== weight producer =====
         if (lane == 0) {
             const int total = my_pairs * nb;
@@ -145,57 +170,57 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                          bar(BAR_WFULL + buf));
             }
         }
-    } else if (warp == 8) {
-        // ===== MMA issuer: one non-blocking state machine per tile =====
-        // stage 0: layer 1 (needs the band's weights, and the X tile on band 0);
-        // stage 1..4: layer-2 k-steps of A1 chunk stage-1, issued as soon as that chunk has
-        // been written back to TMEM by the epilogue (K-pipelined behind the sigmoid).
+    } else if (warp >= 8) {
+        // ===== MMA issuers: warp 8 + T drives tile T, blocking on that tile's barriers in program order =====
+        // per band: layer 1 (needs the band's weights, and the X tile on band 0), then the layer-2 k-steps
+        // of A1 chunk j as soon as the epilogue has written that chunk back to TMEM (K-pipelined behind
+        // the activation).  All descriptors are built once; a k-step advances the start-address field.
         if (lane == 0) {
-            int it[2] = {0, 0}, bnd[2] = {0, 0}, stage[2] = {0, 0};
-            bool done[2] = {my_pairs == 0, my_pairs == 0};
-            while (!(done[0] && done[1])) {
+            const int T = warp - 8;
+            const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;
+            const uint64_t xh = make_desc(xb, 2048, 128), xl = make_desc(xb + X_BYTES, 2048, 128);
+            const uint32_t d1 = tmem + T * 256, d2 = d1 + 128;
+            uint64_t w1h[2], w1l[2], w2h[2], w2l[2];
 #pragma unroll
-                for (int T = 0; T < 2; ++T) {
-                    if (done[T]) continue;
-                    const int g = it[T] * nb + bnd[T];
+            for (int i = 0; i < 2; ++i) {
+                const uint32_t wb = sbase + SM_W + i * BAND_BYTES;
+                w1h[i] = make_desc(wb + OFF_W1H, 2048, 128); w1l[i] = make_desc(wb + OFF_W1L, 2048, 128);
+                w2h[i] = make_desc(wb + OFF_W2H, 2048, 128); w2l[i] = make_desc(wb + OFF_W2L, 2048, 128);
+            }
+            int g = 0;
+            for (int it = 0; it < my_pairs; ++it) {
+                for (int b = 0; b < nb; ++b, ++g) {
                     const int buf = g & 1;
-                    const uint32_t wb = sbase + SM_W + buf * BAND_BYTES;
-                    if (stage[T] == 0) {
-                        if (!mbar_test(bar(BAR_WFULL + buf), (g >> 1) & 1)) continue;
-                        if (bnd[T] == 0 && !mbar_test(bar(BAR_XFULL + T), it[T] & 1)) continue;
+                    mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);
+                    if (b == 0) mbar_wait(bar(BAR_XFULL + T), it & 1);
+                    tc_fence_after();
+                    const uint64_t bh1 = buf ? w1h[1] : w1h[0], bl1 = buf ? w1l[1] : w1l[0];
+                    const uint64_t bh2 = buf ? w2h[1] : w2h[0], bl2 = buf ? w2l[1] : w2l[0];
+                    mma_ss(d1, xh, bh1, 0, IDESC);
+                    mma_ss(d1, xl, bh1, 1, IDESC);
+                    mma_ss(d1, xh, bl1, 1, IDESC);
+                    tc_commit(bar(BAR_D1 + T));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        mbar_wait(bar(BAR_A1 + 4 * T + j), g & 1);
                         tc_fence_after();
-                        const uint64_t w1h = make_desc(wb + OFF_W1H, 2048, 128), w1l = make_desc(wb + OFF_W1L, 2048, 128);
-                        const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;
-                        const uint64_t xh = make_desc(xb, 2048, 128), xl = make_desc(xb + X_BYTES, 2048, 128);
-                        const uint32_t d1 = tmem + T * 256;
-                        mma_ss(d1, xh, w1h, 0, IDESC);
-                        mma_ss(d1, xl, w1h, 1, IDESC);
-                        mma_ss(d1, xh, w1l, 1, IDESC);
-                        tc_commit(bar(BAR_D1 + T));
-                        stage[T] = 1;
-                    } else {
-                        const int j = stage[T] - 1;
-                        if (!mbar_test(bar(BAR_A1 + 4 * T + j), g & 1)) continue;
-                        tc_fence_after();
-                        const uint32_t a1 = tmem + T * 256, d2 = tmem + T * 256 + 128;
 #pragma unroll
                         for (int s2 = 0; s2 < 2; ++s2) {
-                            const int s = 2 * j + s2;
-                            const uint64_t bh = make_desc(wb + OFF_W2H + s * 4096, 2048, 128);
-                            const uint64_t bl = make_desc(wb + OFF_W2L + s * 4096, 2048, 128);
-                            const uint32_t ah = a1 + 32 * j + 8 * s2, al = ah + 16;
-                            mma_ts(d2, ah, bh, s > 0, IDESC);
-                            mma_ts(d2, al, bh, 1, IDESC);
-                            mma_ts(d2, ah, bl, 1, IDESC);
-                        }
-                        if (j == 3) {
-                            tc_commit(bar(BAR_D2 + T));
-                            stage[T] = 0;
-                            if (++bnd[T] == nb) { bnd[T] = 0; if (++it[T] == my_pairs) done[T] = true; }
-                        } else {
-                            stage[T] = j + 2;
+                            const int s = 2 * j + s2;                    // k-step: 4096 B further along K
+                            const uint64_t bh = bh2 + (uint64_t)(s * 256), bl = bl2 + (uint64_t)(s * 256);
+                            if constexpr (FAST) {
+                                const uint32_t ah = d1 + 16 * j + 8 * s2;
+                                mma_ts(d2, ah, bh, s > 0, IDESC);
+                                mma_ts(d2, ah, bl, 1, IDESC);
+                            } else {
+                                const uint32_t ah = d1 + 32 * j + 8 * s2, al = ah + 16;
+                                mma_ts(d2, ah, bh, s > 0, IDESC);
+                                mma_ts(d2, al, bh, 1, IDESC);
+                                mma_ts(d2, ah, bl, 1, IDESC);
+                            }
                         }
                     }
+                    tc_commit(bar(BAR_D2 + T));
                 }
             }
         }
@@ -256,6 +281,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             for (int b = 0; b < nb; ++b, ++g) {
                 const int buf = g & 1;
                 const unsigned char *wb = smem + SM_W + buf * BAND_BYTES;
+                // this band's observation, requested now and used after the two epilogues
+                double obs_o = 0.0, obs_e2 = 1.0;
+                if (a.chi2 || a.lnL) { obs_o = a.obs_mag[(size_t)slot * nb + b]; obs_e2 = a.obs_err2[(size_t)slot * nb + b]; }
                 // ---- layer-1 epilogue: sigmoid, fp16 split, written back in place as the TS A operand
                 mbar_wait(bar(BAR_D1 + T), g & 1);
                 tc_fence_after();
@@ -264,21 +292,29 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     uint32_t v[32], o[32];
                     TMEM_LD32(t_reg1 + 32 * j, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if constexpr (FAST) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            o[i] = pack_half2(tanh_approx(__uint_as_float(v[2 * i])), tanh_approx(__uint_as_float(v[2 * i + 1])));
+                        TMEM_ST16(t_reg1 + 16 * j, o);
+                    } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float a0, a1, a2, a3;
                         sigmoid_quad(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
                                      __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), a0, a1, a2, a3);
                         const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
-                        const float2 b01 = __half22float2(h01), b23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(a0 - b01.x, a1 - b01.y);
-                        const __half2 l23 = __floats2half2_rn(a2 - b23.x, a3 - b23.y);
+                        float e0, e1, e2, e3;
+                        sub_half2(a0, a1, h01, e0, e1);
+                        sub_half2(a2, a3, h23, e2, e3);
+                        const __half2 l01 = __floats2half2_rn(e0, e1), l23 = __floats2half2_rn(e2, e3);
                         o[2 * i] = *reinterpret_cast<const uint32_t *>(&h01);
                         o[2 * i + 1] = *reinterpret_cast<const uint32_t *>(&h23);
                         o[16 + 2 * i] = *reinterpret_cast<const uint32_t *>(&l01);
                         o[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t *>(&l23);
                     }
                     TMEM_ST32(t_reg1 + 32 * j, o);
+                    }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
@@ -301,6 +337,12 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     for (int i = 0; i < 8; ++i) {
                         const float4 c = cb2[8 * j + i], w = w3[8 * j + i];
                         float a0, a1, a2, a3;
+                        if constexpr (FAST) {
+                            a0 = tanh_approx(__uint_as_float(v[4 * i]) + c.x);
+                            a1 = tanh_approx(__uint_as_float(v[4 * i + 1]) + c.y);
+                            a2 = tanh_approx(__uint_as_float(v[4 * i + 2]) + c.z);
+                            a3 = tanh_approx(__uint_as_float(v[4 * i + 3]) + c.w);
+                        } else
                         sigmoid_quad(__uint_as_float(v[4 * i]) + c.x, __uint_as_float(v[4 * i + 1]) + c.y,
                                      __uint_as_float(v[4 * i + 2]) + c.z, __uint_as_float(v[4 * i + 3]) + c.w,
                                      a0, a1, a2, a3);
@@ -316,9 +358,8 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     const double mag = mag0 - (double)(bc0 + bc1 + b3);
                     if (a.mags) a.mags[p * nb + b] = mag;
                     if (a.chi2 || a.lnL) {
-                        const double o = a.obs_mag[(size_t)slot * nb + b];
-                        const double rr = mag - o;
-                        const double t = (rr * rr) / a.obs_err2[(size_t)slot * nb + b];
+                        const double rr = mag - obs_o;
+                        const double t = (rr * rr) / obs_e2;
                         if (t == t) chi2 += t;                           // nansum (likelihood.py:207)
                     }
                 } else if (live && a.mags) {
@@ -371,7 +412,10 @@ int phot_tc_prepare(ms_ctx *ctx) {
     MS_CUDA(cudaMemcpy(b2.data(), P.b2, b2.size() * 4, cudaMemcpyDeviceToHost));
     MS_CUDA(cudaMemcpy(w3.data(), P.w3, w3.size() * 4, cudaMemcpyDeviceToHost));
     MS_CUDA(cudaMemcpy(b3.data(), P.b3, b3.size() * 4, cudaMemcpyDeviceToHost));
-    const double NL2E = -1.4426950408889634;                      // -log2(e), folded into the weights
+    const bool fast = ctx->precision == MS_PREC_TC16;
+    // precise: accumulators hold -log2(e) z.  fast: accumulators hold z / 2 with sigmoid = (1 + tanh) / 2
+    // folded forward: W2 t-form = W2 / 4, bias2 = b2 / 2 + rowsum(W2) / 4, w3 t-form = w3 / 2, b3 += sum(w3) / 2.
+    const double NL2E = fast ? 0.5 : -1.4426950408889634;         // -log2(e), folded into the weights
     std::vector<unsigned char> img((size_t)nb * BAND_BYTES, 0);
     for (int b = 0; b < nb; ++b) {
         unsigned char *base = img.data() + (size_t)b * BAND_BYTES;
@@ -389,20 +433,30 @@ int phot_tc_prepare(ms_ctx *ctx) {
                 split_f16(v, w1h[at], w1l[at]);
             }
             for (int k = 0; k < H; ++k) {
-                const double v = NL2E * (double)w2[((size_t)b * H + n) * H + k];
+                const double v = (fast ? 0.25 : NL2E) * (double)w2[((size_t)b * H + n) * H + k];
                 if (std::fabs(v) > 6.0e4) { ms_set_error("layer-2 weight exceeds the fp16 range"); return MS_EINVAL; }
                 const size_t at = (size_t)(k / 8) * 1024 + (size_t)n * 8 + (k % 8);
                 split_f16(v, w2h[at], w2l[at]);
             }
-            cb2[n] = (float)(NL2E * (double)b2[(size_t)b * H + n]);
-            w3o[n] = w3[(size_t)b * H + n];
+            if (fast) {
+                double rs = 0.0;
+                for (int k = 0; k < H; ++k) rs += (double)w2[((size_t)b * H + n) * H + k];
+                cb2[n] = (float)(0.5 * (double)b2[(size_t)b * H + n] + 0.25 * rs);
+                w3o[n] = 0.5f * w3[(size_t)b * H + n];
+            } else {
+                cb2[n] = (float)(NL2E * (double)b2[(size_t)b * H + n]);
+                w3o[n] = w3[(size_t)b * H + n];
+            }
         }
-        b3o[0] = b3[b];
+        double s3 = 0.0;
+        for (int n = 0; n < H; ++n) s3 += (double)w3[(size_t)b * H + n];
+        b3o[0] = fast ? (float)((double)b3[b] + 0.5 * s3) : b3[b];
     }
     MS_CUDA(cudaMalloc(&P.tc_pack, img.size()));
     MS_CUDA(cudaMemcpy(P.tc_pack, img.data(), img.size(), cudaMemcpyHostToDevice));
     P.tc_pack_bytes = img.size();
-    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     return MS_OK;
 }
 
@@ -420,7 +474,8 @@ int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
     const int64_t npairs = (B + 2 * TILE - 1) / (2 * TILE);
     const int grid = (int)(npairs < ctx->sm_count ? npairs : ctx->sm_count);
     KernelTimer timer_(ctx, MS_K_PHOT, st);
-    phot_mlp_tc_kernel<<<grid, NTHREADS, SM_TOTAL, st>>>(ka, B, (int)npairs);
+    if (ctx->precision == MS_PREC_TC16) phot_mlp_tc_kernel<true><<<grid, NTHREADS, SM_TOTAL, st>>>(ka, B, (int)npairs);
+    else phot_mlp_tc_kernel<false><<<grid, NTHREADS, SM_TOTAL, st>>>(ka, B, (int)npairs);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

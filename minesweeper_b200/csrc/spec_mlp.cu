@@ -110,7 +110,7 @@ int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux
     if ((rc = gemm<T>(ctx, xs, n.w0, n.b0, h1, (int)B, n.h, n.d_in, n.leak, st))) return rc;
     if ((rc = gemm<T>(ctx, h1, n.w1, n.b1, h2, (int)B, n.h, n.h, n.leak, st))) return rc;
     if constexpr (std::is_same<T, float>::value) {
-        if (ctx->precision == MS_PREC_TC)          // output layer on the tensor cores (spec_mlp_tc.cu)
+        if (ctx->precision >= MS_PREC_TC)          // output layer on the tensor cores (spec_mlp_tc.cu)
             return launch_spec_out_tc(ctx, h2, B, flux, st);
     }
     if ((rc = gemm<T>(ctx, h2, n.w2, n.b2, flux, (int)B, n.npix, n.h, -1.0, st))) return rc;

@@ -590,7 +590,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
     const StarDev &star = ctx->stars[a.star_slot];
     // chunk of points whose native flux is materialised between the MLP and the smoother:
     // L2-sized for the CUDA-core GEMM, whole waves of 128x128 tiles for the tensor-core GEMM
-    const int64_t chunk = (ctx->precision == MS_PREC_TC) ? 8192 : 1024;
+    const int64_t chunk = (ctx->precision >= MS_PREC_TC) ? 8192 : 1024;
     const size_t flux_bytes = (size_t)chunk * n.npix * sizeof(T);
     const size_t hid_bytes = (size_t)chunk * (n.d_in + 2 * n.h) * sizeof(T);
     if (ctx->scr_flux_bytes < flux_bytes) {

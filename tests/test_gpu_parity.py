@@ -229,6 +229,26 @@ def test_phot_sed_tc_vs_oracle(n):
     assert err < 2e-5, err
 
 
+TC16_MAG_TOL = 3e-3     # stated tolerance of MS_PREC_TC16 (single fp16 activations + tanh.approx), magnitudes
+
+
+@pytest.mark.parametrize('n', [1, 257, 5000, 148 * 256 * 2 + 77])
+def test_phot_sed_tc16_stated_tolerance(n):
+    """MS_PREC_TC16 (the north_star's "bf16 tolerance on the ANN" mode): magnitudes within
+    TC16_MAG_TOL of the f64 oracle, rms an order of magnitude below that."""
+    from minesweeper_b200 import synth
+    from oracle.payne_port import FastPayneSEDPredict
+    net = synth.make_phot_net(h=128, seed=31)
+    pp = _rand_photpars(n, 40 + n % 7)
+    ref = FastPayneSEDPredict(nnpath=net).sed_batch(pp)
+    eng = _engine(photnet=net, precision='tc16')
+    mags = eng.phot_sed(pp).cpu().numpy()
+    err = np.abs(mags - ref)
+    print('tc16 max/rms mag error', err.max(), np.sqrt((err ** 2).mean()))
+    assert err.max() < TC16_MAG_TOL, err.max()
+    assert np.sqrt((err ** 2).mean()) < TC16_MAG_TOL / 5
+
+
 def test_lnlike_phot_tc_vs_f64_and_oracle():
     from minesweeper_b200 import synth
     from minesweeper_b200.likelihood import likelihood

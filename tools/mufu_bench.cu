@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 __device__ __forceinline__ float ex2a(float x){float y; asm volatile("ex2.approx.ftz.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
 __device__ __forceinline__ float rcpa(float x){float y; asm volatile("rcp.approx.ftz.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
+__device__ __forceinline__ float tanha(float x){float y; asm volatile("tanh.approx.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
 template<int MODE> __global__ void k(float* out, int iters, float seed){
     float x[8];
     #pragma unroll
@@ -16,6 +17,8 @@ template<int MODE> __global__ void k(float* out, int iters, float seed){
             if(MODE==2) x[i]=ex2a(x[i])*0.5f+0.25f;            // 1 MUFU + 1 FFMA
             if(MODE==3) {float e=ex2a(fminf(x[i],30.f)); float d=1.f+e; x[i]=rcpa(d)*0.7f-0.3f;}   // 2 MUFU + 4 fp
             if(MODE==4) {float e=ex2a(fminf(x[i],30.f)); float d=1.f+e; float a=d*0.9f; a=a*1.1f+0.2f; a=a*0.8f-0.1f; a=a*1.05f+0.01f; x[i]=a*0.01f;} // 1 MUFU + 7 fp
+            if(MODE==6) x[i]=tanha(x[i]);                      // 1 MUFU (tanh)
+            if(MODE==7) x[i]=tanha(x[i]+0.3f)*0.9f+0.1f;       // 1 MUFU (tanh) + 2 fp
             if(MODE==5) {float a=x[i]; a=a*1.1f+0.2f; a=a*0.8f-0.1f; a=a*1.05f+0.01f; a=a*0.9f+0.1f; x[i]=a;} // 4 FFMA only
         }
     }
@@ -42,5 +45,6 @@ template<int MODE> void run(const char* name, int mufu_per, int fp_per){
 int main(){
     run<0>("ex2 only",1,0); run<1>("rcp only",1,0); run<2>("ex2 + ffma",1,1);
     run<3>("ex2+rcp sigmoid (2M+4F)",2,4); run<4>("1 MUFU + 7 fp",1,7); run<5>("4 ffma only",0,4);
+    run<6>("tanh only",1,0); run<7>("tanh + 2 fp",1,2);
     return 0;
 }
