@@ -10,22 +10,25 @@
 // factor -log2(e) and the layer-1 bias are folded into the packed weights, so the
 // accumulators hold the exponent argument of the sigmoid directly.
 //
-// Structure (one persistent CTA per SM, 352 threads):
-//   warps 0-3 / 4-7  two epilogue warpgroups, each owning one 128-point tile; a thread
-//                    owns one point (= one TMEM lane) for the whole band sweep
-//   warps 8, 9       MMA issuers, one per tile (one elected lane each, blocking on that tile's barriers)
-//   warp 10          weight producer: bulk async copies of the per-band weight image
+// Structure (one persistent CTA per SM, 736 threads):
+//   warps 0-15       four epilogue warpgroups.  Tile T (128 points = 128 TMEM lanes) is shared by
+//                    warpgroup A_T (warps 4T..4T+3) and B_T (warps 8+4T..): a thread owns one point,
+//                    A takes the even 16-column chunks of each accumulator, B the odd ones, so four
+//                    warps per scheduler are available to hide the MUFU / TMEM latencies.  A also does
+//                    the chi-square.
+//   warps 16, 17     MMA issuers, one per tile (one elected lane each, blocking on that tile's barriers)
+//   warp 18          weight producer: bulk async copies of the per-band weight image
 //                    (global/L2 -> shared) into a two-deep ring
+//   warps 19-22      prologue warpgroup: the next pair's network inputs (X tiles) and distance moduli
 // Per tile and band:
 //   D1 = X W1^T            SS MMA, K = 16 (6 inputs + bias column), X tile in shared memory
-//   A1 = sigmoid(D1)       TMEM -> registers -> (ex2, rcp) -> fp16 hi/lo -> TMEM, written
-//                          in place over D1 so the activations never touch shared memory
-//   D2 = A1 W2^T           TS MMA (A operand read from TMEM), K = 128
-//   BC = w3 . sigmoid(D2 + b2) + b3 ; magnitude ; chi-square term     (registers)
+//   A1 = act(D1)           TMEM -> registers -> activation -> fp16 (hi/lo) -> TMEM, written in place
+//                          over D1 so the activations never touch shared memory
+//   D2 = A1 W2^T           TS MMA (A operand read from TMEM), K = 128, one k-step per 16-column
+//                          chunk, issued as soon as that chunk has landed (K-pipelined)
+//   BC = w3 . act(D2 + b2) + b3 ; magnitude ; chi-square term     (registers; B's half of the dot
+//                          product goes to A through shared memory)
 // TMEM: 2 tiles x (128 columns D1/A1 + 128 columns D2) = 512 columns.
-// The two warpgroups keep the MUFU pipe busy while the tensor pipe works on the
-// other tile.  The layer-2 k-steps of a tile are issued chunk by chunk as its activations land
-// in TMEM.  Binder: instruction issue of the sigmoid stream (see sigmoid_quad).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -36,7 +39,7 @@ namespace {
 constexpr int H = 128;             // hidden width this kernel is specialised for
 constexpr int KX = 16;             // padded layer-1 K (d_in <= 6, bias column at 6)
 constexpr int TILE = 128;          // points per tile = TMEM lanes
-constexpr int NTHREADS = 352;
+constexpr int NTHREADS = 736;
 
 // Per-band weight image in global memory (and in each shared-memory ring slot).
 // Operand images use the K-major no-swizzle core-matrix layout: [k/8][row][k%8] fp16,
@@ -51,18 +54,28 @@ constexpr int OFF_W2L = OFF_W2H + W2_BYTES;
 constexpr int OFF_CB2 = OFF_W2L + W2_BYTES;            // float[128]: -log2e * b2
 constexpr int OFF_W3 = OFF_CB2 + 512;                  // float[128]
 constexpr int OFF_B3 = OFF_W3 + 512;                   // float[4] (b3 in [0])
-constexpr int BAND_BYTES = OFF_B3 + 128;               // 73,856 B (multiple of 128)
+constexpr int BAND_BYTES = OFF_B3 + 128;               // 74,880 B per band in global memory (multiple of 128)
+constexpr int RING_BYTES = OFF_CB2;                    // operand images only: what a ring slot holds
+constexpr int CONST_BYTES = BAND_BYTES - OFF_CB2;      // cb2, w3, b3: resident in shared memory for all bands
 
 constexpr int X_BYTES = 2 * 128 * 16;                  // one X tile image (hi or lo)
 constexpr int SM_W = 0;                                // 2 ring slots
-constexpr int SM_X = SM_W + 2 * BAND_BYTES;            // 2 tiles x (hi, lo)
-constexpr int SM_BAR = SM_X + 4 * X_BYTES;             // mbarriers
-constexpr int SM_TOTAL = SM_BAR + 256;
+constexpr int SM_X = SM_W + 2 * RING_BYTES;            // [2 pair buffers][2 tiles][hi, lo] X tile images
+constexpr int SM_PT = SM_X + 8 * X_BYTES;              // [2 pair buffers][256 points] PointState
+constexpr int SM_PART = SM_PT + 2 * 256 * 16;          // float[2 band parities][2 tiles][128]: B's partial dot products
+constexpr int SM_BAR = SM_PART + 2048;                 // mbarriers
+constexpr int SM_CONST = SM_BAR + 256;                 // [nb][CONST_BYTES] epilogue constants
+constexpr int SM_FIXED = SM_CONST;
+constexpr int MAX_NB = (227 * 1024 - SM_FIXED) / CONST_BYTES;
 
 // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = make_idesc_f16(128, 128);
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR_A1 = 10 /* [tile][chunk] */, BAR_N = 18 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR_A1 = 10 /* [tile][8 chunks] */,
+       BAR_XEMPTY = 26, BAR_N = 28 };
+
+// what the prologue warpgroup hands to the chi-square threads for one point
+struct PointState { double mag0; int32_t slot; int32_t ok; };
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -138,52 +151,58 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(BAR_WFULL + i), 1);
-            mbar_init(bar(BAR_WEMPTY + i), 8);
-            mbar_init(bar(BAR_XFULL + i), 4);
+            mbar_init(bar(BAR_WEMPTY + i), 2);
+            mbar_init(bar(BAR_XFULL + i), 4);                   // [pair buffer]: the 4 prologue warps
+            mbar_init(bar(BAR_XEMPTY + i), 2 + 8);              // both issuers (last layer 1 done) + the 8 A warps
             mbar_init(bar(BAR_D1 + i), 1);
             mbar_init(bar(BAR_D2 + i), 1);
-            for (int j = 0; j < 4; ++j) mbar_init(bar(BAR_A1 + 4 * i + j), 4);
+            for (int j = 0; j < 8; ++j) mbar_init(bar(BAR_A1 + 8 * i + j), 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {                                   // TMEM: all 512 columns
+    if (warp == 16) {                                  // TMEM: all 512 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int nb = a.nb;
+    for (int i = threadIdx.x; i < nb * (CONST_BYTES / 16); i += NTHREADS) {      // epilogue constants of every band
+        const int b = i / (CONST_BYTES / 16), o = i % (CONST_BYTES / 16);
+        reinterpret_cast<uint4 *>(smem + SM_CONST + b * CONST_BYTES)[o] =
+            reinterpret_cast<const uint4 *>(a.wimg + (size_t)b * BAND_BYTES + OFF_CB2)[o];
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
-    const int nb = a.nb;
     int my_pairs = 0;
     for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) ++my_pairs;
 
-    if (warp == 10) {
+    if (warp == 18) {
         // ===== weight producer =====
         if (lane == 0) {
             const int total = my_pairs * nb;
             for (int g = 0; g < total; ++g) {
                 const int buf = g & 1;
                 mbar_wait(bar(BAR_WEMPTY + buf), ((g >> 1) & 1) ^ 1);
-                mbar_expect_tx(bar(BAR_WFULL + buf), BAND_BYTES);
-                bulk_g2s(sbase + SM_W + buf * BAND_BYTES, a.wimg + (size_t)(g % nb) * BAND_BYTES, BAND_BYTES,
+                mbar_expect_tx(bar(BAR_WFULL + buf), RING_BYTES);
+                bulk_g2s(sbase + SM_W + buf * RING_BYTES, a.wimg + (size_t)(g % nb) * BAND_BYTES, RING_BYTES,
                          bar(BAR_WFULL + buf));
             }
         }
-    } else if (warp >= 8) {
-        // ===== MMA issuers: warp 8 + T drives tile T, blocking on that tile's barriers in program order =====
-        // per band: layer 1 (needs the band's weights, and the X tile on band 0), then the layer-2 k-steps
-        // of A1 chunk j as soon as the epilogue has written that chunk back to TMEM (K-pipelined behind
-        // the activation).  All descriptors are built once; a k-step advances the start-address field.
+    } else if (warp == 16 || warp == 17) {
+        // ===== MMA issuers: warp 16 + T drives tile T, blocking on that tile's barriers in program order =====
+        // per band: layer 1 (needs the band's weights, and the X tile on band 0), then one layer-2 k-step
+        // per A1 chunk as soon as the epilogue has written that chunk back to TMEM.  All descriptors are
+        // built once; a k-step advances the start-address field.
         if (lane == 0) {
-            const int T = warp - 8;
-            const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;
-            const uint64_t xh = make_desc(xb, 2048, 128), xl = make_desc(xb + X_BYTES, 2048, 128);
+            const int T = warp - 16;
+            const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;          // pair buffer 1 is 4 * X_BYTES further
+            const uint64_t xh0 = make_desc(xb, 2048, 128), xl0 = make_desc(xb + X_BYTES, 2048, 128);
             const uint32_t d1 = tmem + T * 256, d2 = d1 + 128;
             uint64_t w1h[2], w1l[2], w2h[2], w2l[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const uint32_t wb = sbase + SM_W + i * BAND_BYTES;
+                const uint32_t wb = sbase + SM_W + i * RING_BYTES;
                 w1h[i] = make_desc(wb + OFF_W1H, 2048, 128); w1l[i] = make_desc(wb + OFF_W1L, 2048, 128);
                 w2h[i] = make_desc(wb + OFF_W2H, 2048, 128); w2l[i] = make_desc(wb + OFF_W2L, 2048, 128);
             }
@@ -192,7 +211,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 for (int b = 0; b < nb; ++b, ++g) {
                     const int buf = g & 1;
                     mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);
-                    if (b == 0) mbar_wait(bar(BAR_XFULL + T), it & 1);
+                    if (b == 0) mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+                    const uint64_t xh = xh0 + (uint64_t)((it & 1) * (4 * X_BYTES / 16));
+                    const uint64_t xl = xl0 + (uint64_t)((it & 1) * (4 * X_BYTES / 16));
                     tc_fence_after();
                     const uint64_t bh1 = buf ? w1h[1] : w1h[0], bl1 = buf ? w1l[1] : w1l[0];
                     const uint64_t bh2 = buf ? w2h[1] : w2h[0], bl2 = buf ? w2l[1] : w2l[0];
@@ -200,63 +221,56 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     mma_ss(d1, xl, bh1, 1, IDESC);
                     mma_ss(d1, xh, bl1, 1, IDESC);
                     tc_commit(bar(BAR_D1 + T));
+                    if (b == nb - 1) tc_commit(bar(BAR_XEMPTY + (it & 1)));      // last read of this pair's X tile
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        mbar_wait(bar(BAR_A1 + 4 * T + j), g & 1);
+                    for (int c = 0; c < 8; ++c) {                        // k-step c: 4096 B further along K
+                        mbar_wait(bar(BAR_A1 + 8 * T + c), g & 1);
                         tc_fence_after();
-#pragma unroll
-                        for (int s2 = 0; s2 < 2; ++s2) {
-                            const int s = 2 * j + s2;                    // k-step: 4096 B further along K
-                            const uint64_t bh = bh2 + (uint64_t)(s * 256), bl = bl2 + (uint64_t)(s * 256);
-                            if constexpr (FAST) {
-                                const uint32_t ah = d1 + 16 * j + 8 * s2;
-                                mma_ts(d2, ah, bh, s > 0, IDESC);
-                                mma_ts(d2, ah, bl, 1, IDESC);
-                            } else {
-                                const uint32_t ah = d1 + 32 * j + 8 * s2, al = ah + 16;
-                                mma_ts(d2, ah, bh, s > 0, IDESC);
-                                mma_ts(d2, al, bh, 1, IDESC);
-                                mma_ts(d2, ah, bl, 1, IDESC);
-                            }
-                        }
+                        const uint64_t bh = bh2 + (uint64_t)(c * 256), bl = bl2 + (uint64_t)(c * 256);
+                        const uint32_t ah = d1 + 16 * c;
+                        mma_ts(d2, ah, bh, c > 0, IDESC);
+                        if constexpr (!FAST) mma_ts(d2, ah + 8, bh, 1, IDESC);
+                        mma_ts(d2, ah, bl, 1, IDESC);
                     }
                     tc_commit(bar(BAR_D2 + T));
+                    tc_commit(bar(BAR_WEMPTY + buf));                    // this tile is done with the ring slot
                 }
             }
         }
-    } else {
-        // ===== epilogue warpgroups: tile T, row r =====
-        const int T = warp >> 2;
-        const int r = threadIdx.x & 127;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t t_reg1 = tmem + lane_base + T * 256, t_d2 = t_reg1 + 128;
-        unsigned char *xrow_h = smem + SM_X + T * 2 * X_BYTES, *xrow_l = xrow_h + X_BYTES;
-        int g = 0;
+    } else if (warp >= 19) {
+        // ===== prologue warpgroup: network inputs and distance modulus of the next pair's 256 points =====
+        // (GenMod.genphot, genmod.py:97-142), one pair ahead of the epilogue so the f64 logarithms and the
+        // strided loads of the parameter block never sit on the critical path.
+        const int tid = threadIdx.x - 19 * 32;
         for (int it = 0; it < my_pairs; ++it) {
+            const int xbuf = it & 1;
+            mbar_wait(bar(BAR_XEMPTY + xbuf), ((it >> 1) & 1) ^ 1);
             const int pr = blockIdx.x + it * gridDim.x;
-            const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + r;
-            const bool live = p < B;
-            bool ok = false;
-            double mag0 = 0.0;
-            float xs[8];
+#pragma unroll 1
+            for (int T = 0; T < 2; ++T) {
+                const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + tid;
+                PointState ps{0.0, 0, 0};
+                float xs[8];
 #pragma unroll
-            for (int d = 0; d < 8; ++d) xs[d] = 0.f;
-            if (live) {
-                const double *q = a.pars + p * MS_NPARS;
-                const double teff = q[PV_TEFF];
-                ok = teff != ms_inf();
-                if (ok) {
-                    const double logt = log10(teff);                     // genmod.py:111-113
-                    const double logl = 2.0 * q[PV_LOGR] + 4.0 * (logt - log10(5770.0));
-                    mag0 = -2.5 * logl + 4.74 + 5.0 * log10(q[PV_DIST]) - 5.0;
-                    const double xin[6] = {pow(10.0, logt), q[PV_LOGG], q[PV_FEH], q[PV_AFE], q[PV_AV], 3.1};
+                for (int d = 0; d < 8; ++d) xs[d] = 0.f;
+                if (p < B) {
+                    const double *q = a.pars + p * MS_NPARS;
+                    const double teff = q[PV_TEFF];
+                    if (teff != ms_inf()) {
+                        ps.ok = 1;
+                        const double logt = log10(teff);                     // genmod.py:111-113
+                        const double logl = 2.0 * q[PV_LOGR] + 4.0 * (logt - log10(5770.0));
+                        ps.mag0 = -2.5 * logl + 4.74 + 5.0 * log10(q[PV_DIST]) - 5.0;
+                        const double xin[6] = {pow(10.0, logt), q[PV_LOGG], q[PV_FEH], q[PV_AFE], q[PV_AV], 3.1};
 #pragma unroll
-                    for (int d = 0; d < 6; ++d)
-                        if (d < a.d_in) xs[d] = (float)((xin[d] - a.xmin[d]) * a.xscale[d] - 0.5);
+                        for (int d = 0; d < 6; ++d)
+                            if (d < a.d_in) xs[d] = (float)((xin[d] - a.xmin[d]) * a.xscale[d] - 0.5);
+                    }
+                    if (a.star_slot) ps.slot = a.star_slot[p];
                 }
-            }
-            xs[6] = 1.0f;                                                // bias column
-            {   // X tile row in the core-matrix layout: chunk c (8 k) at c*2048 + r*16
+                xs[6] = 1.0f;                                                // bias column
+                // X tile row in the core-matrix layout: chunk c (8 k) at c*2048 + r*16
+                unsigned char *xrow_h = smem + SM_X + (xbuf * 2 + T) * 2 * X_BYTES, *xrow_l = xrow_h + X_BYTES;
                 __half2 hh[8], ll[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -267,95 +281,131 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     hh[4 + i] = __floats2half2_rn(0.f, 0.f);
                     ll[4 + i] = hh[4 + i];
                 }
-                *reinterpret_cast<uint4 *>(xrow_h + r * 16) = *reinterpret_cast<uint4 *>(&hh[0]);
-                *reinterpret_cast<uint4 *>(xrow_h + 2048 + r * 16) = *reinterpret_cast<uint4 *>(&hh[4]);
-                *reinterpret_cast<uint4 *>(xrow_l + r * 16) = *reinterpret_cast<uint4 *>(&ll[0]);
-                *reinterpret_cast<uint4 *>(xrow_l + 2048 + r * 16) = *reinterpret_cast<uint4 *>(&ll[4]);
+                *reinterpret_cast<uint4 *>(xrow_h + tid * 16) = *reinterpret_cast<uint4 *>(&hh[0]);
+                *reinterpret_cast<uint4 *>(xrow_h + 2048 + tid * 16) = *reinterpret_cast<uint4 *>(&hh[4]);
+                *reinterpret_cast<uint4 *>(xrow_l + tid * 16) = *reinterpret_cast<uint4 *>(&ll[0]);
+                *reinterpret_cast<uint4 *>(xrow_l + 2048 + tid * 16) = *reinterpret_cast<uint4 *>(&ll[4]);
+                reinterpret_cast<PointState *>(smem + SM_PT)[(xbuf * 2 + T) * TILE + tid] = ps;
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar(BAR_XFULL + T));
-            const int slot = (live && a.star_slot) ? a.star_slot[p] : 0;
+            if (lane == 0) mbar_arrive(bar(BAR_XFULL + xbuf));
+        }
+    } else {
+        // ===== epilogue warpgroups: tile T, row r, chunk parity `half` =====
+        const int half = warp >> 3;                    // 0: warpgroup A (even chunks, prologue, chi-square), 1: B
+        const int T = (warp >> 2) & 1;
+        const int r = threadIdx.x & 127;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t t_reg1 = tmem + lane_base + T * 256, t_d2 = t_reg1 + 128;
+        float *part = reinterpret_cast<float *>(smem + SM_PART);
+        int g = 0;
+        // skew: tile 1 starts when tile 0 has finished its first layer-1 epilogue, so that one tile's waits for
+        // the tensor pipe fall into the other tile's activation phases instead of coinciding with its own
+        if (T == 1 && my_pairs > 0) mbar_wait(bar(BAR_A1 + 7), 0);
+        for (int it = 0; it < my_pairs; ++it) {
+            const int pr = blockIdx.x + it * gridDim.x;
+            const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + r;
+            const bool live = half == 0 && p < B;
+            bool ok = false;
+            double mag0 = 0.0;
+            int slot = 0;
+            if (half == 0) {                           // point state from the prologue warpgroup
+                mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+                const PointState ps = reinterpret_cast<const PointState *>(smem + SM_PT)[((it & 1) * 2 + T) * TILE + r];
+                ok = ps.ok != 0; mag0 = ps.mag0; slot = ps.slot;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_XEMPTY + (it & 1)));
+            }
             double chi2 = 0.0;
 
             for (int b = 0; b < nb; ++b, ++g) {
-                const int buf = g & 1;
-                const unsigned char *wb = smem + SM_W + buf * BAND_BYTES;
+                const unsigned char *cb = smem + SM_CONST + b * CONST_BYTES;
                 // this band's observation, requested now and used after the two epilogues
                 double obs_o = 0.0, obs_e2 = 1.0;
-                if (a.chi2 || a.lnL) { obs_o = a.obs_mag[(size_t)slot * nb + b]; obs_e2 = a.obs_err2[(size_t)slot * nb + b]; }
-                // ---- layer-1 epilogue: sigmoid, fp16 split, written back in place as the TS A operand
+                if (half == 0 && (a.chi2 || a.lnL)) {
+                    obs_o = a.obs_mag[(size_t)slot * nb + b]; obs_e2 = a.obs_err2[(size_t)slot * nb + b];
+                }
+                // ---- layer-1 epilogue: activation, fp16 (split), written back in place as the TS A operand
                 mbar_wait(bar(BAR_D1 + T), g & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t v[32], o[32];
-                    TMEM_LD32(t_reg1 + 32 * j, v);
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const int c = 2 * i4 + half;
+                    uint32_t v[16], o[16];
+                    TMEM_LD16(t_reg1 + 16 * c, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if constexpr (FAST) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
+                        for (int i = 0; i < 8; ++i)
                             o[i] = pack_half2(tanh_approx(__uint_as_float(v[2 * i])), tanh_approx(__uint_as_float(v[2 * i + 1])));
-                        TMEM_ST16(t_reg1 + 16 * j, o);
+                        TMEM_ST8(t_reg1 + 16 * c, o);
                     } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float a0, a1, a2, a3;
-                        sigmoid_quad(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                     __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), a0, a1, a2, a3);
-                        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
-                        float e0, e1, e2, e3;
-                        sub_half2(a0, a1, h01, e0, e1);
-                        sub_half2(a2, a3, h23, e2, e3);
-                        const __half2 l01 = __floats2half2_rn(e0, e1), l23 = __floats2half2_rn(e2, e3);
-                        o[2 * i] = *reinterpret_cast<const uint32_t *>(&h01);
-                        o[2 * i + 1] = *reinterpret_cast<const uint32_t *>(&h23);
-                        o[16 + 2 * i] = *reinterpret_cast<const uint32_t *>(&l01);
-                        o[16 + 2 * i + 1] = *reinterpret_cast<const uint32_t *>(&l23);
-                    }
-                    TMEM_ST32(t_reg1 + 32 * j, o);
+                        for (int i = 0; i < 4; ++i) {
+                            float a0, a1, a2, a3;
+                            sigmoid_quad(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]), a0, a1, a2, a3);
+                            const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                            float e0, e1, e2, e3;
+                            sub_half2(a0, a1, h01, e0, e1);
+                            sub_half2(a2, a3, h23, e2, e3);
+                            const __half2 l01 = __floats2half2_rn(e0, e1), l23 = __floats2half2_rn(e2, e3);
+                            o[2 * i] = *reinterpret_cast<const uint32_t *>(&h01);
+                            o[2 * i + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+                            o[8 + 2 * i] = *reinterpret_cast<const uint32_t *>(&l01);
+                            o[8 + 2 * i + 1] = *reinterpret_cast<const uint32_t *>(&l23);
+                        }
+                        TMEM_ST16(t_reg1 + 16 * c, o);
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(BAR_A1 + 4 * T + j));   // chunk j usable as TS A operand
+                    if (lane == 0) mbar_arrive(bar(BAR_A1 + 8 * T + c));   // chunk c usable as TS A operand
                 }
 
-                // ---- layer-2 epilogue: sigmoid, dot with w3, magnitude, chi-square term
-                mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);           // epilogue constants visible
-                const float4 *cb2 = reinterpret_cast<const float4 *>(wb + OFF_CB2);
-                const float4 *w3 = reinterpret_cast<const float4 *>(wb + OFF_W3);
+                // ---- layer-2 epilogue: activation, dot with w3
+                const float4 *cb2 = reinterpret_cast<const float4 *>(cb);
+                const float4 *w3 = reinterpret_cast<const float4 *>(cb + (OFF_W3 - OFF_CB2));
                 float bc0 = 0.f, bc1 = 0.f;
                 mbar_wait(bar(BAR_D2 + T), g & 1);
                 tc_fence_after();
 #pragma unroll 1
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t v[32];
-                    TMEM_LD32(t_d2 + 32 * j, v);
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const int c = 2 * i4 + half;
+                    uint32_t v[16];
+                    TMEM_LD16(t_d2 + 16 * c, v);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 c = cb2[8 * j + i], w = w3[8 * j + i];
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 cc = cb2[4 * c + i], w = w3[4 * c + i];
                         float a0, a1, a2, a3;
                         if constexpr (FAST) {
-                            a0 = tanh_approx(__uint_as_float(v[4 * i]) + c.x);
-                            a1 = tanh_approx(__uint_as_float(v[4 * i + 1]) + c.y);
-                            a2 = tanh_approx(__uint_as_float(v[4 * i + 2]) + c.z);
-                            a3 = tanh_approx(__uint_as_float(v[4 * i + 3]) + c.w);
-                        } else
-                        sigmoid_quad(__uint_as_float(v[4 * i]) + c.x, __uint_as_float(v[4 * i + 1]) + c.y,
-                                     __uint_as_float(v[4 * i + 2]) + c.z, __uint_as_float(v[4 * i + 3]) + c.w,
-                                     a0, a1, a2, a3);
+                            a0 = tanh_approx(__uint_as_float(v[4 * i]) + cc.x);
+                            a1 = tanh_approx(__uint_as_float(v[4 * i + 1]) + cc.y);
+                            a2 = tanh_approx(__uint_as_float(v[4 * i + 2]) + cc.z);
+                            a3 = tanh_approx(__uint_as_float(v[4 * i + 3]) + cc.w);
+                        } else {
+                            sigmoid_quad(__uint_as_float(v[4 * i]) + cc.x, __uint_as_float(v[4 * i + 1]) + cc.y,
+                                         __uint_as_float(v[4 * i + 2]) + cc.z, __uint_as_float(v[4 * i + 3]) + cc.w,
+                                         a0, a1, a2, a3);
+                        }
                         bc0 = fmaf(w.x, a0, bc0); bc1 = fmaf(w.y, a1, bc1);
                         bc0 = fmaf(w.z, a2, bc0); bc1 = fmaf(w.w, a3, bc1);
                     }
                 }
-                const float b3 = *reinterpret_cast<const float *>(wb + OFF_B3);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(BAR_WEMPTY + buf));       // ring slot free for band g + 2
+                const float b3 = *reinterpret_cast<const float *>(cb + (OFF_B3 - OFF_CB2));
+                float *pslot = part + ((g & 1) * 2 + T) * TILE + r;
+                if (half == 1) {                                         // B: hand the odd-chunk half to A
+                    *pslot = bc0 + bc1;
+                    __threadfence_block();
+                    asm volatile("bar.arrive %0, 256;" ::"r"(1 + T) : "memory");
+                    continue;
+                }
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + T) : "memory");
+                const float bc = (bc0 + bc1) + *pslot + b3;
                 if (ok) {
-                    const double mag = mag0 - (double)(bc0 + bc1 + b3);
+                    const double mag = mag0 - (double)bc;
                     if (a.mags) a.mags[p * nb + b] = mag;
                     if (a.chi2 || a.lnL) {
                         const double rr = mag - obs_o;
@@ -366,6 +416,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     a.mags[p * nb + b] = ms_nan();
                 }
             }
+            if (half == 1) continue;
             if (live && a.lnL) {
                 double l = -ms_inf();
                 if (ok) {
@@ -380,7 +431,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
 }
@@ -398,9 +449,9 @@ void split_f16(double v, uint16_t &hi, uint16_t &lo) {
 
 int phot_tc_prepare(ms_ctx *ctx) {
     PhotNetDev &P = ctx->phot;
-    if (P.h != H || P.d_in > 6) {
-        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 128 and <= 6 inputs "
-                     "(got h=%d, d_in=%d); use MS_PREC_F32", P.h, P.d_in);
+    if (P.h != H || P.d_in > 6 || P.nb > MAX_NB) {
+        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 128, <= 6 inputs and <= %d bands "
+                     "(got h=%d, d_in=%d, nb=%d); use MS_PREC_F32", MAX_NB, P.h, P.d_in, P.nb);
         return MS_EINVAL;
     }
     const int nb = P.nb, D = P.d_in;
@@ -455,8 +506,9 @@ int phot_tc_prepare(ms_ctx *ctx) {
     MS_CUDA(cudaMalloc(&P.tc_pack, img.size()));
     MS_CUDA(cudaMemcpy(P.tc_pack, img.data(), img.size(), cudaMemcpyHostToDevice));
     P.tc_pack_bytes = img.size();
-    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    const int smem_total = SM_FIXED + nb * CONST_BYTES;
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
     return MS_OK;
 }
 
@@ -474,8 +526,9 @@ int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
     const int64_t npairs = (B + 2 * TILE - 1) / (2 * TILE);
     const int grid = (int)(npairs < ctx->sm_count ? npairs : ctx->sm_count);
     KernelTimer timer_(ctx, MS_K_PHOT, st);
-    if (ctx->precision == MS_PREC_TC16) phot_mlp_tc_kernel<true><<<grid, NTHREADS, SM_TOTAL, st>>>(ka, B, (int)npairs);
-    else phot_mlp_tc_kernel<false><<<grid, NTHREADS, SM_TOTAL, st>>>(ka, B, (int)npairs);
+    const int smem_total = SM_FIXED + n.nb * CONST_BYTES;
+    if (ctx->precision == MS_PREC_TC16) phot_mlp_tc_kernel<true><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
+    else phot_mlp_tc_kernel<false><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

@@ -5,6 +5,7 @@
 __device__ __forceinline__ float ex2a(float x){float y; asm volatile("ex2.approx.ftz.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
 __device__ __forceinline__ float rcpa(float x){float y; asm volatile("rcp.approx.ftz.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
 __device__ __forceinline__ float tanha(float x){float y; asm volatile("tanh.approx.f32 %0, %1;":"=f"(y):"f"(x)); return y;}
+__device__ __forceinline__ unsigned packh2(float lo, float hi){unsigned p; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;":"=r"(p):"f"(hi),"f"(lo)); return p;}
 template<int MODE> __global__ void k(float* out, int iters, float seed){
     float x[8];
     #pragma unroll
@@ -19,6 +20,8 @@ template<int MODE> __global__ void k(float* out, int iters, float seed){
             if(MODE==4) {float e=ex2a(fminf(x[i],30.f)); float d=1.f+e; float a=d*0.9f; a=a*1.1f+0.2f; a=a*0.8f-0.1f; a=a*1.05f+0.01f; x[i]=a*0.01f;} // 1 MUFU + 7 fp
             if(MODE==6) x[i]=tanha(x[i]);                      // 1 MUFU (tanh)
             if(MODE==7) x[i]=tanha(x[i]+0.3f)*0.9f+0.1f;       // 1 MUFU (tanh) + 2 fp
+            if(MODE==8) x[i]=__uint_as_float(packh2(x[i],x[(i+1)&7])&0x3fff3fffu);  // 1 F2FP + 1 LOP
+            if(MODE==9) {float t=tanha(x[i]); x[i]=__uint_as_float(packh2(t,x[(i+1)&7])&0x3fff3fffu);}  // 1 MUFU + 1 F2FP + LOP
             if(MODE==5) {float a=x[i]; a=a*1.1f+0.2f; a=a*0.8f-0.1f; a=a*1.05f+0.01f; a=a*0.9f+0.1f; x[i]=a;} // 4 FFMA only
         }
     }
@@ -45,6 +48,7 @@ template<int MODE> void run(const char* name, int mufu_per, int fp_per){
 int main(){
     run<0>("ex2 only",1,0); run<1>("rcp only",1,0); run<2>("ex2 + ffma",1,1);
     run<3>("ex2+rcp sigmoid (2M+4F)",2,4); run<4>("1 MUFU + 7 fp",1,7); run<5>("4 ffma only",0,4);
+    run<8>("f2fp pack + lop",0,2); run<9>("tanh + f2fp + lop",1,2);
     run<6>("tanh only",1,0); run<7>("tanh + 2 fp",1,2);
     return 0;
 }
