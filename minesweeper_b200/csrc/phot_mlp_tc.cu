@@ -194,11 +194,14 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         // per band: layer 1 (needs the band's weights, and the X tile on band 0), then one layer-2 k-step
         // per A1 chunk as soon as the epilogue has written that chunk back to TMEM.  All descriptors are
         // built once; a k-step advances the start-address field.
-        if (lane == 0) {
-            const int T = warp - 16;
+        // The whole warp runs the loop converged and one elected lane issues: every operand is
+        // warp-uniform, so the descriptors live in uniform registers and an MMA is a single instruction.
+        {
+            const int T = __shfl_sync(0xffffffffu, warp, 0) - 16;
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
             const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;          // pair buffer 1 is 4 * X_BYTES further
             const uint64_t xh0 = make_desc(xb, 2048, 128), xl0 = make_desc(xb + X_BYTES, 2048, 128);
-            const uint32_t d1 = tmem + T * 256, d2 = d1 + 128;
+            const uint32_t d1 = tm + T * 256, d2 = d1 + 128;
             uint64_t w1h[2], w1l[2], w2h[2], w2l[2];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -217,23 +220,31 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     tc_fence_after();
                     const uint64_t bh1 = buf ? w1h[1] : w1h[0], bl1 = buf ? w1l[1] : w1l[0];
                     const uint64_t bh2 = buf ? w2h[1] : w2h[0], bl2 = buf ? w2l[1] : w2l[0];
-                    mma_ss(d1, xh, bh1, 0, IDESC);
-                    mma_ss(d1, xl, bh1, 1, IDESC);
-                    mma_ss(d1, xh, bl1, 1, IDESC);
-                    tc_commit(bar(BAR_D1 + T));
-                    if (b == nb - 1) tc_commit(bar(BAR_XEMPTY + (it & 1)));      // last read of this pair's X tile
+                    if (elect_one()) {
+                        mma_ss(d1, xh, bh1, 0, IDESC);
+                        mma_ss(d1, xl, bh1, 1, IDESC);
+                        mma_ss(d1, xh, bl1, 1, IDESC);
+                        tc_commit(bar(BAR_D1 + T));
+                        if (b == nb - 1) tc_commit(bar(BAR_XEMPTY + (it & 1)));  // last read of this pair's X tile
+                    }
+                    __syncwarp();
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {                        // k-step c: 4096 B further along K
                         mbar_wait(bar(BAR_A1 + 8 * T + c), g & 1);
                         tc_fence_after();
                         const uint64_t bh = bh2 + (uint64_t)(c * 256), bl = bl2 + (uint64_t)(c * 256);
                         const uint32_t ah = d1 + 16 * c;
-                        mma_ts(d2, ah, bh, c > 0, IDESC);
-                        if constexpr (!FAST) mma_ts(d2, ah + 8, bh, 1, IDESC);
-                        mma_ts(d2, ah, bl, 1, IDESC);
+                        if (elect_one()) {
+                            mma_ts(d2, ah, bh, c > 0, IDESC);
+                            if constexpr (!FAST) mma_ts(d2, ah + 8, bh, 1, IDESC);
+                            mma_ts(d2, ah, bl, 1, IDESC);
+                            if (c == 7) {
+                                tc_commit(bar(BAR_D2 + T));
+                                tc_commit(bar(BAR_WEMPTY + buf));        // this tile is done with the ring slot
+                            }
+                        }
+                        __syncwarp();
                     }
-                    tc_commit(bar(BAR_D2 + T));
-                    tc_commit(bar(BAR_WEMPTY + buf));                    // this tile is done with the ring slot
                 }
             }
         }
