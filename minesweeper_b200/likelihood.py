@@ -10,7 +10,7 @@ are ``lnlike_batch`` (arrays, stays on the GPU) and ``lnlikefn_batch`` (NumPy in
 out, plus one ``parsdict`` per row).
 
 ``fitargs['MISTpath' | 'photANNpath' | 'specANNpath']`` are model containers (dict
-or ``.npz``); extra keyword ``precision`` in {'f64', 'f32', 'tc'} selects the
+or ``.npz``); extra keyword ``precision`` in {'f64', 'f32', 'tc', 'tc16'} selects the
 arithmetic mode and ``device`` the GPU.
 """
 import numpy as np
