@@ -73,40 +73,46 @@ __global__ void ns_accept_kernel(ms_ns_state s) {
     }
 }
 
+// ---- one warp per star ---------------------------------------------------------------------------
+// The per-star bookkeeping is a chain of dependent global round trips and f64 logarithms with a few
+// 150-wide or 19-wide loops in between, so a star gets one warp (no block barriers, results of the
+// reductions in every lane) and a CTA carries NS_WARPS independent stars; what bounds the kernel is
+// how many stars are in flight per SM.
+constexpr int NS_WARPS = 4;
+
 // update of ln Z, H and the weighted posterior moments of one star with a point of ln weight logwt
 __device__ __forceinline__ void ns_accumulate(const ms_ns_state &s, int star, double lnl, double logwt,
-                                              const double *row, int ncol, double *sh) {
-    // sh[0] = r_old, sh[1] = w  (broadcast from thread 0)
-    if (threadIdx.x == 0) {
+                                              const double *row, int ncol, int lane) {
+    double r_old = 0.0, w = 0.0;
+    if (lane == 0) {
         const double lz = s.logz[star], lz_new = logaddexp_d(lz, logwt);
         double h = s.hacc[star] * exp(lz - lz_new) + exp(logwt - lz_new) * lnl;
         if (lz == -ms_inf()) h = exp(logwt - lz_new) * lnl;
         s.hacc[star] = h;
         s.logz[star] = lz_new;
         const double m_old = s.wmax[star], m_new = fmax(m_old, logwt);
-        const double r_old = (m_old == -ms_inf()) ? 0.0 : exp(m_old - m_new);
-        const double w = exp(logwt - m_new);
+        r_old = (m_old == -ms_inf()) ? 0.0 : exp(m_old - m_new);
+        w = exp(logwt - m_new);
         s.wmax[star] = m_new;
         s.wtot[star] = s.wtot[star] * r_old + w;
-        sh[0] = r_old; sh[1] = w;
     }
-    __syncthreads();
-    const double r_old = sh[0], w = sh[1];
-    for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+    r_old = __shfl_sync(0xffffffffu, r_old, 0);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    for (int c = lane; c < ncol; c += 32) {
         double v = row[c];
         if (!(fabs(v) < 1e300)) v = 0.0;
         const int64_t at = (int64_t)star * ncol + c;
         s.wsum[at] = s.wsum[at] * r_old + w * v;
         s.wsq[at] = s.wsq[at] * r_old + w * v * v;
     }
-    __syncthreads();
+    __syncwarp();
 }
 
-// block-wide arg-min and max of lp[0..K)
-__device__ __forceinline__ void ns_minmax(const double *lp, int K, double *sv, int *si, double &vmin, int &imin, double &vmax) {
+// warp-wide arg-min (lowest index on ties) and max of lp[0..K); the result is in every lane
+__device__ __forceinline__ void ns_minmax(const double *lp, int K, int lane, double &vmin, int &imin, double &vmax) {
     double mn = ms_inf(), mx = -ms_inf();
     int im = 0;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = lane; k < K; k += 32) {
         const double v = lp[k];
         if (v < mn) { mn = v; im = k; }
         mx = fmax(mx, v);
@@ -118,44 +124,33 @@ __device__ __forceinline__ void ns_minmax(const double *lp, int K, double *sv, i
         if (omn < mn || (omn == mn && oim < im)) { mn = omn; im = oim; }
         mx = fmax(mx, omx);
     }
-    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    if ((threadIdx.x & 31) == 0) { sv[w] = mn; si[w] = im; sv[32 + w] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < nw; ++i) {
-            if (sv[i] < sv[0] || (sv[i] == sv[0] && si[i] < si[0])) { sv[0] = sv[i]; si[0] = si[i]; }
-            sv[32] = fmax(sv[32], sv[32 + i]);
-        }
-    }
-    __syncthreads();
-    vmin = sv[0]; imin = si[0]; vmax = sv[32];
-    __syncthreads();
+    vmin = mn; imin = im; vmax = mx;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * NS_WARPS)
 ns_consume_kernel(ms_ns_state s, uint64_t seed) {
-    extern __shared__ double sm[];
-    const int star = blockIdx.x;
+    extern __shared__ double sm_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int star = blockIdx.x * NS_WARPS + wib;
+    if (star >= s.S) return;
     const uint64_t round = *s.rng_round;
     const int K = s.K, Q = s.Q, nd = s.nd, ncol = s.nd + s.nder;
-    double *lp = sm;                       // K live ln-probabilities
-    double *sv = lp + K;                   // 64 reduction slots
-    double *sh = sv + 64;                  // 4 broadcast slots
-    int *si = reinterpret_cast<int *>(sh + 4);             // 64 ints = 32 doubles
+    const int per_warp = K + 2 * nd + nd * nd;             // lp, mean, variances, covariance
+    double *lp = sm_all + wib * per_warp;                  // K live ln-probabilities
+    double *mean = lp + K, *diag = mean + nd, *cov = diag + nd;
     const int64_t lbase = (int64_t)star * K;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) lp[k] = s.live_lp[lbase + k];
-    __syncthreads();
+    for (int k = lane; k < K; k += 32) lp[k] = s.live_lp[lbase + k];
+    __syncwarp();
     const double log_shrink = log1p(-exp(-1.0 / K));
     bool done = s.done[star] != 0;
-    const int done_in = s.done[star];
     int nacc_tot = 0;
     if (!done) {
-        if (threadIdx.x == 0 && round > 0) s.ncall[star] += (int64_t)Q * s.walks;     // the walk steps of this round
+        if (lane == 0 && round > 0) s.ncall[star] += (int64_t)Q * s.walks;           // the walk steps of this round
         for (int q = 0; q < Q; ++q) {
             const int64_t wk = (int64_t)star * Q + q;
             nacc_tot += s.nacc[wk];
             double lmin, lmax; int w;
-            ns_minmax(lp, K, sv, si, lmin, w, lmax);
+            ns_minmax(lp, K, lane, lmin, w, lmax);
             const double lpq = s.cur_lp[wk];
             if (!(s.nacc[wk] > 0 && lpq > lmin)) continue;          // never moved, or overtaken by the threshold
             const int64_t it = s.niter[star];
@@ -164,57 +159,54 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
             const double *row_w = s.live_row + (lbase + w) * ncol;
             if (s.dead && it < s.dead_cap) {                        // optional dead-point record
                 double *o = s.dead + ((int64_t)star * s.dead_cap + it) * (ncol + 3);
-                for (int c = threadIdx.x; c < ncol; c += blockDim.x) o[c] = row_w[c];
-                if (threadIdx.x == 0) { o[ncol] = lmin; o[ncol + 1] = logvol; o[ncol + 2] = logwt; }
+                for (int c = lane; c < ncol; c += 32) o[c] = row_w[c];
+                if (lane == 0) { o[ncol] = lmin; o[ncol + 1] = logvol; o[ncol + 2] = logwt; }
             }
-            ns_accumulate(s, star, lmin, logwt, row_w, ncol, sh);
+            ns_accumulate(s, star, lmin, logwt, row_w, ncol, lane);
             // the candidate replaces the worst live point
-            for (int c = threadIdx.x; c < ncol; c += blockDim.x) s.live_row[(lbase + w) * ncol + c] = s.cur_row[wk * ncol + c];
-            for (int d = threadIdx.x; d < nd; d += blockDim.x) s.live_u[(lbase + w) * nd + d] = s.cur_u[wk * nd + d];
-            if (threadIdx.x == 0) { lp[w] = lpq; s.live_lp[lbase + w] = lpq; s.niter[star] = it + 1; }
-            __syncthreads();
+            for (int c = lane; c < ncol; c += 32) s.live_row[(lbase + w) * ncol + c] = s.cur_row[wk * ncol + c];
+            for (int d = lane; d < nd; d += 32) s.live_u[(lbase + w) * nd + d] = s.cur_u[wk * nd + d];
+            if (lane == 0) { lp[w] = lpq; s.live_lp[lbase + w] = lpq; s.niter[star] = it + 1; }
+            __syncwarp();
             lmax = fmax(lmax, lpq);
             const double lz = s.logz[star];
             const double dl = logaddexp_d(lz, lmax + logvol) - lz;
             if (dl < s.dlogz || it + 1 >= s.maxiter) { done = true; break; }
         }
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             s.done[star] = done ? 1 : 0;
-            (void)done_in;
             // dynesty's rwalk scale update towards 50 % acceptance
             const double facc = (double)nacc_tot / ((double)Q * s.walks);
             double sc = s.scale[star] * exp((facc - 0.5) / nd / 0.5);
             s.scale[star] = fmin(fmax(sc, 1e-4), 10.0);
         }
     }
-    __syncthreads();
+    __syncwarp();
     // covariance of the live points and its Cholesky factor (proposal shape of the next rounds);
-    // at most Q of the K live points change per round, so it is refreshed every ~16 replacements
+    // at most Q of the K live points change per round, so it is refreshed every ~16 replacements.
+    // Lane pe owns covariance entry pe (nd * nd <= 32 in practice, otherwise the lanes stride); the live
+    // points stream through once per entry pair from L2, 7 KB per star.
     const uint64_t cov_every = (uint64_t)(Q >= 16 ? 1 : 16 / Q);
     if (round % cov_every == 0) {
-        double *mean = sv;                                   // nd <= 24 < 64 slots
-        double *cov = sm + (K + 64 + 4 + 32);                // nd * nd, after lp / sv / sh / si
-        double *lu = cov + nd * nd + nd;                     // K * nd: this star's live points, staged once
-        for (int i = threadIdx.x; i < K * nd; i += blockDim.x) lu[i] = s.live_u[lbase * nd + i];
-        __syncthreads();
-        for (int d = threadIdx.x; d < nd; d += blockDim.x) {
+        const double *lu = s.live_u + lbase * nd;
+        for (int d = lane; d < nd; d += 32) {
             double a = 0.0;
             for (int k = 0; k < K; ++k) a += lu[k * nd + d];
             mean[d] = a / K;
         }
-        __syncthreads();
-        for (int pe = threadIdx.x; pe < nd * nd; pe += blockDim.x) {
+        __syncwarp();
+        for (int pe = lane; pe < nd * nd; pe += 32) {
             const int d = pe / nd, e = pe - d * nd;
             if (e > d) { cov[pe] = 0.0; continue; }
             double a = 0.0;
-            for (int k = 0; k < K; ++k) a += (lu[k * nd + d] - mean[d]) * (lu[k * nd + e] - mean[e]);
+            const double md = mean[d], me = mean[e];
+            for (int k = 0; k < K; ++k) a += (lu[k * nd + d] - md) * (lu[k * nd + e] - me);
             cov[pe] = a / (K - 1);
         }
-        __syncthreads();
-        double *diag = sm + (K + 64 + 4 + 32 + nd * nd);     // variances, kept for the degenerate fallback
-        for (int d = threadIdx.x; d < nd; d += blockDim.x) diag[d] = cov[d * nd + d];
-        __syncthreads();
-        if (threadIdx.x == 0) {                              // in-place Cholesky, row by row, lower triangle
+        __syncwarp();
+        for (int d = lane; d < nd; d += 32) diag[d] = cov[d * nd + d];      // kept for the degenerate fallback
+        __syncwarp();
+        if (lane == 0) {                                     // in-place Cholesky, row by row, lower triangle
             bool ok = true;
             for (int i = 0; i < nd && ok; ++i)
                 for (int j = 0; j <= i; ++j) {
@@ -229,39 +221,39 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
                     out[i * nd + j] = ok ? (j <= i ? cov[i * nd + j] : 0.0)
                                          : (i == j ? sqrt(fmax(diag[i], 1e-24)) : 0.0);   // degenerate: diagonal
         }
-        __syncthreads();
+        __syncwarp();
     }
     // threshold and restart points of the next round: random live points other than the worst
     double lmin, lmax; int w;
-    ns_minmax(lp, K, sv, si, lmin, w, lmax);
-    if (threadIdx.x == 0) s.lmin[star] = lmin;
-    for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    ns_minmax(lp, K, lane, lmin, w, lmax);
+    if (lane == 0) s.lmin[star] = lmin;
+    for (int q = 0; q < Q; ++q) {                          // the warp copies one restart row at a time
         const int64_t wk = (int64_t)star * Q + q;
         curandStatePhilox4_32_10_t st;
         curand_init(seed ^ 0x9e3779b97f4a7c15ull, (unsigned long long)wk, round * 4ull, &st);
         int j = (int)(curand(&st) % (unsigned)(K - 1));
         if (j >= w) ++j;
-        s.cur_lp[wk] = lp[j];
-        s.nacc[wk] = 0;
-        for (int d = 0; d < nd; ++d) s.cur_u[wk * nd + d] = s.live_u[(lbase + j) * nd + d];
-        for (int c = 0; c < ncol; ++c) s.cur_row[wk * ncol + c] = s.live_row[(lbase + j) * ncol + c];
+        if (lane == 0) { s.cur_lp[wk] = lp[j]; s.nacc[wk] = 0; }
+        for (int d = lane; d < nd; d += 32) s.cur_u[wk * nd + d] = s.live_u[(lbase + j) * nd + d];
+        for (int c = lane; c < ncol; c += 32) s.cur_row[wk * ncol + c] = s.live_row[(lbase + j) * ncol + c];
     }
 }
 
 __global__ void ns_tick_kernel(uint64_t *counter) { *counter += 1; }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * NS_WARPS)
 ns_finalize_kernel(ms_ns_state s) {
-    __shared__ double sh[4];
-    const int star = blockIdx.x;
-    if (s.done[star] != 1) return;                     // only stars that finished and are not yet finalised
+    const int lane = threadIdx.x & 31;
+    const int star = blockIdx.x * NS_WARPS + (threadIdx.x >> 5);
+    if (star >= s.S || s.done[star] != 1) return;      // only stars that finished and are not yet finalised
     const int K = s.K, ncol = s.nd + s.nder;
     const double logvol_f = -((double)s.niter[star]) / K - log((double)K);
     for (int k = 0; k < K; ++k) {
         const double l = s.live_lp[(int64_t)star * K + k];
-        ns_accumulate(s, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, sh);
+        ns_accumulate(s, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, lane);
     }
-    if (threadIdx.x == 0) s.done[star] = 2;
+    __syncwarp();
+    if (lane == 0) s.done[star] = 2;
 }
 
 int check_state(const ms_ns_state *s) {
@@ -306,8 +298,8 @@ extern "C" int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, v
     int rc = check_state(s);
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
-    const size_t smem = (size_t)(s->K + 64 + 4 + 32 + s->nd * s->nd + s->nd + s->K * s->nd) * sizeof(double);   // lp, reductions, broadcast, int slots, covariance, variances, live points
-    ns_consume_kernel<<<(unsigned)s->S, 128, smem, (cudaStream_t)stream>>>(*s, seed);
+    const size_t smem = (size_t)NS_WARPS * (s->K + 2 * s->nd + s->nd * s->nd) * sizeof(double);   // per star: lp, mean, variances, covariance
+    ns_consume_kernel<<<(unsigned)((s->S + NS_WARPS - 1) / NS_WARPS), 32 * NS_WARPS, smem, (cudaStream_t)stream>>>(*s, seed);
     ns_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s->rng_round);
     ctx->launches += 2;
     MS_CUDA(cudaGetLastError());
@@ -318,7 +310,7 @@ extern "C" int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream) {
     int rc = check_state(s);
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
-    ns_finalize_kernel<<<(unsigned)s->S, 128, 0, (cudaStream_t)stream>>>(*s);
+    ns_finalize_kernel<<<(unsigned)((s->S + NS_WARPS - 1) / NS_WARPS), 32 * NS_WARPS, 0, (cudaStream_t)stream>>>(*s);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;
