@@ -80,24 +80,32 @@ __global__ void ns_accept_kernel(ms_ns_state s) {
 // how many stars are in flight per SM.
 constexpr int NS_WARPS = 4;
 
-// update of ln Z, H and the weighted posterior moments of one star with a point of ln weight logwt
-__device__ __forceinline__ void ns_accumulate(const ms_ns_state &s, int star, double lnl, double logwt,
-                                              const double *row, int ncol, int lane) {
-    double r_old = 0.0, w = 0.0;
-    if (lane == 0) {
-        const double lz = s.logz[star], lz_new = logaddexp_d(lz, logwt);
-        double h = s.hacc[star] * exp(lz - lz_new) + exp(logwt - lz_new) * lnl;
-        if (lz == -ms_inf()) h = exp(logwt - lz_new) * lnl;
-        s.hacc[star] = h;
-        s.logz[star] = lz_new;
-        const double m_old = s.wmax[star], m_new = fmax(m_old, logwt);
-        r_old = (m_old == -ms_inf()) ? 0.0 : exp(m_old - m_new);
-        w = exp(logwt - m_new);
-        s.wmax[star] = m_new;
-        s.wtot[star] = s.wtot[star] * r_old + w;
+// Evidence state of one star, held in registers by every lane of its warp (loaded with one round of
+// independent loads, written back once) so the update chain never waits on global memory.
+struct NsEv {
+    double logz, hacc, wmax, wtot;
+    __device__ void load(const ms_ns_state &s, int star) {
+        logz = s.logz[star]; hacc = s.hacc[star]; wmax = s.wmax[star]; wtot = s.wtot[star];
     }
-    r_old = __shfl_sync(0xffffffffu, r_old, 0);
-    w = __shfl_sync(0xffffffffu, w, 0);
+    __device__ void store(const ms_ns_state &s, int star) const {
+        s.logz[star] = logz; s.hacc[star] = hacc; s.wmax[star] = wmax; s.wtot[star] = wtot;
+    }
+};
+
+// update of ln Z, H and the weighted posterior moments of one star with a point of ln weight logwt
+// (all lanes compute the same scalars; the lanes share the columns of the moment sums)
+__device__ __forceinline__ void ns_accumulate(const ms_ns_state &s, NsEv &ev, int star, double lnl, double logwt,
+                                              const double *row, int ncol, int lane) {
+    const double lz = ev.logz, lz_new = logaddexp_d(lz, logwt);
+    double h = ev.hacc * exp(lz - lz_new) + exp(logwt - lz_new) * lnl;
+    if (lz == -ms_inf()) h = exp(logwt - lz_new) * lnl;
+    ev.hacc = h;
+    ev.logz = lz_new;
+    const double m_old = ev.wmax, m_new = fmax(m_old, logwt);
+    const double r_old = (m_old == -ms_inf()) ? 0.0 : exp(m_old - m_new);
+    const double w = exp(logwt - m_new);
+    ev.wmax = m_new;
+    ev.wtot = ev.wtot * r_old + w;
     for (int c = lane; c < ncol; c += 32) {
         double v = row[c];
         if (!(fabs(v) < 1e300)) v = 0.0;
@@ -105,7 +113,6 @@ __device__ __forceinline__ void ns_accumulate(const ms_ns_state &s, int star, do
         s.wsum[at] = s.wsum[at] * r_old + w * v;
         s.wsq[at] = s.wsq[at] * r_old + w * v * v;
     }
-    __syncwarp();
 }
 
 // warp-wide arg-min (lowest index on ties) and max of lp[0..K); the result is in every lane
@@ -127,7 +134,7 @@ __device__ __forceinline__ void ns_minmax(const double *lp, int K, int lane, dou
     vmin = mn; imin = im; vmax = mx;
 }
 
-__global__ void __launch_bounds__(32 * NS_WARPS)
+__global__ void __launch_bounds__(32 * NS_WARPS, 8)
 ns_consume_kernel(ms_ns_state s, uint64_t seed) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -145,6 +152,11 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
     bool done = s.done[star] != 0;
     int nacc_tot = 0;
     if (!done) {
+        // everything the update chain needs, requested together
+        NsEv ev; ev.load(s, star);
+        int64_t it = s.niter[star];
+        const int64_t it_in = it;
+        const double scale_in = s.scale[star];
         if (lane == 0 && round > 0) s.ncall[star] += (int64_t)Q * s.walks;           // the walk steps of this round
         for (int q = 0; q < Q; ++q) {
             const int64_t wk = (int64_t)star * Q + q;
@@ -153,7 +165,6 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
             ns_minmax(lp, K, lane, lmin, w, lmax);
             const double lpq = s.cur_lp[wk];
             if (!(s.nacc[wk] > 0 && lpq > lmin)) continue;          // never moved, or overtaken by the threshold
-            const int64_t it = s.niter[star];
             const double logvol = -((double)it + 1.0) / K;
             const double logwt = lmin + (logvol + 1.0 / K + log_shrink);
             const double *row_w = s.live_row + (lbase + w) * ncol;
@@ -162,22 +173,24 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
                 for (int c = lane; c < ncol; c += 32) o[c] = row_w[c];
                 if (lane == 0) { o[ncol] = lmin; o[ncol + 1] = logvol; o[ncol + 2] = logwt; }
             }
-            ns_accumulate(s, star, lmin, logwt, row_w, ncol, lane);
+            ns_accumulate(s, ev, star, lmin, logwt, row_w, ncol, lane);
+            __syncwarp();                                       // row_w read by every lane before it is replaced
             // the candidate replaces the worst live point
             for (int c = lane; c < ncol; c += 32) s.live_row[(lbase + w) * ncol + c] = s.cur_row[wk * ncol + c];
             for (int d = lane; d < nd; d += 32) s.live_u[(lbase + w) * nd + d] = s.cur_u[wk * nd + d];
-            if (lane == 0) { lp[w] = lpq; s.live_lp[lbase + w] = lpq; s.niter[star] = it + 1; }
+            if (lane == 0) { lp[w] = lpq; s.live_lp[lbase + w] = lpq; }
+            ++it;
             __syncwarp();
             lmax = fmax(lmax, lpq);
-            const double lz = s.logz[star];
-            const double dl = logaddexp_d(lz, lmax + logvol) - lz;
-            if (dl < s.dlogz || it + 1 >= s.maxiter) { done = true; break; }
+            const double dl = logaddexp_d(ev.logz, lmax + logvol) - ev.logz;
+            if (dl < s.dlogz || it >= s.maxiter) { done = true; break; }
         }
         if (lane == 0) {
+            if (it != it_in) { ev.store(s, star); s.niter[star] = it; }
             s.done[star] = done ? 1 : 0;
             // dynesty's rwalk scale update towards 50 % acceptance
             const double facc = (double)nacc_tot / ((double)Q * s.walks);
-            double sc = s.scale[star] * exp((facc - 0.5) / nd / 0.5);
+            const double sc = scale_in * exp((facc - 0.5) / nd / 0.5);
             s.scale[star] = fmin(fmax(sc, 1e-4), 10.0);
         }
     }
@@ -248,12 +261,13 @@ ns_finalize_kernel(ms_ns_state s) {
     if (star >= s.S || s.done[star] != 1) return;      // only stars that finished and are not yet finalised
     const int K = s.K, ncol = s.nd + s.nder;
     const double logvol_f = -((double)s.niter[star]) / K - log((double)K);
+    NsEv ev; ev.load(s, star);
     for (int k = 0; k < K; ++k) {
         const double l = s.live_lp[(int64_t)star * K + k];
-        ns_accumulate(s, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, lane);
+        ns_accumulate(s, ev, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, lane);
     }
     __syncwarp();
-    if (lane == 0) s.done[star] = 2;
+    if (lane == 0) { ev.store(s, star); s.done[star] = 2; }
 }
 
 int check_state(const ms_ns_state *s) {
