@@ -9,14 +9,13 @@
 // point (ln X_i = -i / K), provided it still lies above the rising likelihood threshold --
 // exactly dynesty's `queue_size` logic: a point uniform in {L > L_a} that also satisfies
 // L > L_b >= L_a is uniform in {L > L_b}.
-//   ns_propose_kernel   Gaussian step in the unit cube, reflected at the walls (Philox)
+//   ns_propose_kernel   Gaussian step in the unit cube, reflected at the walls (counter-based RNG)
 //   ns_accept_kernel    accept iff lnprob > threshold of the round; carries theta / derived along
 //   ns_consume_kernel   worst point, ln Z / H / posterior moments, replacement, stopping rule,
 //                       live-point spread, step-scale adaptation, restart points of the next round
 //   ns_finalize_kernel  contribution of the remaining live points
 #include "common.cuh"
 
-#include <curand_kernel.h>
 
 namespace {
 
@@ -27,20 +26,33 @@ __device__ __forceinline__ double logaddexp_d(double a, double b) {
     return m + log1p(exp(-fabs(a - b)));
 }
 
+// counter-based generator: splitmix64 finaliser of a linear mix of (seed, stream, counter)
+__device__ __forceinline__ uint64_t ns_mix(uint64_t seed, uint64_t stream, uint64_t counter) {
+    uint64_t z = seed + stream * 0xbf58476d1ce4e5b9ull + counter * 0x94d049bb133111ebull + 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
 __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
     const int64_t n = (int64_t)s.S * s.Q;
     for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < n; wk += (int64_t)gridDim.x * blockDim.x) {
         const int star = (int)(wk / s.Q);
-        curandStatePhilox4_32_10_t st;
-        curand_init(seed, (unsigned long long)wk, (*s.rng_round * (uint64_t)s.walks + step) * 32ull, &st);
+        const uint64_t ctr = (*s.rng_round * (uint64_t)s.walks + step) * 16ull;
         const double sc = s.scale[star];
         // step = scale * L z with L the Cholesky factor of the live-point covariance (the analogue of
         // dynesty's rwalk proposing along the axes of the bounding ellipsoid)
         double zv[MS_NPARAM];
         for (int d = 0; d < s.nd; d += 2) {
-            const double2 g = curand_normal2_double(&st);
-            zv[d] = g.x;
-            if (d + 1 < s.nd) zv[d + 1] = g.y;
+            // Box-Muller on two 32-bit uniforms in (0, 1)
+            const uint64_t z = ns_mix(seed, (uint64_t)wk, ctr + (uint64_t)(d >> 1));
+            const double u1 = ((double)(uint32_t)(z >> 32) + 0.5) * 2.3283064365386963e-10;
+            const double u2 = ((double)(uint32_t)z + 0.5) * 2.3283064365386963e-10;
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            zv[d] = rad * cs;
+            if (d + 1 < s.nd) zv[d + 1] = rad * sn;
         }
         const double *Lc = s.sigma + (int64_t)star * s.nd * s.nd;
         for (int d = 0; d < s.nd; ++d) {
@@ -135,7 +147,7 @@ __device__ __forceinline__ void ns_minmax(const double *lp, int K, int lane, dou
 }
 
 __global__ void __launch_bounds__(32 * NS_WARPS, 8)
-ns_consume_kernel(ms_ns_state s, uint64_t seed) {
+ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
     extern __shared__ double sm_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int star = blockIdx.x * NS_WARPS + wib;
@@ -148,7 +160,6 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
     const int64_t lbase = (int64_t)star * K;
     for (int k = lane; k < K; k += 32) lp[k] = s.live_lp[lbase + k];
     __syncwarp();
-    const double log_shrink = log1p(-exp(-1.0 / K));
     bool done = s.done[star] != 0;
     int nacc_tot = 0;
     if (!done) {
@@ -242,9 +253,9 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed) {
     if (lane == 0) s.lmin[star] = lmin;
     for (int q = 0; q < Q; ++q) {                          // the warp copies one restart row at a time
         const int64_t wk = (int64_t)star * Q + q;
-        curandStatePhilox4_32_10_t st;
-        curand_init(seed ^ 0x9e3779b97f4a7c15ull, (unsigned long long)wk, round * 4ull, &st);
-        int j = (int)(curand(&st) % (unsigned)(K - 1));
+        // one draw per walker and round: a counter-based mix (splitmix64 finaliser) of (seed, walker, round)
+        const uint64_t z = ns_mix(seed ^ 0x5851f42d4c957f2dull, (uint64_t)wk, round);
+        int j = (int)(((z >> 32) * (uint64_t)(K - 1)) >> 32);       // uniform in [0, K - 1)
         if (j >= w) ++j;
         if (lane == 0) { s.cur_lp[wk] = lp[j]; s.nacc[wk] = 0; }
         for (int d = lane; d < nd; d += 32) s.cur_u[wk * nd + d] = s.live_u[(lbase + j) * nd + d];
@@ -313,7 +324,8 @@ extern "C" int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, v
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
     const size_t smem = (size_t)NS_WARPS * (s->K + 2 * s->nd + s->nd * s->nd) * sizeof(double);   // per star: lp, mean, variances, covariance
-    ns_consume_kernel<<<(unsigned)((s->S + NS_WARPS - 1) / NS_WARPS), 32 * NS_WARPS, smem, (cudaStream_t)stream>>>(*s, seed);
+    const double log_shrink = std::log1p(-std::exp(-1.0 / s->K));             // ln(1 - e^{-1/K}): the shell width
+    ns_consume_kernel<<<(unsigned)((s->S + NS_WARPS - 1) / NS_WARPS), 32 * NS_WARPS, smem, (cudaStream_t)stream>>>(*s, seed, log_shrink);
     ns_tick_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s->rng_round);
     ctx->launches += 2;
     MS_CUDA(cudaGetLastError());
