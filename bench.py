@@ -193,6 +193,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     from minesweeper_b200.likelihood import likelihood
     L = likelihood(fitargs, fitpars, runbools, precision=args.precision, device=local, verbose=False)
