@@ -192,7 +192,10 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    numa_cores = None
     if world > 1:
+        from minesweeper_b200.distributed import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local)          # before the pinned staging buffers are allocated
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line
         if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
             os.environ['NCCL_DEBUG'] = 'WARN'
@@ -324,6 +327,7 @@ def main():
             config=dict(workload=workload_name(args, fitargs['MISTpath']), precision=args.precision,
                         l2='flushed between steps (256 MiB memset outside the timed events)',
                         collective='all_gather_into_tensor(lnL) per step' if world > 1 else 'none',
+                        host_affinity=('%d cores local to the GPU' % len(numa_cores)) if numa_cores else 'default',
                         flop_per_eval=flop_pt),
             clocks=clocks,
             e2e=dict(value=e2e, unit=UNIT, h2d_bytes_per_step=B * theta_np.shape[1] * 8,

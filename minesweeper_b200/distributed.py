@@ -67,3 +67,24 @@ def star_blocks(n_stars, rank=None, size=None):
     size = s if size is None else size
     lo, hi = shard_bounds(n_stars, rank, size)
     return np.arange(lo, hi)
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process (and the pinned host buffers it allocates afterwards) to the CPU cores NVML reports as
+    local to the GPU.  With one process per GPU the host<->device copies of every rank then stay on their own
+    socket.  Returns the core list, or None when NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
