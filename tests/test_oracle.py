@@ -85,3 +85,30 @@ def test_mist_ingest_roundtrip_and_reference_lib(tmp_path):
     ie, im, jf, ja = G.X.T
     np.testing.assert_array_equal(dense['values'][ja, jf, im, ie], G.output)
     assert dense['valid'].sum() == len(G.output)
+
+
+def test_postproc_weighted_quantiles(tmp_path):
+    """minesweeper_b200.postproc against the oracle's restatement of Payne's weighted quantile and against an
+    analytic case (equal weights on a fine grid)."""
+    from minesweeper_b200 import postproc
+    from oracle.payne_port import quantile
+    rng = np.random.default_rng(11)
+    x = rng.normal(2.0, 0.5, 4000)
+    w = rng.uniform(0.0, 1.0, 4000)
+    q = [0.001, 0.16, 0.5, 0.84, 0.999]
+    np.testing.assert_allclose(postproc.weighted_quantile(x, q, w), quantile(x, q, weights=w), rtol=0, atol=1e-14)
+    g = np.linspace(0.0, 1.0, 100001)
+    np.testing.assert_allclose(postproc.weighted_quantile(g, [0.16, 0.5, 0.84], np.ones_like(g)), [0.16, 0.5, 0.84],
+                               atol=2e-5)
+    # a samples file in the reference layout: quantiles of a weighted Gaussian posterior
+    n = 3000
+    logwt = -0.5 * ((x[:n] - 2.0) / 0.5) ** 2 * 0.0 + np.log(w[:n] + 1e-12)
+    path = tmp_path / 'star_samp.dat'
+    with open(path, 'w') as f:
+        f.write('Iter Dist log(lk) log(vol) log(wt) h nc log(z) delta(log(z))\n')
+        for i in range(n):
+            f.write('%d %.12g 0 0 %.12g nan nan nan nan\n' % (i, x[i], logwt[i]))
+    st = postproc.summarize_samples_file(str(path))['Dist']
+    ref = quantile(x[:n], [0.16, 0.5, 0.84], weights=w[:n] + 1e-12)
+    np.testing.assert_allclose(st[:3], ref, rtol=1e-9)
+    assert abs(st[3] - 0.5) < 0.05 and st[4][0] < st[0] < st[2] < st[4][1]
