@@ -229,6 +229,15 @@ int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, void *stream
 /* adds the remaining live points of every star with done == 1 and marks it 2 */
 int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
 
+/* In the tensor-core modes a photometry-only isochrone batch (likelihood.lnlikefn with runbools =
+ * [spec off, phot on], reference likelihood.py:92-181) runs as ONE kernel: the MIST interpolation of
+ * fastMISTmod.GenMIST.getMIST (fastMISTmod.py:100-108) is folded into the prologue of the photometric
+ * MLP kernel and the per-point parameter block never exists in HBM.  Results are identical to the
+ * two-kernel sequence up to rounding (same interpolation code).  Applied to batches of at least four tile pairs
+ * per SM (smaller batches keep the two-kernel sequence, which is faster there).  ms_set_fusion(ctx, 0) selects
+ * the two-kernel sequence always (used by the tests and to time kernel (1) on its own); the default is 1. */
+int ms_set_fusion(ms_ctx *ctx, int enable);
+
 /* Number of kernel launches issued by this ctx so far (bench bookkeeping). */
 int64_t ms_launch_count(const ms_ctx *ctx);
 

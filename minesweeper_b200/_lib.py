@@ -122,6 +122,7 @@ PROTOTYPES = {
     'ms_ns_consume': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_void_p]),
     'ms_ns_finalize': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
+    'ms_set_fusion': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_read': (C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int64)]),
 }

@@ -320,6 +320,12 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
 extern "C" int ms_precision(const ms_ctx *ctx) { return ctx ? ctx->precision : MS_EINVAL; }
 extern "C" int64_t ms_launch_count(const ms_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int ms_set_fusion(ms_ctx *ctx, int enable) {
+    if (!ctx) { ms_set_error("bad arguments"); return MS_EINVAL; }
+    ctx->fuse_interp = enable ? 1 : 0;
+    return MS_OK;
+}
+
 extern "C" int ms_profile_enable(ms_ctx *ctx, int on) {
     if (!ctx) return MS_EINVAL;
     for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -493,6 +499,15 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
     if (!iso && (derived || brackets)) {
         ms_set_error("derived / brackets requested but EEP is not a parameter");
         return MS_EINVAL;
+    }
+    // photometry-only isochrone batch on the tensor-core path: interpolation folded into the MLP kernel
+    // (worth it once every persistent CTA sweeps several tile pairs, so that the interpolation of pair k + 1
+    // hides behind the MLP of pair k; below that the two-kernel sequence is faster)
+    if (iso && flags->phot && !flags->spec && !brackets && ctx->fuse_interp && ctx->precision >= MS_PREC_TC &&
+        B >= (int64_t)ctx->sm_count * 256 * 4 && phot_tc_can_fuse(ctx)) {
+        PhotArgs pa{nullptr, star_slot, nullptr, nullptr};
+        pa.lnL = lnL; pa.ageweight = flags->ageweight;
+        return launch_phot_tc_fused(ctx, tv, pa, derived, flags->mistdif, B, st);
     }
     if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS))) return rc;
     // chi2 scratch is only needed when a spectrum term precedes the photometry

@@ -73,6 +73,7 @@ struct StarDev {
 struct ms_ctx {
     int device = 0;
     int precision = MS_PREC_F32;
+    int fuse_interp = 1;           // ms_set_fusion
     int sm_count = 148;
     GridDev grid;
     PhotNetDev phot;
@@ -163,6 +164,10 @@ struct PhotArgs {
 int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
 int phot_tc_prepare(ms_ctx *ctx);          // pack weights for the tensor-core kernel
 int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
+// fused kernels (1) + (2): the prologue warpgroup of the tensor-core kernel interpolates the grid itself
+bool phot_tc_can_fuse(const ms_ctx *ctx);
+int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, double *derived, int mistdif,
+                         int64_t B, cudaStream_t st);
 
 struct SpecArgs {
     const double *pars;            // [B][MS_NPARS]

@@ -13,39 +13,9 @@
 // HBM-bound: algorithmic bytes per point = 4*8 (theta) + 16*9*sizeof(T) (corners)
 // + 13*8 (derived) -> 712 B (f32 table) / 1288 B (f64 table).
 #include "common.cuh"
+#include "mist_interp.cuh"
 
 namespace {
-
-// number of axis values <= x, minus one  ==  np.digitize([x], g, right=False) - 1.
-// NaN compares false everywhere and lands at n - 1, like NumPy's NaN-last ordering.
-__device__ __forceinline__ int bracket_of(const double *g, int n, double x) {
-    int lo = 0, hi = n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (x < g[mid]) hi = mid; else lo = mid + 1;
-    }
-    return lo - 1;
-}
-
-template <typename T> struct Row;
-template <> struct Row<float> {
-    static constexpr int CP = MS_CP32;
-    __device__ static void load(const float *p, double *v) {
-        const float4 *q = reinterpret_cast<const float4 *>(p);
-        float4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; v[8] = c.x;
-    }
-};
-template <> struct Row<double> {
-    static constexpr int CP = MS_CP64;
-    __device__ static void load(const double *p, double *v) {
-        const double2 *q = reinterpret_cast<const double2 *>(p);
-        double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x;
-        v[5] = c.y; v[6] = d.x; v[7] = d.y; v[8] = e.x;
-    }
-};
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -59,7 +29,6 @@ mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int
     __syncthreads();
     const double *g[4] = {s_axes, s_axes + ne, s_axes + ne + nm, s_axes + ne + nm + nf};
     const int n[4] = {ne, nm, nf, na};
-    constexpr int CP = Row<T>::CP;
 
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < B;
          p += (int64_t)gridDim.x * blockDim.x) {
@@ -69,56 +38,11 @@ mist_interp_kernel(ThetaView tv, int64_t B, const double *__restrict__ axes, int
         x[2] = theta_get(tv, p, MS_P_INIT_FEH);
         x[3] = theta_get(tv, p, MS_P_INIT_AFE);
         int idx[4];
-        double wl[4], wu[4];
-        bool inside = true;
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            int i = bracket_of(g[d], n[d], x[d]);
-            idx[d] = i;
-            inside = inside && (i >= 0) && (i <= n[d] - 2);
-            int ic = inside ? i : 0;
-            // same operation order as the reference: frac, i + frac, then dx per corner
-            double frac = (x[d] - g[d][ic]) / (g[d][ic + (n[d] > 1 ? 1 : 0)] - g[d][ic]);
-            double xt = (double)ic + frac;
-            double dl = xt - (double)ic;           // >= 0
-            double du = xt - (double)(ic + 1);     // in [-1, 0)
-            wl[d] = 1.0 - dl;
-            wu[d] = (du > -1.0) ? 1.0 + du : 0.0;
-        }
+        double acc[MS_NCOL], wsum;
+        const bool inside = mist::interp_point<T, 1>(g, n, table, x, idx, acc, wsum);
         if (brackets) {
             int4 b4 = make_int4(idx[0], idx[1], idx[2], idx[3]);
             *reinterpret_cast<int4 *>(brackets + 4 * p) = b4;
-        }
-        double acc[MS_NCOL];
-#pragma unroll
-        for (int c = 0; c < MS_NCOL; ++c) acc[c] = 0.0;
-        double wsum = 0.0;
-        if (inside) {
-            const int64_t sE = CP, sM = (int64_t)ne * CP, sF = (int64_t)nm * sM, sA = (int64_t)nf * sF;
-            const T *base = table + idx[3] * sA + idx[2] * sF + idx[1] * sM + idx[0] * sE;
-            // ascending reference row id = (feh, afe, mass, eep) nesting
-#pragma unroll
-            for (int cf = 0; cf < 2; ++cf)
-#pragma unroll
-                for (int ca = 0; ca < 2; ++ca)
-#pragma unroll
-                    for (int cm = 0; cm < 2; ++cm)
-#pragma unroll
-                        for (int ce = 0; ce < 2; ++ce) {
-                            double w = (ce ? wu[0] : wl[0]);
-                            w = w * (cm ? wu[1] : wl[1]);
-                            w = w * (cf ? wu[2] : wl[2]);
-                            w = w * (ca ? wu[3] : wl[3]);
-                            if (w > 0.0) {
-                                double v[MS_NCOL];
-                                Row<T>::load(base + ca * sA + cf * sF + cm * sM + ce * sE, v);
-                                if (v[0] == v[0]) {      // vertex present
-                                    wsum += w;
-#pragma unroll
-                                    for (int c = 0; c < MS_NCOL; ++c) acc[c] = fma(w, v[c], acc[c]);
-                                }
-                            }
-                        }
         }
         const bool ok = inside && (wsum > 0.0);
         if (okflag) okflag[p] = ok ? 1 : 0;

@@ -30,6 +30,7 @@
 //                          product goes to A through shared memory)
 // TMEM: 2 tiles x (128 columns D1/A1 + 128 columns D2) = 512 columns.
 #include "common.cuh"
+#include "mist_interp.cuh"
 #include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
@@ -62,11 +63,12 @@ constexpr int X_BYTES = 2 * 128 * 16;                  // one X tile image (hi o
 constexpr int SM_W = 0;                                // 2 ring slots
 constexpr int SM_X = SM_W + 2 * RING_BYTES;            // [2 pair buffers][2 tiles][hi, lo] X tile images
 constexpr int SM_PT = SM_X + 8 * X_BYTES;              // [2 pair buffers][256 points] PointState
-constexpr int SM_PART = SM_PT + 2 * 256 * 16;          // float[2 band parities][2 tiles][128]: B's partial dot products
+constexpr int SM_PART = SM_PT + 2 * 256 * 24;          // float[2 band parities][2 tiles][128]: B's partial dot products
 constexpr int SM_BAR = SM_PART + 2048;                 // mbarriers
 constexpr int SM_CONST = SM_BAR + 256;                 // [nb][CONST_BYTES] epilogue constants
 constexpr int SM_FIXED = SM_CONST;
-constexpr int MAX_NB = (227 * 1024 - SM_FIXED) / CONST_BYTES;
+constexpr int SMEM_LIMIT = 227 * 1024 - 4096;          // opt-in maximum minus the static part and the reserved KB
+constexpr int MAX_NB = (SMEM_LIMIT - SM_FIXED) / CONST_BYTES;
 
 // instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = make_idesc_f16(128, 128);
@@ -75,7 +77,8 @@ enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR
        BAR_XEMPTY = 26, BAR_N = 28 };
 
 // what the prologue warpgroup hands to the chi-square threads for one point
-struct PointState { double mag0; int32_t slot; int32_t ok; };
+struct PointState { double mag0, agewgt; int32_t slot; int32_t ok; };
+static_assert(sizeof(PointState) == 24, "PointState layout");
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -133,6 +136,13 @@ struct TcArgs {
     const unsigned char *wimg;         // [nb][BAND_BYTES]
     double xmin[8], xscale[8];
     int nb, d_in;
+    // fused form: the prologue warpgroup interpolates the MIST grid itself (kernel (1) folded in), so the
+    // parameter block never exists in HBM; `pars` is then unused
+    int fused;
+    ThetaView tv;
+    const double *axes; const float *table;
+    int ne, nm, nf, na, mistdif;
+    double *derived;                   // [B][MS_NDERIVED] or nullptr
 };
 
 // FAST = MS_PREC_TC16: sigmoid(z) = 1/2 + tanh(z/2)/2 with the affine part folded into the next
@@ -170,6 +180,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         reinterpret_cast<uint4 *>(smem + SM_CONST + b * CONST_BYTES)[o] =
             reinterpret_cast<const uint4 *>(a.wimg + (size_t)b * BAND_BYTES + OFF_CB2)[o];
     }
+    double *s_axes = reinterpret_cast<double *>(smem + SM_CONST + nb * CONST_BYTES);     // grid axes (fused form)
+    if (a.fused)
+        for (int i = threadIdx.x; i < a.ne + a.nm + a.nf + a.na; i += NTHREADS) s_axes[i] = a.axes[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -260,19 +273,57 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
 #pragma unroll 1
             for (int T = 0; T < 2; ++T) {
                 const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + tid;
-                PointState ps{0.0, 0, 0};
+                PointState ps{0.0, 1.0, 0, 0};
                 float xs[8];
 #pragma unroll
                 for (int d = 0; d < 8; ++d) xs[d] = 0.f;
                 if (p < B) {
-                    const double *q = a.pars + p * MS_NPARS;
-                    const double teff = q[PV_TEFF];
+                    double teff, logt, logg, feh, afe, logr, dist, av;
+                    if (a.fused) {
+                        // kernel (1) for this point: brackets, corner gather, renormalised sum, then the
+                        // parameter block of likelihood.lnlikefn (likelihood.py:121-141) in registers
+                        const double *g[4] = {s_axes, s_axes + a.ne, s_axes + a.ne + a.nm, s_axes + a.ne + a.nm + a.nf};
+                        const int n[4] = {a.ne, a.nm, a.nf, a.na};
+                        double x[4];
+                        x[0] = theta_get(a.tv, p, MS_P_EEP);
+                        x[1] = theta_get(a.tv, p, MS_P_INIT_MASS);
+                        x[2] = theta_get(a.tv, p, MS_P_INIT_FEH);
+                        x[3] = theta_get(a.tv, p, MS_P_INIT_AFE);
+                        int idx[4];
+                        double acc[MS_NCOL], wsum;
+                        const bool inside = mist::interp_point<float, FAST ? 1 : 2>(g, n, a.table, x, idx, acc, wsum);   // rows per round trip: measured
+                        const bool okp = inside && (wsum > 0.0);
+                        const double inv = okp ? 1.0 / wsum : 0.0;
+                        const double inf = ms_inf();
+                        // Teff = 10**log(Teff) (likelihood.py:121) is only needed as a network input here;
+                        // genphot's log10(Teff) (genmod.py:111) is the interpolated value itself
+                        logt = acc[4] * inv;
+                        teff = okp ? exp10(logt) : inf;
+                        logg = okp ? acc[7] * inv : inf;
+                        feh = okp ? (a.mistdif ? acc[5] * inv : x[2]) : inf;     // :127-132
+                        afe = okp ? (a.mistdif ? acc[6] * inv : x[3]) : inf;
+                        logr = okp ? acc[2] * inv : inf;
+                        ps.agewgt = okp ? acc[8] * inv : inf;
+                        dist = theta_get(a.tv, p, MS_P_DIST);
+                        av = theta_get(a.tv, p, MS_P_AV);
+                        if (a.derived) {
+                            double *o = a.derived + p * MS_NDERIVED;
+                            o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
+#pragma unroll
+                            for (int c = 0; c < MS_NCOL; ++c) o[4 + c] = okp ? acc[c] * inv : inf;
+                        }
+                    } else {
+                        const double *q = a.pars + p * MS_NPARS;
+                        teff = q[PV_TEFF]; logg = q[PV_LOGG]; feh = q[PV_FEH]; afe = q[PV_AFE];
+                        logr = q[PV_LOGR]; dist = q[PV_DIST]; av = q[PV_AV];
+                        ps.agewgt = q[PV_AGEWGT];
+                        logt = log10(teff);                                  // genmod.py:111-113
+                    }
                     if (teff != ms_inf()) {
                         ps.ok = 1;
-                        const double logt = log10(teff);                     // genmod.py:111-113
-                        const double logl = 2.0 * q[PV_LOGR] + 4.0 * (logt - log10(5770.0));
-                        ps.mag0 = -2.5 * logl + 4.74 + 5.0 * log10(q[PV_DIST]) - 5.0;
-                        const double xin[6] = {pow(10.0, logt), q[PV_LOGG], q[PV_FEH], q[PV_AFE], q[PV_AV], 3.1};
+                        const double logl = 2.0 * logr + 4.0 * (logt - log10(5770.0));
+                        ps.mag0 = -2.5 * logl + 4.74 + 5.0 * log10(dist) - 5.0;
+                        const double xin[6] = {teff, logg, feh, afe, av, 3.1};    // 10**logt of the reference's sed()
 #pragma unroll
                         for (int d = 0; d < 6; ++d)
                             if (d < a.d_in) xs[d] = (float)((xin[d] - a.xmin[d]) * a.xscale[d] - 0.5);
@@ -319,12 +370,12 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + r;
             const bool live = half == 0 && p < B;
             bool ok = false;
-            double mag0 = 0.0;
+            double mag0 = 0.0, agewgt = 1.0;
             int slot = 0;
             if (half == 0) {                           // point state from the prologue warpgroup
                 mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
                 const PointState ps = reinterpret_cast<const PointState *>(smem + SM_PT)[((it & 1) * 2 + T) * TILE + r];
-                ok = ps.ok != 0; mag0 = ps.mag0; slot = ps.slot;
+                ok = ps.ok != 0; mag0 = ps.mag0; agewgt = ps.agewgt; slot = ps.slot;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(BAR_XEMPTY + (it & 1)));
             }
@@ -432,7 +483,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 double l = -ms_inf();
                 if (ok) {
                     l = -0.5 * ((a.chi2 ? a.chi2[p] : 0.0) + chi2);
-                    if (a.ageweight) l += log(a.pars[p * MS_NPARS + PV_AGEWGT]);
+                    if (a.ageweight) l += log(agewgt);
                 }
                 a.lnL[p] = l;
             } else if (ok && a.chi2) {
@@ -517,13 +568,15 @@ int phot_tc_prepare(ms_ctx *ctx) {
     MS_CUDA(cudaMalloc(&P.tc_pack, img.size()));
     MS_CUDA(cudaMemcpy(P.tc_pack, img.data(), img.size(), cudaMemcpyHostToDevice));
     P.tc_pack_bytes = img.size();
-    const int smem_total = SM_FIXED + nb * CONST_BYTES;
-    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
-    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    MS_CUDA(cudaFuncSetAttribute(phot_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     return MS_OK;
 }
 
-int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
+namespace {
+
+int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const ThetaView *tv, double *derived,
+              int mistdif) {
     const PhotNetDev &n = ctx->phot;
     if (!n.tc_pack) { ms_set_error("photometric net not packed for MS_PREC_TC"); return MS_ESTATE; }
     if (B <= 0) return MS_OK;
@@ -534,13 +587,41 @@ int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
     ka.wimg = static_cast<const unsigned char *>(n.tc_pack);
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
     ka.nb = n.nb; ka.d_in = n.d_in;
+    ka.fused = tv != nullptr;
+    int smem_total = SM_FIXED + n.nb * CONST_BYTES;
+    if (tv) {
+        const GridDev &g = ctx->grid;
+        ka.tv = *tv; ka.axes = g.axes; ka.table = g.tab32;
+        ka.ne = g.ne; ka.nm = g.nm; ka.nf = g.nf; ka.na = g.na; ka.mistdif = mistdif; ka.derived = derived;
+        smem_total += (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double);
+    } else {
+        ka.axes = nullptr; ka.table = nullptr; ka.ne = ka.nm = ka.nf = ka.na = 0; ka.mistdif = 0; ka.derived = nullptr;
+    }
     const int64_t npairs = (B + 2 * TILE - 1) / (2 * TILE);
     const int grid = (int)(npairs < ctx->sm_count ? npairs : ctx->sm_count);
     KernelTimer timer_(ctx, MS_K_PHOT, st);
-    const int smem_total = SM_FIXED + n.nb * CONST_BYTES;
     if (ctx->precision == MS_PREC_TC16) phot_mlp_tc_kernel<true><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
     else phot_mlp_tc_kernel<false><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;
+}
+
+}  // namespace
+
+int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
+    return launch_tc(ctx, a, B, st, nullptr, nullptr, 0);
+}
+
+// shared memory the fused form needs on top of the kernel's own, and whether it fits
+bool phot_tc_can_fuse(const ms_ctx *ctx) {
+    const GridDev &g = ctx->grid;
+    if (!ctx->phot.tc_pack || !g.tab32 || !g.axes) return false;
+    return SM_FIXED + ctx->phot.nb * CONST_BYTES + (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double) <= SMEM_LIMIT;
+}
+
+int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, double *derived, int mistdif,
+                         int64_t B, cudaStream_t st) {
+    if (!phot_tc_can_fuse(ctx)) { ms_set_error("fused interpolation + photometry does not fit this model"); return MS_ESTATE; }
+    return launch_tc(ctx, a, B, st, &tv, derived, mistdif);
 }

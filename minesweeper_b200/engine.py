@@ -244,6 +244,11 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.ms_launch_count(self._ctx))
 
+    def set_fusion(self, on=True):
+        """Tensor-core modes: run photometry-only isochrone batches as one kernel (default) or as the
+        interpolation kernel followed by the MLP kernel."""
+        check(self.lib.ms_set_fusion(self._ctx, int(bool(on))))
+
     def profile(self, on=True):
         check(self.lib.ms_profile_enable(self._ctx, int(on)))
 

@@ -420,3 +420,45 @@ def test_empty_and_degenerate_batches(g_like_phot):
     full = L.lnlike_batch(g['theta'][:257])[0].cpu().numpy()
     np.testing.assert_array_equal(l257, full)
     np.testing.assert_array_equal(l1, full[:1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prec', ['tc', 'tc16'])
+@pytest.mark.parametrize('n', [148 * 256 * 4, 148 * 256 * 5 + 19])
+def test_fused_interp_phot_matches_two_kernel_sequence(prec, n):
+    """Tensor-core modes: the one-kernel form (MIST interpolation inside the MLP kernel's prologue) and the
+    interpolation kernel followed by the MLP kernel share the interpolation code: the derived block is
+    bit-identical and lnL agrees to rounding, including out-of-grid rows and an unobserved band; the launch
+    count drops."""
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
+    phot = synth.make_phot_net(h=128, seed=32)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    obs = synth.demo_obs_phot()
+    obs['WISE_W4'] = [np.nan, np.nan]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot, obs_phot=obs)
+    th = synth.draw_theta_phot(n, seed=6 + n % 5, frac_out=0.05,
+                               box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0),
+                                        afe=(-0.2, 0.6), mass=(0.5, 1.25)))
+    L = likelihood(fitargs, fitpars, [False, True, False, False, False], precision=prec, verbose=False)
+    c0 = L.engine.launch_count()
+    lf, df, _ = L.lnlike_batch(th)
+    c1 = L.engine.launch_count()
+    L.engine.set_fusion(False)
+    lu, du, _ = L.lnlike_batch(th)
+    c2 = L.engine.launch_count()
+    assert c1 - c0 == 1 and c2 - c1 == 2
+    small = L.lnlike_batch(th[:1000])[0]                     # below the fusion threshold: two kernels either way
+    assert L.engine.launch_count() - c2 == 2 and np.array_equal(small.cpu().numpy(), lu.cpu().numpy()[:1000])
+    lf, lu, df, du = (t.cpu().numpy() for t in (lf, lu, df, du))
+    assert np.array_equal(np.isneginf(lf), np.isneginf(lu))
+    fin = np.isfinite(lf)
+    # same interpolation code, so the derived block is identical; the one-kernel form takes log10(Teff) straight
+    # from the interpolated column instead of log10(10**x): lnL agrees to rounding
+    assert np.array_equal(df, du)
+    np.testing.assert_allclose(lf[fin], lu[fin], rtol=1e-12, atol=1e-9)
+    assert np.isneginf(lf).sum() > 0 or n < 50
