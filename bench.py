@@ -188,6 +188,10 @@ def main():
                           'processes (%.1f s); single-core probe %.0f evals/s' % (ne, arm.cores, te, r1))
         del arm
 
+    # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (read when the library loads); stdout carries
+    # the one JSON line
+    if world > 1 and os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local)
@@ -196,9 +200,6 @@ def main():
     if world > 1:
         from minesweeper_b200.distributed import bind_to_gpu_numa
         numa_cores = bind_to_gpu_numa(local)          # before the pinned staging buffers are allocated
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the one JSON line
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     from minesweeper_b200.likelihood import likelihood
     L = likelihood(fitargs, fitpars, runbools, precision=args.precision, device=local, verbose=False)
@@ -206,14 +207,35 @@ def main():
     B = args.batch
     theta_np = synth.draw_theta_phot(B, seed=3 + rank, box=box)
     theta = torch.from_numpy(theta_np).to(dev)
-    lnl = torch.empty(B, dtype=torch.float64, device=dev)
-    gathered = torch.empty(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    # Results are double-buffered and the one collective of the path (the gather of lnL) runs on a side stream,
+    # so the gather of step k overlaps the kernels of step k + 1; the last timed step waits for every gather.
+    lnl_bufs = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2)]
+    gathered = [torch.empty(B * world, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    comm = torch.cuda.Stream(dev) if world > 1 else None
+    gather_done = [None, None]
+    nstep = [0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def step():
-        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=lnl)
+        i = nstep[0] & 1
+        nstep[0] += 1
+        main = torch.cuda.current_stream()
+        if gather_done[i] is not None:
+            main.wait_event(gather_done[i])                             # this buffer's previous gather has read it
+        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=lnl_bufs[i])
         if world > 1:                                                   # the only collective: gather results
-            dist.all_gather_into_tensor(gathered, lnl)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                dist.all_gather_into_tensor(gathered[i], lnl_bufs[i])
+                gather_done[i] = torch.cuda.Event()
+                gather_done[i].record(comm)
+
+    def drain():
+        for e in gather_done:
+            if e is not None:
+                torch.cuda.current_stream().wait_event(e)
 
     def barrier():
         if world > 1:
@@ -229,12 +251,15 @@ def main():
     l0 = eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    for e0, e1 in ev:
+    for k, (e0, e1) in enumerate(ev):
         flush.zero_()                                                   # L2 flush, outside the timed pair
         e0.record()
         step()
+        if k == len(ev) - 1:
+            drain()                                                     # every gather is inside the timed region
         e1.record()
     barrier()
+    lnl = lnl_bufs[(nstep[0] - 1) & 1]
     ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     launches = eng.launch_count() - l0
     prof = eng.profile_read()
@@ -344,7 +369,7 @@ def main():
                    'tc16': 'f16 (fp32 accumulate)'}[args.precision], data='synthetic',
             config=dict(workload=workload_name(args, fitargs['MISTpath']), precision=args.precision,
                         l2='flushed between steps (256 MiB memset outside the timed events)',
-                        collective='all_gather_into_tensor(lnL) per step' if world > 1 else 'none',
+                        collective='all_gather_into_tensor(lnL) per step, on a side stream, overlapping the next step' if world > 1 else 'none',
                         host_affinity=('%d cores local to the GPU' % len(numa_cores)) if numa_cores else 'default',
                         flop_per_eval=flop_pt),
             clocks=clocks,
