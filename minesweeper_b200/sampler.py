@@ -399,7 +399,7 @@ class QueuedNestedSampler(object):
 
     Each star owns ``queue`` random-walk walkers; a round advances all walkers of all stars by
     ``walks`` steps (one batched prior-transform / likelihood / ln-prior call per step) and then
-    ``ns_consume_kernel`` (one CTA per star) uses the walkers' end points in order, each one
+    ``ns_consume_kernel`` (one warp per star) uses the walkers' end points in order, each one
     replacing the then-worst live point if it is still above the threshold -- dynesty's
     ``queue_size`` scheme.  ``queue > 1`` is what makes a *single* star fast on a GPU (the
     sequential depth drops from ~niter to ~niter / queue rounds); ``queue = 1`` with many stars is
