@@ -65,3 +65,14 @@ def test_sharded_lnlike_gloo_world2(n):
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
     assert res[0][2] + res[1][2] == list(range(11))      # stars partitioned, bit-identical union
+
+
+def test_bind_to_gpu_numa_degrades_gracefully():
+    """Without NVML (this container) the affinity helper reports None and leaves the process alone."""
+    import os
+    from minesweeper_b200.distributed import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    cores = bind_to_gpu_numa(0)
+    assert cores is None or set(cores) <= before
+    if cores is None:
+        assert os.sched_getaffinity(0) == before

@@ -287,6 +287,16 @@ def test_lnlike_phot_tc_vs_f64_and_oracle():
         assert abs(ltc[i] - want) <= tol + 1e-6, (i, ltc[i], want, tol)
     rel = np.abs(ltc[fin] - l64[fin]) / np.maximum(1.0, np.abs(l64[fin]))
     assert rel.max() < 1e-4, rel.max()
+    # MS_PREC_TC16: same bound with its stated magnitude tolerance instead of 1e-5 relative
+    L16 = likelihood(fitargs, fitpars, runbools, precision='tc16', verbose=False)
+    l16 = L16.lnlike_batch(th)[0].cpu().numpy()
+    assert np.array_equal(np.isneginf(l64), np.isneginf(l16))
+    for i in np.flatnonzero(fin)[:40]:
+        want = ref.lnlikefn(list(th[i]))
+        sed = ref.genphot([ref.parsdict[k] for k in ('Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'log(R)', 'Dist', 'Av')])
+        tol = sum((abs(sed[k] - o) * TC16_MAG_TOL + 0.5 * TC16_MAG_TOL ** 2) / s ** 2
+                  for k, (o, s) in obs.items() if np.isfinite(o))
+        assert abs(l16[i] - want) <= tol + 1e-6, (i, l16[i], want, tol)
 
 
 def test_sharded_equals_single_rank(g_like_phot):
