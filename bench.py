@@ -45,8 +45,9 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--spec-batch', type=int, default=65536,
                     help='points per GPU of the auxiliary spectrum + photometry measurement (0 = skip)')
-    ap.add_argument('--catalog-stars', type=int, default=65536,
-                    help='stars per GPU fitted with the batched nested sampler for the stars/hour figure (0 = skip)')
+    ap.add_argument('--catalog-stars', type=int, default=75776,
+                    help='stars per GPU fitted with the batched nested sampler for the stars/hour figure (0 = skip); '
+                         'the default is two full waves of the persistent photometry kernel (148 SMs x 256 points x 2)')
     return ap.parse_args()
 
 
