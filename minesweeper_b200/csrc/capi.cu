@@ -555,7 +555,16 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
         const int64_t wave = (int64_t)ctx->sm_count * 256;
         chunk = (chunk + wave - 1) / wave * wave;
     }
-    const int nchunks = (int)((B + chunk - 1) / chunk);
+    // chunk boundaries: a short first chunk (one wave) so the kernels start after a small copy, a short last chunk
+    // (what is left, at most one chunk) so little is left to copy back after the last kernel
+    std::vector<int64_t> cuts{0};
+    {
+        const int64_t wave = (int64_t)ctx->sm_count * 256;
+        if (B > chunk + wave) cuts.push_back(wave);
+        while (B - cuts.back() > chunk) cuts.push_back(cuts.back() + chunk);
+        cuts.push_back(B);
+    }
+    const int nchunks = (int)cuts.size() - 1;
     while ((int)ctx->ev_pool.size() < 2 * nchunks) {
         cudaEvent_t e;
         MS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -565,7 +574,7 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
     if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)chunk * MS_NPARS))) return rc;
     if ((rc = ensure_scratch(&ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)chunk))) return rc;
     for (int k = 0; k < nchunks; ++k) {
-        const int64_t b0 = (int64_t)k * chunk, nb = (B - b0 < chunk) ? B - b0 : chunk;
+        const int64_t b0 = cuts[k], nb = cuts[k + 1] - cuts[k];
         cudaEvent_t up = ctx->ev_pool[2 * k], done = ctx->ev_pool[2 * k + 1];
         MS_CUDA(cudaMemcpyAsync(ctx->scr_theta + b0 * ndim, theta_host + b0 * ndim,
                                 (size_t)nb * ndim * sizeof(double), cudaMemcpyHostToDevice, ctx->h2d_stream));
