@@ -45,9 +45,9 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--spec-batch', type=int, default=65536,
                     help='points per GPU of the auxiliary spectrum + photometry measurement (0 = skip)')
-    ap.add_argument('--catalog-stars', type=int, default=75776,
+    ap.add_argument('--catalog-stars', type=int, default=100000,
                     help='stars per GPU fitted with the batched nested sampler for the stars/hour figure (0 = skip); '
-                         'the default is two full waves of the persistent photometry kernel (148 SMs x 256 points x 2)')
+                         'the default is the size of configs[4]')
     return ap.parse_args()
 
 
@@ -313,9 +313,9 @@ def main():
                 dist.all_reduce(ncalls)
             catalog = dict(stars=args.catalog_stars * world, seconds=float(tcat.item()),
                            stars_per_hour=args.catalog_stars * world / float(tcat.item()) * 3600.0,
-                           loglike_calls=float(ncalls.item()), sampler='lock-step static nested sampling, rwalk, bookkeeping in CUDA kernels, CUDA-graph replay',
+                           loglike_calls=float(ncalls.item()), sampler='lock-step static nested sampling, rwalk, 4 queued walkers per star, bookkeeping in CUDA kernels, CUDA-graph replay',
                            nlive=150, walks=5, dlogz=0.01, converged_frac=float(rc['converged'].mean()),
-                           note='configs[4] at reduced size: stars per GPU fixed (weak scaling)')
+                           note='configs[4]: stars per GPU fixed (weak scaling)')
         except Exception as e:                                           # never lose the main line
             catalog = dict(error=repr(e))
 

@@ -23,7 +23,7 @@ NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R',
 ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
 
 
-def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed, queued=1):
+def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed, queued=4):
     """Synthetic catalog of S stars on this device (truths from the prior, observations from the
     model itself, Gaia-like parallaxes) registered with the engine, and a sampler over it.
     Returns (sampler, truth_theta)."""
@@ -77,7 +77,7 @@ def main():
     ap.add_argument('--maxiter', type=int, default=20000)
     ap.add_argument('--small-grid', action='store_true')
     ap.add_argument('--eager', action='store_true', help='use the eager sampler loop instead of the CUDA-graph one')
-    ap.add_argument('--queued', type=int, default=1,
+    ap.add_argument('--queued', type=int, default=4,
                     help='walkers per star of the kernel-bookkeeping sampler; 0 = torch-tensor sampler')
     args = ap.parse_args()
     import torch
