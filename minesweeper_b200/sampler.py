@@ -402,8 +402,9 @@ class QueuedNestedSampler(object):
     ``ns_consume_kernel`` (one warp per star) uses the walkers' end points in order, each one
     replacing the then-worst live point if it is still above the threshold -- dynesty's
     ``queue_size`` scheme.  ``queue > 1`` is what makes a *single* star fast on a GPU (the
-    sequential depth drops from ~niter to ~niter / queue rounds); ``queue = 1`` with many stars is
-    the catalog mode.  One round is captured in a CUDA graph and replayed; the RNG stream is
+    sequential depth drops from ~niter to ~niter / queue rounds); for catalogs a small queue
+    (4: 9.0e7 stars/hour on a B200 at 100k stars, against 5.6e7 with 1) amortises the per-round
+    bookkeeping and makes the likelihood batches large enough for the fused photometry kernel.  One round is captured in a CUDA graph and replayed; the RNG stream is
     driven by a device-side round counter so replays draw fresh numbers.
     """
 
