@@ -572,12 +572,21 @@ class QueuedNestedSampler(object):
 
 def write_samples_file(path, res, star=0):
     """Dead points of one star in the reference's samples-file layout (header fitstar.py:235-242:
-    ``Iter <pars...> log(lk) log(vol) log(wt) h nc log(z) delta(log(z))``); needs store_samples."""
+    ``Iter <pars...> log(lk) log(vol) log(wt) h nc log(z) delta(log(z))``); needs store_samples.
+    Accepts the records of both samplers: per-iteration tuples (BatchedNestedSampler) or one
+    ``[niter, ncol + 3]`` array per star (QueuedNestedSampler: row, ln L, ln X, ln w)."""
     names = res['names']
+    dead = res['dead']
     with open(path, 'w') as f:
         f.write('Iter ' + ' '.join(names) + ' log(lk) log(vol) log(wt) h nc log(z) delta(log(z))\n')
+        if len(dead) and isinstance(dead[0], np.ndarray) and dead[0].ndim == 2:
+            ncol = len(names)
+            for it, r in enumerate(dead[star]):
+                f.write('%d ' % it + ' '.join('%.10g' % v for v in r[:ncol]) +
+                        ' %.10g %.10g %.10g nan nan nan nan\n' % (r[ncol], r[ncol + 1], r[ncol + 2]))
+            return
         it = 0
-        for act, row, lnl, logvol, logwt in res['dead']:
+        for act, row, lnl, logvol, logwt in dead:
             k = np.flatnonzero(act == star)
             if len(k) == 0:
                 continue

@@ -112,3 +112,27 @@ def test_postproc_weighted_quantiles(tmp_path):
     ref = quantile(x[:n], [0.16, 0.5, 0.84], weights=w[:n] + 1e-12)
     np.testing.assert_allclose(st[:3], ref, rtol=1e-9)
     assert abs(st[3] - 0.5) < 0.05 and st[4][0] < st[0] < st[2] < st[4][1]
+
+
+def test_samples_file_roundtrip_both_record_layouts(tmp_path):
+    """sampler.write_samples_file -> postproc.read_samples_file for the per-iteration tuples of the torch sampler
+    and for the per-star arrays of the kernel-bookkeeping sampler: same file either way."""
+    from minesweeper_b200 import postproc
+    from minesweeper_b200.sampler import write_samples_file
+    rng = np.random.default_rng(3)
+    names = ['Dist', 'Av', 'EEP']
+    n = 50
+    rows = rng.normal(size=(n, 3))
+    lnl, logvol, logwt = np.sort(rng.normal(size=n)), -np.arange(1, n + 1) / 150.0, rng.normal(size=n)
+    per_star = [np.zeros((0, 6)), np.column_stack([rows, lnl, logvol, logwt])]
+    tuples = [(np.array([0, 1]), np.stack([rng.normal(size=3), rows[i]]), np.array([0.0, lnl[i]]),
+               np.array([0.0, logvol[i]]), np.array([0.0, logwt[i]])) for i in range(n)]
+    pa, pb = str(tmp_path / 'a.dat'), str(tmp_path / 'b.dat')
+    write_samples_file(pa, dict(names=names, dead=per_star), star=1)
+    write_samples_file(pb, dict(names=names, dead=tuples), star=1)
+    assert open(pa).read() == open(pb).read()
+    tab = postproc.read_samples_file(pa)
+    np.testing.assert_allclose(tab['EEP'], rows[:, 2], rtol=1e-9)
+    np.testing.assert_allclose(tab['log(wt)'], logwt, rtol=1e-9)
+    st = postproc.summarize_samples_file(pa)
+    assert set(st) == set(names) and st['Dist'][0] <= st['Dist'][1] <= st['Dist'][2]
