@@ -19,7 +19,10 @@
 //   warps 16, 17     MMA issuers, one per tile (one elected lane each, blocking on that tile's barriers)
 //   warp 18          weight producer: bulk async copies of the per-band weight image
 //                    (global/L2 -> shared) into a two-deep ring
-//   warps 19-22      prologue warpgroup: the next pair's network inputs (X tiles) and distance moduli
+//   warps 19-22      prologue warpgroup, one pair ahead: the next pair's network inputs (X tiles) and distance
+//                    moduli and, in the fused form, kernel (1) itself: the MIST interpolation of those points
+//                    (mist_interp.cuh), so a photometry-only batch is one launch and the parameter block never
+//                    exists in HBM
 // Per tile and band:
 //   D1 = X W1^T            SS MMA, K = 16 (6 inputs + bias column), X tile in shared memory
 //   A1 = act(D1)           TMEM -> registers -> activation -> fp16 (hi/lo) -> TMEM, written in place
