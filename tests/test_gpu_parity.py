@@ -472,3 +472,46 @@ def test_fused_interp_phot_matches_two_kernel_sequence(prec, n):
     assert np.array_equal(df, du)
     np.testing.assert_allclose(lf[fin], lu[fin], rtol=1e-12, atol=1e-9)
     assert np.isneginf(lf).sum() > 0 or n < 50
+
+
+@pytest.mark.gpu
+def test_fused_interp_phot_with_star_slots():
+    """Catalog form of the fused kernel: every row carries its own star slot (its own observed magnitudes).
+    One-kernel and two-kernel forms agree, and a row evaluated against slot s equals the single-star result
+    for that star's observations."""
+    import torch
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
+    phot = synth.make_phot_net(h=128, seed=32)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    obs = synth.demo_obs_phot()
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot, obs_phot=obs)
+    L = likelihood(fitargs, fitpars, [False, True, False, False, False], precision='tc', verbose=False)
+    nb = len(L.engine.bands)
+    rng = np.random.default_rng(2)
+    nstars = 7
+    mags = np.array([obs[b][0] for b in L.engine.bands])[None, :] + rng.normal(0, 0.3, (nstars, nb))
+    errs = np.full((nstars, nb), 0.05)
+    L.engine.set_stars_phot(mags, errs)
+    n = 148 * 256 * 4 + 11
+    th = synth.draw_theta_phot(n, seed=9, frac_out=0.03,
+                               box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0),
+                                        afe=(-0.2, 0.6), mass=(0.5, 1.25)))
+    slot = torch.from_numpy(rng.integers(0, nstars, n).astype(np.int32)).to(L.engine.device)
+    c0 = L.engine.launch_count()
+    lf = L.lnlike_batch(th, want_derived=False, star_slot=slot)[0].cpu().numpy()
+    assert L.engine.launch_count() - c0 == 1
+    L.engine.set_fusion(False)
+    lu = L.lnlike_batch(th, want_derived=False, star_slot=slot)[0].cpu().numpy()
+    fin = np.isfinite(lu)
+    assert np.array_equal(fin, np.isfinite(lf)) and fin.sum() > n // 2
+    np.testing.assert_allclose(lf[fin], lu[fin], rtol=1e-12, atol=1e-9)
+    s = 3
+    pick = np.flatnonzero(slot.cpu().numpy() == s)[:2000]
+    L.engine.set_star(0, (mags[s], errs[s]))
+    single = L.lnlike_batch(th[pick], want_derived=False)[0].cpu().numpy()
+    np.testing.assert_allclose(single[np.isfinite(single)], lu[pick][np.isfinite(single)], rtol=1e-12, atol=1e-9)
