@@ -59,3 +59,30 @@ def test_cuda_brackets_equal_digitize_everywhere():
     rbr, rpred, rok = mist_port.interp_dense(MIST, q[:, 0], q[:, 1], q[:, 2], q[:, 3])
     assert np.array_equal(ok.cpu().numpy().astype(bool), rok)
     np.testing.assert_allclose(der.cpu().numpy()[rok][:, 4:], rpred[rok], rtol=3e-6, atol=3e-6)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 10 ** 6), st.floats(0.0, 0.4), st.floats(0.0, 0.5))
+def test_ingest_roundtrip_with_missing_and_truncated_tracks(seed, frac_missing, frac_trunc):
+    """ingest.mist_dense_from_tables inverts synth.mist_rows for any pattern of missing / truncated tracks:
+    same axes (as long as every label value survives somewhere), same validity mask, same values; table row
+    order does not matter."""
+    from minesweeper_b200.ingest import mist_dense_from_tables
+    mist = synth.make_mist(ne=12, nm=6, nf=4, na=3, seed=seed, frac_missing=frac_missing, frac_trunc=frac_trunc)
+    tables = synth.mist_rows(mist)
+    if not tables['index']:
+        return
+    rng = np.random.default_rng(seed)
+    for k in tables['index']:
+        tables[k] = tables[k][rng.permutation(len(tables[k]))]
+    rng.shuffle(tables['index'])
+    dense = mist_dense_from_tables(tables)
+    # axes present in the tables are a subset of the generating axes; map dense back onto the full grid
+    sel = [np.searchsorted(mist[k], dense[k]) for k in ('eep', 'mass', 'feh', 'afe')]
+    for k, s_ in zip(('eep', 'mass', 'feh', 'afe'), sel):
+        np.testing.assert_array_equal(mist[k][s_], dense[k])
+    sub_valid = mist['valid'][np.ix_(sel[3], sel[2], sel[1], sel[0])]
+    sub_vals = mist['values'][np.ix_(sel[3], sel[2], sel[1], sel[0])]
+    np.testing.assert_array_equal(dense['valid'], sub_valid)
+    np.testing.assert_array_equal(dense['values'][dense['valid']], sub_vals[sub_valid])
+    assert dense['valid'].sum() == mist['valid'].sum()
