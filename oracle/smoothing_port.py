@@ -105,3 +105,31 @@ def smooth_vsini(wave, spec, vsini, outwave=None, inres=0.0):
         outwave = wave
     sigma = np.sqrt(vsini ** 2 - inres ** 2)
     return _fft_filter(w, s, outwave, sigma, rotation_transfer)
+
+
+def smooth_lsf(wave, spec, outwave, sigma, pix_per_sigma=2.0):
+    """smoothspec(..., smoothtype='lsf', fftsmooth=True) with an array ``sigma`` (same units and length
+    as ``wave``): wavelength-dependent Gaussian line-spread function (smoothing.py:125-128, 412-514).
+
+    The wavelength axis is warped by the cumulative distribution of d(lambda) / sigma(lambda) so that the
+    kernel has constant width in the warped coordinate x in [0, 1]; the spectrum is resampled on
+    ``nx = 2**ceil(log2(pix_per_sigma / x_per_sigma))`` uniform x points, smoothed there by FFT with a
+    Gaussian of ``x_per_sigma`` (the median over pixels of dx / (d lambda / sigma)), and interpolated onto
+    ``outwave``.  The reference's mask for this mode pads by 20 x 100 wavelength units (smoothing.py:
+    125-132), i.e. keeps the whole model spectrum for any realistic window, so no masking is restated.
+    Not on the CUDA path yet; this restatement and its golden vectors pin the
+    semantics for it."""
+    wave = np.asarray(wave, dtype=np.float64)
+    spec = np.asarray(spec, dtype=np.float64)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    dw = np.gradient(wave)
+    cdf = np.cumsum(dw / sigma)
+    cdf = cdf / cdf.max()
+    x_per_sigma = np.nanmedian(np.gradient(cdf) / (dw / sigma))
+    nx = int(pow2_ceil(pix_per_sigma / x_per_sigma))
+    x = np.linspace(0.0, 1.0, nx)
+    lam = np.interp(x, cdf, wave)
+    resampled = np.interp(lam, wave, spec)
+    f = np.fft.rfftfreq(nx, d=1.0 / nx)
+    conv = np.fft.irfft(np.fft.rfft(resampled) * np.exp(-2.0 * np.pi ** 2 * x_per_sigma ** 2 * f ** 2))
+    return np.interp(outwave, lam, conv)

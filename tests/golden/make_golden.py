@@ -110,9 +110,13 @@ def gen_smoothing():
     rs = np.array([20000.0 * 2.355, 35000.0 * 2.355, 60000.0])
     r_out = np.stack([S.smoothspec(wave * (1 + 3.3 / 299792.458), flux, r, outwave=outwave,
                                    smoothtype='R', fftsmooth=True, inres=100000.0) for r in rs])
+    # wavelength-dependent LSF (array sigma in wavelength units, smoothtype='lsf'): sigma = a + b (lambda - lambda_0)
+    lsf_ab = np.array([[0.05, 0.0], [0.08, 4e-5], [0.15, -1e-5]])
+    lsf_out = np.stack([S.smoothspec(wave, flux, a + b * (wave - wave[0]), outwave=outwave, smoothtype='lsf',
+                                     fftsmooth=True) for a, b in lsf_ab])
     np.savez_compressed(os.path.join(HERE, 'smoothing.npz'), wave=wave, flux=flux, outwave=outwave,
                         vsini=vs, vsini_out=vs_out, rsigma=rs, r_out=r_out, r_inres=100000.0,
-                        r_vshift=3.3)
+                        r_vshift=3.3, lsf_ab=lsf_ab, lsf_out=lsf_out)
     print('smoothing: done')
 
 

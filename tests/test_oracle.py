@@ -42,6 +42,15 @@ def test_smoothing_port_matches_reference(g_smooth):
         np.testing.assert_allclose(out, ref, rtol=0, atol=1e-14)
 
 
+def test_lsf_smoothing_port_matches_reference(g_smooth):
+    """Row a14 (array Inst_R / wavelength-dependent LSF, smoothing.py:412-514): oracle restatement against the
+    reference's own output.  The CUDA path does not implement this mode yet; the vectors pin it for when it does."""
+    w, f, ow = g_smooth['wave'], g_smooth['flux'], g_smooth['outwave']
+    for (a, b), ref in zip(g_smooth['lsf_ab'], g_smooth['lsf_out']):
+        out = smoothing_port.smooth_lsf(w, f, ow, a + b * (w - w[0]))
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-13)
+
+
 @pytest.mark.parametrize('which', ['phot', 'spec'])
 def test_like_port_matches_reference(which, g_like_phot, g_like_spec):
     g = g_like_phot if which == 'phot' else g_like_spec
