@@ -307,7 +307,7 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
         cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2);
         cudaFree(s.cheb_x);
     }
-    cudaFree(ctx->scr_derived); cudaFree(ctx->scr_pars); cudaFree(ctx->scr_chi2);
+    cudaFree(ctx->scr_derived); cudaFree(ctx->scr_pars); cudaFree(ctx->scr_chi2); cudaFree(ctx->scr_chi2g);
     cudaFree(ctx->scr_flux); cudaFree(ctx->scr_hid); cudaFree(ctx->scr_theta); cudaFree(ctx->scr_out);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);

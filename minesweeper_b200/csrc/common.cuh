@@ -86,6 +86,7 @@ struct ms_ctx {
     double *scr_derived = nullptr; size_t scr_derived_n = 0;
     double *scr_pars = nullptr;    size_t scr_pars_n = 0;
     double *scr_chi2 = nullptr;    size_t scr_chi2_n = 0;
+    double *scr_chi2g = nullptr;   size_t scr_chi2g_n = 0;   // chi-square carried between band groups (phot_mlp_tc.cu)
     void *scr_flux = nullptr;      size_t scr_flux_bytes = 0;
     void *scr_hid = nullptr;       size_t scr_hid_bytes = 0;
     double *scr_theta = nullptr;   size_t scr_theta_n = 0;     // for the host-buffer entry point

@@ -138,7 +138,8 @@ struct TcArgs {
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
     double xmin[8], xscale[8];
-    int nb, d_in;
+    int nb, d_in;                      // bands of this launch (a group when the net has more than MAX_NB)
+    int nb_total, b0;                  // row length of obs / mags and the first band of the group
     // fused form: the prologue warpgroup interpolates the MIST grid itself (kernel (1) folded in), so the
     // parameter block never exists in HBM; `pars` is then unused
     int fused;
@@ -389,7 +390,8 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 // this band's observation, requested now and used after the two epilogues
                 double obs_o = 0.0, obs_e2 = 1.0;
                 if (half == 0 && (a.chi2 || a.lnL)) {
-                    obs_o = a.obs_mag[(size_t)slot * nb + b]; obs_e2 = a.obs_err2[(size_t)slot * nb + b];
+                    const size_t at = (size_t)slot * a.nb_total + a.b0 + b;
+                    obs_o = a.obs_mag[at]; obs_e2 = a.obs_err2[at];
                 }
                 // ---- layer-1 epilogue: activation, fp16 (split), written back in place as the TS A operand
                 mbar_wait(bar(BAR_D1 + T), g & 1);
@@ -471,14 +473,14 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 const float bc = (bc0 + bc1) + *pslot + b3;
                 if (ok) {
                     const double mag = mag0 - (double)bc;
-                    if (a.mags) a.mags[p * nb + b] = mag;
+                    if (a.mags) a.mags[p * a.nb_total + a.b0 + b] = mag;
                     if (a.chi2 || a.lnL) {
                         const double rr = mag - obs_o;
                         const double t = (rr * rr) / obs_e2;
                         if (t == t) chi2 += t;                           // nansum (likelihood.py:207)
                     }
                 } else if (live && a.mags) {
-                    a.mags[p * nb + b] = ms_nan();
+                    a.mags[p * a.nb_total + a.b0 + b] = ms_nan();
                 }
             }
             if (half == 1) continue;
@@ -514,9 +516,9 @@ void split_f16(double v, uint16_t &hi, uint16_t &lo) {
 
 int phot_tc_prepare(ms_ctx *ctx) {
     PhotNetDev &P = ctx->phot;
-    if (P.h != H || P.d_in > 6 || P.nb > MAX_NB) {
-        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 128, <= 6 inputs and <= %d bands "
-                     "(got h=%d, d_in=%d, nb=%d); use MS_PREC_F32", MAX_NB, P.h, P.d_in, P.nb);
+    if (P.h != H || P.d_in > 6) {
+        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 128 and <= 6 inputs "
+                     "(got h=%d, d_in=%d); use MS_PREC_F32", P.h, P.d_in);
         return MS_EINVAL;
     }
     const int nb = P.nb, D = P.d_in;
@@ -585,28 +587,49 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
     if (B <= 0) return MS_OK;
     if ((a.chi2 || a.lnL) && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
     TcArgs ka;
-    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2; ka.lnL = a.lnL; ka.ageweight = a.ageweight;
+    ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.ageweight = a.ageweight;
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
-    ka.wimg = static_cast<const unsigned char *>(n.tc_pack);
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
-    ka.nb = n.nb; ka.d_in = n.d_in;
+    ka.d_in = n.d_in; ka.nb_total = n.nb;
     ka.fused = tv != nullptr;
-    int smem_total = SM_FIXED + n.nb * CONST_BYTES;
+    int smem_extra = 0;
     if (tv) {
         const GridDev &g = ctx->grid;
         ka.tv = *tv; ka.axes = g.axes; ka.table = g.tab32;
         ka.ne = g.ne; ka.nm = g.nm; ka.nf = g.nf; ka.na = g.na; ka.mistdif = mistdif; ka.derived = derived;
-        smem_total += (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double);
+        smem_extra = (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double);
     } else {
         ka.axes = nullptr; ka.table = nullptr; ka.ne = ka.nm = ka.nf = ka.na = 0; ka.mistdif = 0; ka.derived = nullptr;
+    }
+    // A net with more bands than the resident constants allow runs as consecutive band groups: every group but
+    // the last adds its chi-square to a carry buffer, the last one turns the sum into lnL (two-kernel form only).
+    const int ngroups = (n.nb + MAX_NB - 1) / MAX_NB;
+    double *carry = a.chi2;
+    if (ngroups > 1) {
+        if (tv) { ms_set_error("fused interpolation + photometry needs <= %d bands", MAX_NB); return MS_ESTATE; }
+        if (!carry && a.lnL) {
+            int rc = ensure_scratch(&ctx->scr_chi2g, &ctx->scr_chi2g_n, (size_t)B);
+            if (rc) return rc;
+            carry = ctx->scr_chi2g;
+            MS_CUDA(cudaMemsetAsync(carry, 0, (size_t)B * sizeof(double), st));
+        }
     }
     const int64_t npairs = (B + 2 * TILE - 1) / (2 * TILE);
     const int grid = (int)(npairs < ctx->sm_count ? npairs : ctx->sm_count);
     KernelTimer timer_(ctx, MS_K_PHOT, st);
-    if (ctx->precision == MS_PREC_TC16) phot_mlp_tc_kernel<true><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
-    else phot_mlp_tc_kernel<false><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
-    ctx->launches++;
-    MS_CUDA(cudaGetLastError());
+    for (int gi = 0; gi < ngroups; ++gi) {
+        const bool last = gi == ngroups - 1;
+        ka.b0 = gi * MAX_NB;
+        ka.nb = last ? n.nb - ka.b0 : MAX_NB;
+        ka.wimg = static_cast<const unsigned char *>(n.tc_pack) + (size_t)ka.b0 * BAND_BYTES;
+        ka.chi2 = carry;
+        ka.lnL = last ? a.lnL : nullptr;
+        const int smem_total = SM_FIXED + ka.nb * CONST_BYTES + smem_extra;
+        if (ctx->precision == MS_PREC_TC16) phot_mlp_tc_kernel<true><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
+        else phot_mlp_tc_kernel<false><<<grid, NTHREADS, smem_total, st>>>(ka, B, (int)npairs);
+        ctx->launches++;
+        MS_CUDA(cudaGetLastError());
+    }
     return MS_OK;
 }
 
@@ -620,7 +643,8 @@ int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
 bool phot_tc_can_fuse(const ms_ctx *ctx) {
     const GridDev &g = ctx->grid;
     if (!ctx->phot.tc_pack || !g.tab32 || !g.axes) return false;
-    return SM_FIXED + ctx->phot.nb * CONST_BYTES + (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double) <= SMEM_LIMIT;
+    return ctx->phot.nb <= MAX_NB &&
+           SM_FIXED + ctx->phot.nb * CONST_BYTES + (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double) <= SMEM_LIMIT;
 }
 
 int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, double *derived, int mistdif,

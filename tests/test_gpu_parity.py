@@ -515,3 +515,44 @@ def test_fused_interp_phot_with_star_slots():
     L.engine.set_star(0, (mags[s], errs[s]))
     single = L.lnlike_batch(th[pick], want_derived=False)[0].cpu().numpy()
     np.testing.assert_allclose(single[np.isfinite(single)], lu[pick][np.isfinite(single)], rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prec', ['tc', 'tc16'])
+def test_tc_many_bands_run_as_band_groups(prec):
+    """More bands than the tensor-core kernel keeps resident (29): the bands run as consecutive groups with the
+    chi-square carried between launches.  Magnitudes against the f64 oracle, lnL against the f64 engine."""
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    from oracle.payne_port import FastPayneSEDPredict
+    bands = ['B%02d' % i for i in range(40)]
+    net = synth.make_phot_net(bands=bands, h=128, seed=33)
+    pp = _rand_photpars(700, 12)
+    ref = FastPayneSEDPredict(nnpath=net).sed_batch(pp)
+    eng = _engine(photnet=net, precision=prec)
+    mags = eng.phot_sed(pp).cpu().numpy()
+    tol = 2e-5 if prec == 'tc' else TC16_MAG_TOL
+    assert np.abs(mags - ref).max() < tol
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    rng = np.random.default_rng(4)
+    obs = {b: [float(ref[0, i] + rng.normal(0, 0.05)), 0.05] for i, b in enumerate(bands)}
+    obs['B07'] = [np.nan, np.nan]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=net, obs_phot=obs)
+    th = synth.draw_theta_phot(148 * 256 * 4 + 5, seed=8, frac_out=0.03,
+                               box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0),
+                                        afe=(-0.2, 0.6), mass=(0.5, 1.25)))
+    L64 = likelihood(fitargs, fitpars, [False, True, False, False, False], precision='f64', verbose=False)
+    Lt = likelihood(fitargs, fitpars, [False, True, False, False, False], precision=prec, verbose=False)
+    sub = th[:3000]
+    l64 = L64.lnlike_batch(sub, want_derived=False)[0].cpu().numpy()
+    lt_small = Lt.lnlike_batch(sub, want_derived=False)[0].cpu().numpy()
+    lt_big = Lt.lnlike_batch(th, want_derived=False)[0].cpu().numpy()        # large batch: still the grouped two-kernel form
+    assert np.array_equal(np.isneginf(l64), np.isneginf(lt_small))
+    fin = np.isfinite(l64)
+    rel = np.abs(lt_small[fin] - l64[fin]) / np.maximum(1.0, np.abs(l64[fin]))
+    assert rel.max() < (1e-4 if prec == 'tc' else 5e-2), rel.max()
+    assert np.array_equal(lt_big[:3000], lt_small)
