@@ -29,6 +29,9 @@ UNIT = 'evals/s'
 NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
          'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
 PHOT_ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+KIND_TEXT = {'reference': "the reference's own likelihood.likelihood class, unmodified modules from oracle/_ref",
+             'port': 'the oracle port oracle/like_port.py (no reference copy present)'}
+PARITY_ROWS = 4096
 
 
 def parse():
@@ -131,6 +134,40 @@ class ClockSampler(object):
                     reasons=reasons)
 
 
+def parity_check(L, eng, theta_np, lnl_timed, ref, precision):
+    """The timed step's own lnL (one-kernel tensor-core form in 'tc') on the first rows of the batch against the
+    oracle: -inf rows identical, lnL within the per-row chi-square bound of a 1e-5 relative magnitude error (the
+    north_star's fp32 tolerance; 1e-6 absolute in f64); brackets bit-exact (two-kernel form exposes them) and
+    magnitudes 1e-5 relative at the oracle's interpolated parameters.  Raises on failure."""
+    n = len(ref['lnl'])
+    ok = ref['ok']
+    got = lnl_timed[:n]
+    assert np.array_equal(np.isneginf(got), ~ok), 'parity: out-of-grid rows differ from the oracle'
+    err = np.abs(got[ok] - ref['lnl'][ok])
+    mag_tol = {'f64': 1e-11, 'tc16': 3e-3}.get(precision, 1e-5)
+    if precision == 'f64':
+        bound = np.full(ok.sum(), 1e-6)
+    elif precision == 'tc16':            # stated absolute magnitude tolerance (3e-3 mag) instead of 1e-5 relative
+        bound = np.nansum((np.abs(ref['mags'][ok] - ref['obs_mag']) * 3e-3 + 0.5 * 3e-3 ** 2) / ref['obs_err'] ** 2,
+                          axis=1) + 1e-6
+    else:
+        bound = ref['bound'][ok] + 1e-6 + 1e-9 * np.abs(ref['lnl'][ok])
+    eng.set_fusion(False)
+    _, _, br = L.lnlike_batch(theta_np[:n], want_brackets=True)
+    eng.set_fusion(True)
+    br_ok = bool(np.array_equal(br.cpu().numpy(), ref['brackets']))
+    mags = eng.phot_sed(ref['photpars'][ok]).cpu().numpy()
+    rel_mag = np.abs(mags - ref['mags'][ok]) / np.maximum(np.abs(ref['mags'][ok]), 1.0)
+    out = dict(rows=int(n), out_of_grid_rows=int((~ok).sum()), brackets_bit_exact=br_ok,
+               max_rel_mag=float(rel_mag.max()), max_dlnL=float(err.max()),
+               max_dlnL_over_bound=float((err / bound).max()), mag_tolerance=mag_tol,
+               checked='lnL of the timed kernel vs oracle.like_port.lnlike_phot_dense on the first rows of the batch')
+    assert br_ok, 'parity: brackets differ from the oracle'
+    assert rel_mag.max() <= mag_tol, 'parity: magnitudes off by %g' % rel_mag.max()
+    assert np.all(err <= bound), 'parity: lnL outside the per-row bound (%g x)' % (err / bound).max()
+    return out
+
+
 def run_reference(args):
     """CPU arm: the reference's per-point execution model on all host cores."""
     rank = int(os.environ.get('RANK', '0'))
@@ -152,13 +189,14 @@ def run_reference(args):
         n_tot += n; t_tot += t
     arm.close()
     val = n_tot / t_tot
-    sample = '%d evaluations per step over %d worker processes (per-point lnlikefn loop)' % (per_step, arm.cores)
+    sample = ('%d evaluations per step over %d worker processes (per-point lnlikefn loop of %s)'
+              % (per_step, arm.cores, KIND_TEXT[arm.kind]))
     print(json.dumps(dict(
         impl='reference', metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
         warmup=args.warmup, ms_per_step=1e3 * t_tot / args.steps, higher_is_better=True, scaling='weak',
         vs_baseline=None, dtype='f64', data='synthetic',
         config=dict(workload=workload_name(args, fitargs['MISTpath']), sample=sample),
-        cpu_baseline=dict(value=val, unit=UNIT, cores=arm.cores, kind='port', sample=sample),
+        cpu_baseline=dict(value=val, unit=UNIT, cores=arm.cores, kind=arm.kind, sample=sample),
         e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0)))
 
@@ -184,10 +222,19 @@ def main():
         arm.step(max(n // 20, arm.cores))
         ne, te = arm.step(n)
         arm.close()
-        cpu = dict(value=ne / te, unit=UNIT, cores=arm.cores, kind='port',
+        cpu = dict(value=ne / te, unit=UNIT, cores=arm.cores, kind=arm.kind,
                    sample='%d per-point lnlikefn evaluations of the same workload over %d worker '
-                          'processes (%.1f s); single-core probe %.0f evals/s' % (ne, arm.cores, te, r1))
+                          'processes (%.1f s; %s); single-core probe %.0f evals/s'
+                          % (ne, arm.cores, te, KIND_TEXT[arm.kind], r1))
         del arm
+
+    # ---- oracle values for the in-run parity sample (CPU leg): the first PARITY_ROWS rows of THIS rank-0 batch,
+    # 1 % of them out of grid, through the dense oracle (pinned to the reference by tests/golden)
+    parity_ref = None
+    if rank == 0:
+        from oracle.like_port import lnlike_phot_dense
+        parity_ref = lnlike_phot_dense(fitargs['MISTpath'], fitargs['photANNpath'], fitargs['obs_phot'],
+                                       synth.draw_theta_phot(args.batch, seed=3, box=box)[:PARITY_ROWS])
 
     # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (read when the library loads); stdout carries
     # the one JSON line
@@ -294,6 +341,11 @@ def main():
         np.allclose(out_h[np.isfinite(dev_l)], dev_l[np.isfinite(dev_l)], rtol=1e-12, atol=1e-9), \
         'host and device entry points disagree'
 
+    # ---- in-run parity: the output of the timed (fused) kernel itself against the oracle sample
+    parity = None
+    if parity_ref is not None:
+        parity = parity_check(L, eng, theta_np, dev_l, parity_ref, args.precision)
+
     # ---- auxiliary: stars fitted per hour (BASELINE.json metric, configs[4]) on a small catalog
     catalog = None
     if args.catalog_stars > 0:
@@ -389,6 +441,7 @@ def main():
                                  ms_per_launch=in_ms / max(in_n, 1)),
             kernel_ms={k: v[0] / args.steps for k, v in prof.items() if v[1]},
             kernel_ms_two_kernel_sequence={k: v[0] / 5 for k, v in prof2.items() if v[1]},
+            parity_check=parity,
             catalog=catalog,
             spec_phot=specblk,
             cpu_baseline=cpu)

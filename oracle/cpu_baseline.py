@@ -5,8 +5,11 @@ worker process per core (the reference's intended scale-out is one OS process
 per star, fitstar.py:244-249), BLAS threads pinned to 1.
 
 Used only by bench.py (``cpu_baseline`` leg and ``--impl reference``).  The
-likelihood object is oracle/like_port.py (``kind: "port"``): the reference is
-Python and /root/reference does not exist on the GPU box.
+likelihood object is the reference's OWN ``minesweeper.likelihood.likelihood`` class
+(``kind: "reference"``) imported through oracle/refshim.py from /root/reference or, on
+the GPU box, from the verbatim copy ``oracle/_ref`` that oracle/make_ref.py writes
+(un-vendored Payne / h5py stubbed as for the golden vectors).  Only when neither is
+present does it fall back to oracle/like_port.py (``kind: "port"``).
 
 Must be called BEFORE the parent process initialises CUDA (workers are forked).
 """
@@ -34,15 +37,36 @@ def _work(args):
     return hi - lo, time.perf_counter() - t0, acc
 
 
+def make_likeobj(fitargs, fitpars, runbools, kind=None):
+    """(likelihood object, kind).  kind None = the reference's own class when importable."""
+    from . import refshim
+    if kind is None:
+        kind = 'reference' if refshim.available() else 'port'
+    if kind == 'port':
+        from .like_port import LikelihoodPort
+        return LikelihoodPort(fitargs, fitpars, runbools), 'port'
+    import contextlib
+    import io
+    from .like_port import _mist_rows
+    refshim.install()
+    from minesweeper.likelihood import likelihood as RefLikelihood
+    fa = dict(fitargs)
+    if fitpars[1].get('EEP', False):
+        refshim.register_h5('cpuarm://mist', _mist_rows(fitargs['MISTpath']))
+        fa['MISTpath'] = 'cpuarm://mist'
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = RefLikelihood(fa, fitpars, runbools, verbose=False)
+    return obj, 'reference'
+
+
 class CpuArm(object):
-    def __init__(self, fitargs, fitpars, runbools, theta, cores=None):
+    def __init__(self, fitargs, fitpars, runbools, theta, cores=None, kind=None):
         global _PORT, _THETA
         for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'OPENBLAS_NUM_THREADS'):
             os.environ.setdefault(k, '1')
-        from .like_port import LikelihoodPort
         self.cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity')
                                else os.cpu_count())
-        _PORT = LikelihoodPort(fitargs, fitpars, runbools)
+        _PORT, self.kind = make_likeobj(fitargs, fitpars, runbools, kind)
         _THETA = np.asarray(theta, dtype=np.float64)
         self.pool = mp.get_context('fork').Pool(self.cores)
         self.rate1 = None

@@ -17,7 +17,7 @@ tests/golden/like_*.npz.
 import numpy as np
 from numpy.polynomial.chebyshev import chebval
 
-from .mist_port import GenMISTPort
+from .mist_port import GenMISTPort, dense_to_rows
 from .payne_port import FastPayneSEDPredict, PayneSpecPredict, _load
 
 SPEC_KEYS = ('Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R')
@@ -34,8 +34,7 @@ def blaze(coef, wave):
 def _mist_rows(container):
     c = _load(container)
     if 'values' in c:                       # dense form -> track tables
-        from minesweeper_b200.synth import mist_rows
-        return mist_rows(c)
+        return dense_to_rows(c)
     return c
 
 
@@ -152,3 +151,38 @@ def lnprobfn(pars, likeobj, priorobj):
     if lnp == -np.inf:
         return -np.inf
     return lnp + lnl
+
+
+def lnlike_phot_dense(mist, photnet, obs_phot, theta6, ageweight=True, mistdif=True, rel=1e-5):
+    """Batched restatement of the photometry-only isochrone likelihood (config 2) on the dense grid
+    container: the vectorised ``mist_port.interp_dense`` (pinned to the reference's getMIST by the goldens)
+    -> derived parameters (likelihood.py:121-141) -> ``FastPayneSEDPredict.sed_batch`` (genmod.py:97-142)
+    -> nansum chi-square over the observed bands (likelihood.py:207-210) -> + log(Agewgt) (:168-176).
+    theta6 columns = (Dist, Av, EEP, initial_[Fe/H], initial_[a/Fe], initial_Mass) = ``fitpars_i`` of that
+    fit.  For parity checks at sizes where the per-point form is too slow (bench.py's in-run sample, the
+    full-grid GPU test).  Returns a dict with brackets[B,4], ok[B], pred[B,9], mags[B,nb] (NaN rows when
+    not ok), lnl[B] (-inf when not ok) and ``bound[B]``: the |d lnL| a relative model-magnitude error
+    ``rel`` can cause (first + second order), the per-row tolerance of the fp32-class modes."""
+    from .mist_port import interp_dense
+    th = np.asarray(theta6, dtype=np.float64)
+    dist, av, eep, feh, afe, mass = th.T
+    br, pred, ok = interp_dense(mist, eep, mass, feh, afe)
+    sed = FastPayneSEDPredict(usebands=list(obs_phot.keys()), nnpath=photnet)
+    # columns of pred: log(Age), Mass, log(R), log(L), log(Teff), [Fe/H], [a/Fe], log(g), Agewgt
+    teff = 10.0 ** pred[:, 4]
+    sfeh, safe_ = (pred[:, 5], pred[:, 6]) if mistdif else (feh, afe)
+    pp = np.stack([teff, pred[:, 7], sfeh, safe_, pred[:, 2], dist, av], 1)
+    with np.errstate(invalid='ignore', divide='ignore', over='ignore'):
+        mags = np.full((len(th), len(sed.filternames)), np.nan)
+        mags[ok] = sed.sed_batch(pp[ok])
+        o = np.array([obs_phot[b][0] for b in sed.filternames])
+        s = np.array([obs_phot[b][1] for b in sed.filternames])
+        chi = np.nansum((mags - o) ** 2.0 / s ** 2.0, axis=1)
+        lnl = -0.5 * chi
+        if ageweight:
+            lnl = lnl + np.log(pred[:, 8])
+        lnl = np.where(ok, lnl, -np.inf)
+        dm = rel * np.abs(mags)
+        bound = np.nansum((np.abs(mags - o) * dm + 0.5 * dm ** 2) / s ** 2, axis=1)
+    return dict(brackets=br, ok=ok, pred=pred, mags=mags, lnl=lnl, bound=bound, photpars=pp,
+                bands=list(sed.filternames), obs_mag=o, obs_err=s)

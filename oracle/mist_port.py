@@ -29,6 +29,33 @@ PREDICTIONS = ('log(Age)', 'Mass', 'log(R)', 'log(L)', 'log(Teff)', '[Fe/H]',
                '[a/Fe]', 'log(g)')
 
 
+def dense_to_rows(mist):
+    """Dense container ``{eep, mass, feh, afe, values[na,nf,nm,ne,9], valid}`` -> the HDF5-like
+    ``{'index': [...], key: structured rows}`` that ``GenMIST.make_lib`` concatenates
+    (fastMISTmod.py:76-98): one table per ([Fe/H], [a/Fe]) pair keyed
+    ``'{feh:4.2f}/{afe:4.2f}/0.00'`` (key format of reference pullspectra.py:231), rows ordered by
+    mass then EEP.  The oracle's own converter, so that the checker does not depend on product code."""
+    dt = np.dtype([(n, 'f8') for n in _ROW_FIELDS + _OUT_FIELDS + ('Agewgt',)])
+    out = {'index': []}
+    for j, f in enumerate(mist['feh']):
+        for i, a in enumerate(mist['afe']):
+            mi, ei = np.nonzero(mist['valid'][i, j])
+            if len(mi) == 0:
+                continue
+            rows = np.empty(len(mi), dtype=dt)
+            rows['EEP'] = mist['eep'][ei]
+            rows['initial_mass'] = mist['mass'][mi]
+            rows['initial_[Fe/H]'] = f
+            rows['initial_[a/Fe]'] = a
+            vals = mist['values'][i, j][mi, ei]
+            for c, name in enumerate(_OUT_FIELDS + ('Agewgt',)):
+                rows[name] = vals[:, c]
+            key = '{0:4.2f}/{1:4.2f}/0.00'.format(f, a)
+            out['index'].append(key)
+            out[key] = rows
+    return out
+
+
 def bracket(axis, x):
     """``digitize([x], axis, right=False) - 1``: the i with
     ``axis[i] <= x < axis[i+1]``; -1 below the axis, ``len(axis)-1`` at or

@@ -74,9 +74,12 @@ class FastPayneSEDPredict(object):
     def bolcorr_batch(self, X):
         """Vectorised ``bolcorr`` for X[B, d_in] (test helper; same arithmetic)."""
         xs = (np.asarray(X, dtype=np.float64)[:, :self.d_in] - self.xmin) / (self.xmax - self.xmin) - 0.5
-        a1 = _sigmoid(np.einsum('bhd,nd->nbh', self.w1, xs) + self.b1)
-        a2 = _sigmoid(np.einsum('bhk,nbk->nbh', self.w2, a1) + self.b2)
-        return np.einsum('bk,nbk->nb', self.w3[:, 0, :], a2) + self.b3[:, 0]
+        out = np.empty((len(xs), len(self.w1)))
+        for b in range(len(self.w1)):                  # one BLAS product per band and layer
+            a1 = _sigmoid(xs @ self.w1[b].T + self.b1[b])
+            a2 = _sigmoid(a1 @ self.w2[b].T + self.b2[b])
+            out[:, b] = a2 @ self.w3[b, 0] + self.b3[b, 0]
+        return out
 
     def sed_batch(self, photpars):
         """photpars[B,7] = (Teff, logg, feh, afe, logR, Dist, Av) -> mags[B, nb], following

@@ -556,3 +556,51 @@ def test_tc_many_bands_run_as_band_groups(prec):
     rel = np.abs(lt_small[fin] - l64[fin]) / np.maximum(1.0, np.abs(l64[fin]))
     assert rel.max() < (1e-4 if prec == 'tc' else 5e-2), rel.max()
     assert np.array_equal(lt_big[:3000], lt_small)
+
+
+@pytest.mark.gpu
+def test_headline_config_fused_vs_oracle_full_grid():
+    """bench.py's configuration itself: the real-shape 607 x 140 x 19 x 5 grid (8.07 M vertices, 387 MB f32
+    table -- int64 offsets and strides a small grid cannot exercise), 10 x (6-128-128-1) net, 2^18 live points
+    incl. 1 % out of grid, evaluated by the ONE-kernel tensor-core form that the benchmark times, against the
+    dense oracle (pinned to the reference by the goldens): brackets bit-exact (two-kernel form exposes them),
+    derived values 2e-6 (f32 table), magnitudes 1e-5 relative, lnL within the per-row chi-square bound."""
+    from minesweeper_b200 import synth
+    from minesweeper_b200.likelihood import likelihood
+    from oracle.like_port import lnlike_phot_dense
+    mist = synth.make_mist(seed=0)
+    assert mist['values'].shape[:4] == (5, 19, len(mist['mass']), 607)
+    phot = synth.make_phot_net(h=128, seed=1)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    obs = synth.demo_obs_phot()
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot, obs_phot=obs)
+    n = 1 << 18
+    th = synth.draw_theta_phot(n, seed=3)
+    # the whole grid, not only the demo prior box: a second half spread over every axis
+    th[n // 2:] = synth.draw_theta_phot(n - n // 2, seed=4, frac_out=0.02,
+                                        box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 808.0),
+                                                 feh=(-4.0, 0.5), afe=(-0.2, 0.6), mass=(0.25, 30.0)))
+    ref = lnlike_phot_dense(mist, phot, obs, th)
+    L = likelihood(fitargs, fitpars, [False, True, False, False, False], precision='tc', verbose=False)
+    c0 = L.engine.launch_count()
+    lnl, der, _ = L.lnlike_batch(th)
+    assert L.engine.launch_count() - c0 == 1                       # the fused kernel, as timed
+    lnl, der = lnl.cpu().numpy(), der.cpu().numpy()
+    ok = ref['ok']
+    assert np.array_equal(np.isneginf(lnl), ~ok) and 0.005 < (~ok).mean() < 0.2
+    np.testing.assert_allclose(der[ok][:, 4:], ref['pred'][ok], rtol=2e-6, atol=2e-6)
+    assert np.all(np.isposinf(der[~ok][:, 4:]))
+    err = np.abs(lnl[ok] - ref['lnl'][ok])
+    tol = ref['bound'][ok] + 1e-6 + 1e-9 * np.abs(ref['lnl'][ok])
+    assert np.all(err <= tol), (err / tol).max()
+    # brackets (two-kernel form) bit-exact on the full grid
+    L.engine.set_fusion(False)
+    l2, d2, br = L.lnlike_batch(th, want_brackets=True)
+    assert np.array_equal(br.cpu().numpy(), ref['brackets'])
+    np.testing.assert_array_equal(d2.cpu().numpy(), der)
+    # magnitudes of the tensor-core MLP at the interpolated parameters
+    mags = L.engine.phot_sed(ref['photpars'][ok][:65536]).cpu().numpy()
+    np.testing.assert_allclose(mags, ref['mags'][ok][:65536], rtol=1e-5, atol=1e-5)

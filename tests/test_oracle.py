@@ -1,5 +1,7 @@
 """CPU: the oracle ports against golden vectors written by the reference itself
 (tests/golden/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -145,3 +147,54 @@ def test_samples_file_roundtrip_both_record_layouts(tmp_path):
     np.testing.assert_allclose(tab['log(wt)'], logwt, rtol=1e-9)
     st = postproc.summarize_samples_file(pa)
     assert set(st) == set(names) and st['Dist'][0] <= st['Dist'][1] <= st['Dist'][2]
+
+
+def test_dense_batched_lnlike_matches_reference_golden(g_like_phot):
+    """oracle.like_port.lnlike_phot_dense (the checker bench.py and the full-grid GPU test use at sizes
+    where the per-point form is too slow) against lnL / mags written by the reference's own likelihood
+    object (tests/golden/like_phot.npz)."""
+    from oracle.like_port import lnlike_phot_dense
+    g = g_like_phot
+    fitargs, fitpars, runbools = fit_setup(g)
+    assert [str(s) for s in g['fitpars_i']] == ['Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    r = lnlike_phot_dense(fitargs['MISTpath'], fitargs['photANNpath'], fitargs['obs_phot'], g['theta'])
+    fin = np.isfinite(g['lnl'])
+    assert np.array_equal(np.isneginf(r['lnl']), np.isneginf(g['lnl']))
+    np.testing.assert_allclose(r['lnl'][fin], g['lnl'][fin], rtol=1e-11, atol=1e-8)
+    assert [str(b) for b in g['bands']] == r['bands']
+    np.testing.assert_allclose(r['mags'][fin], g['mags'][fin], rtol=1e-12, atol=1e-12)
+
+
+def test_reference_copy_and_cpu_arm_object():
+    """oracle/make_ref.py copies the reference modules byte for byte, and the CPU arm's likelihood object is the
+    reference's own class (kind 'reference') agreeing with the port."""
+    import hashlib
+    from oracle import make_ref, refshim
+    from oracle.cpu_baseline import make_likeobj
+    from minesweeper_b200 import synth
+    if not refshim.available():
+        pytest.skip('no reference checkout and no oracle/_ref copy')
+    dst = make_ref.make(verbose=False)
+    if os.path.isdir('/root/reference/minesweeper'):
+        for f in make_ref.FILES:
+            a = hashlib.sha256(open(os.path.join('/root/reference/minesweeper', f), 'rb').read()).hexdigest()
+            b = hashlib.sha256(open(os.path.join(dst, 'minesweeper', f), 'rb').read()).hexdigest()
+            assert a == b, f
+    mist = synth.make_mist(ne=30, nm=9, nf=4, na=3, seed=5)
+    phot = synth.make_phot_net(h=16, seed=1)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+    fitpars = [names, {n: (n in on) for n in names}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot,
+                   obs_phot=synth.demo_obs_phot())
+    rb = [False, True, False, False, False]
+    R, kind = make_likeobj(fitargs, fitpars, rb)
+    P, kp = make_likeobj(fitargs, fitpars, rb, 'port')
+    assert kind == 'reference' and kp == 'port' and type(R).__module__ == 'minesweeper.likelihood'
+    th = synth.draw_theta_phot(60, seed=3, frac_out=0.1,
+                               box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 231.0), feh=(-4.0, 0.5),
+                                        afe=(-0.2, 0.6), mass=(0.25, 30.0)))
+    a = np.array([R.lnlikefn(list(t)) for t in th])
+    b = np.array([P.lnlikefn(list(t)) for t in th])
+    np.testing.assert_array_equal(a, b)
