@@ -112,6 +112,8 @@ typedef struct {
     int32_t ageweight;               /* fitargs['ageweight']  likelihood.py:23,168-176 */
     int32_t mistdif;                 /* fitargs['mistdif']    likelihood.py:27,127-132 */
     int32_t n_pc;                    /* number of blaze coefficients when modpoly */
+    int32_t slot;                    /* star slot whose observations (ms_set_star) every row is compared with when
+                                        the per-row star_slot array is NULL; 0 for a single-star ctx */
 } ms_flags;
 
 const char *ms_version(void);
@@ -153,8 +155,9 @@ int ms_spec_model(ms_ctx *ctx, int star_slot, const double *specpars, int n_pc,
 /* The batched likelihood.  theta[B][ndim] device f64; colmap[ndim] host int32
  * mapping each column to an MS_P_* id; fixed[MS_NPARAM] host f64 with NaN for
  * "not fixed" (fitargs['fixedpars']); star_slot[B] device int32 or NULL (= slot
- * 0 for every row).  lnL[B] device f64; derived[B][13] and brackets[B][4] may
- * be NULL. */
+ * flags->slot for every row).  A row whose slot lies outside the loaded slots gets
+ * lnL = NaN (nothing is read out of bounds).  lnL[B] device f64; derived[B][13] and
+ * brackets[B][4] may be NULL. */
 int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double *theta,
                     const int32_t *star_slot, int64_t B, int ndim, const int32_t *colmap,
                     const double *fixed, double *lnL, double *derived, int32_t *brackets,
@@ -237,6 +240,14 @@ int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
  * per SM (smaller batches keep the two-kernel sequence, which is faster there).  ms_set_fusion(ctx, 0) selects
  * the two-kernel sequence always (used by the tests and to time kernel (1) on its own); the default is 1. */
 int ms_set_fusion(ms_ctx *ctx, int enable);
+
+/* Scratch policy.  A ctx grows its per-batch scratch on demand (cudaFree + cudaMalloc inside the call), which
+ * is illegal while `stream` captures a CUDA graph and unsafe once a captured graph has baked the pointers in.
+ * ms_reserve pre-sizes every scratch buffer for batches of up to max_batch rows; with lock != 0 the buffers are
+ * pinned and a later call that needs more returns MS_ESTATE instead of reallocating (callers that capture
+ * ms_lnlike_batch / ms_lnprob_batch into graphs -- minesweeper_b200/sampler.py -- reserve first).  lock == 0
+ * lifts the pin.  Growth attempted during stream capture is refused with MS_ESTATE either way. */
+int ms_reserve(ms_ctx *ctx, int64_t max_batch, int lock);
 
 /* Number of kernel launches issued by this ctx so far (bench bookkeeping). */
 int64_t ms_launch_count(const ms_ctx *ctx);

@@ -64,7 +64,7 @@ class SpecNetDesc(C.Structure):
 
 class Flags(C.Structure):
     _fields_ = [('spec', C.c_int32), ('phot', C.c_int32), ('modpoly', C.c_int32),
-                ('ageweight', C.c_int32), ('mistdif', C.c_int32), ('n_pc', C.c_int32)]
+                ('ageweight', C.c_int32), ('mistdif', C.c_int32), ('n_pc', C.c_int32), ('slot', C.c_int32)]
 
 
 class PriorCol(C.Structure):
@@ -121,6 +121,7 @@ PROTOTYPES = {
     'ms_ns_accept': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
     'ms_ns_consume': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_void_p]),
     'ms_ns_finalize': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
+    'ms_reserve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
     'ms_set_fusion': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),

@@ -362,7 +362,11 @@ extern "C" int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, co
             while (ns <= star_slot) ns *= 2;
             double *m = nullptr, *e = nullptr;
             MS_CUDA(cudaMalloc((void **)&m, (size_t)ns * nb * sizeof(double)));
-            MS_CUDA(cudaMalloc((void **)&e, (size_t)ns * nb * sizeof(double)));
+            if (cudaMalloc((void **)&e, (size_t)ns * nb * sizeof(double)) != cudaSuccess) {
+                cudaGetLastError(); cudaFree(m);
+                ms_set_error("cudaMalloc of the star-slot table failed");
+                return MS_ENOMEM;
+            }
             // unobserved everywhere by default: NaN magnitude drops the band
             MS_CUDA(cudaMemset(m, 0xff, (size_t)ns * nb * sizeof(double)));
             MS_CUDA(cudaMemset(e, 0xff, (size_t)ns * nb * sizeof(double)));
@@ -453,7 +457,7 @@ extern "C" int ms_phot_sed(ms_ctx *ctx, const double *photpars, int64_t B, doubl
     MS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS))) return rc;
+    if ((rc = ensure_scratch(ctx, &ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS, st))) return rc;
     if ((rc = launch_repack_pars(ctx, photpars, 7, 0, B, ctx->scr_pars, st))) return rc;
     PhotArgs a{ctx->scr_pars, nullptr, mags, nullptr};
     return run_phot(ctx, a, B, st);
@@ -466,35 +470,36 @@ extern "C" int ms_spec_model(ms_ctx *ctx, int star_slot, const double *specpars,
     MS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS))) return rc;
+    if ((rc = ensure_scratch(ctx, &ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS, st))) return rc;
     if ((rc = launch_repack_pars(ctx, specpars, 8 + n_pc, 1, B, ctx->scr_pars, st))) return rc;
     SpecArgs a{ctx->scr_pars, star_slot, n_pc > 0, n_pc, flux, nullptr};
     return launch_spec(ctx, a, B, st);
 }
 
+static int check_batch_args(const ms_ctx *ctx, const ms_flags *flags, int64_t B, int ndim, const int32_t *colmap);
+
 extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double *theta,
                                const int32_t *star_slot, int64_t B, int ndim, const int32_t *colmap,
                                const double *fixed, double *lnL, double *derived, int32_t *brackets,
                                void *stream) {
-    if (ctx && B == 0) return MS_OK;                       // empty batch: nothing to do, NULL buffers allowed
-    if (!ctx || !flags || !theta || !colmap || !lnL || B < 0 || ndim < 1 || ndim > MS_NPARAM) {
-        ms_set_error("bad arguments");
-        return MS_EINVAL;
-    }
+    int rc;
+    if ((rc = check_batch_args(ctx, flags, B, ndim, colmap))) return rc;
+    if (B == 0) return MS_OK;                              // empty batch: nothing to do, NULL buffers allowed
+    if (!theta || !lnL) { ms_set_error("bad arguments"); return MS_EINVAL; }
     MS_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     ThetaView tv;
     identity_view(tv, theta, ndim);
     if (fixed) for (int i = 0; i < MS_NPARAM; ++i) tv.fixed[i] = fixed[i];
-    for (int c = 0; c < ndim; ++c) {
-        if (colmap[c] < 0 || colmap[c] >= MS_NPARAM) { ms_set_error("colmap[%d] = %d out of range", c, colmap[c]); return MS_EINVAL; }
-        tv.col[colmap[c]] = c;
-    }
+    for (int c = 0; c < ndim; ++c) tv.col[colmap[c]] = c;
     if (flags->spec && star_slot) {
-        ms_set_error("per-row star slots are supported for photometry-only batches; spectra use slot 0");
+        ms_set_error("per-row star slots are supported for photometry-only batches; spectra use flags->slot");
         return MS_EINVAL;
     }
-    int rc;
+    if (flags->phot && !star_slot && flags->slot >= ctx->nslots) {
+        ms_set_error("star slot %d has no photometry loaded (%d slots)", flags->slot, ctx->nslots);
+        return MS_ESTATE;
+    }
     const bool iso = tv.col[MS_P_EEP] >= 0 || tv.fixed[MS_P_EEP] == tv.fixed[MS_P_EEP];
     if (!iso && (derived || brackets)) {
         ms_set_error("derived / brackets requested but EEP is not a parameter");
@@ -506,14 +511,14 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
     if (iso && flags->phot && !flags->spec && !brackets && ctx->fuse_interp && ctx->precision >= MS_PREC_TC &&
         B >= (int64_t)ctx->sm_count * 256 * 4 && phot_tc_can_fuse(ctx)) {
         PhotArgs pa{nullptr, star_slot, nullptr, nullptr};
-        pa.lnL = lnL; pa.ageweight = flags->ageweight;
+        pa.lnL = lnL; pa.ageweight = flags->ageweight; pa.slot0 = flags->slot;
         return launch_phot_tc_fused(ctx, tv, pa, derived, flags->mistdif, B, st);
     }
-    if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS))) return rc;
+    if ((rc = ensure_scratch(ctx, &ctx->scr_pars, &ctx->scr_pars_n, (size_t)B * MS_NPARS, st))) return rc;
     // chi2 scratch is only needed when a spectrum term precedes the photometry
     double *chi2 = nullptr;
     if (flags->spec || !flags->phot) {
-        if ((rc = ensure_scratch(&ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)B))) return rc;
+        if ((rc = ensure_scratch(ctx, &ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)B, st))) return rc;
         chi2 = ctx->scr_chi2;
     }
     if (iso) {      // interpolation + parameter assembly in one kernel
@@ -523,27 +528,43 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
         if ((rc = launch_build_pars(ctx, tv, nullptr, flags->mistdif, B, ctx->scr_pars, chi2, st))) return rc;
     }
     if (flags->spec) {
-        SpecArgs sa{ctx->scr_pars, 0, flags->modpoly, flags->n_pc, nullptr, chi2};
+        SpecArgs sa{ctx->scr_pars, flags->slot, flags->modpoly, flags->n_pc, nullptr, chi2};
         if ((rc = launch_spec(ctx, sa, B, st))) return rc;
     }
     const int agew = iso && flags->ageweight;
     if (flags->phot) {   // photometry is the last term: it also writes lnL
         PhotArgs pa{ctx->scr_pars, star_slot, nullptr, chi2};
-        pa.lnL = lnL; pa.ageweight = agew;
+        pa.lnL = lnL; pa.ageweight = agew; pa.slot0 = flags->slot;
         return run_phot(ctx, pa, B, st);
     }
     return launch_finalize(ctx, ctx->scr_pars, chi2, agew, B, lnL, st);
 }
 
+static int check_batch_args(const ms_ctx *ctx, const ms_flags *flags, int64_t B, int ndim, const int32_t *colmap) {
+    if (!ctx || !flags || !colmap || B < 0 || ndim < 1 || ndim > MS_NPARAM) {
+        ms_set_error("bad arguments (ctx / flags / colmap NULL, B < 0 or ndim outside 1..%d)", MS_NPARAM);
+        return MS_EINVAL;
+    }
+    for (int c = 0; c < ndim; ++c)
+        if (colmap[c] < 0 || colmap[c] >= MS_NPARAM) {
+            ms_set_error("colmap[%d] = %d out of range", c, colmap[c]);
+            return MS_EINVAL;
+        }
+    if (flags->n_pc < 0 || flags->n_pc > MS_MAX_PC) { ms_set_error("n_pc out of range"); return MS_EINVAL; }
+    if (flags->slot < 0) { ms_set_error("flags->slot is negative"); return MS_EINVAL; }
+    return MS_OK;
+}
+
 extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const double *theta_host,
                                     int64_t B, int ndim, const int32_t *colmap, const double *fixed,
                                     double *lnL_host, double *derived_host) {
-    if (ctx && B == 0) return MS_OK;
-    if (!ctx || !theta_host || !lnL_host || B < 0) { ms_set_error("bad arguments"); return MS_EINVAL; }
-    MS_CUDA(cudaSetDevice(ctx->device));
     int rc;
-    if ((rc = ensure_scratch(&ctx->scr_theta, &ctx->scr_theta_n, (size_t)B * ndim))) return rc;
-    if ((rc = ensure_scratch(&ctx->scr_out, &ctx->scr_out_n, (size_t)B * (1 + MS_NDERIVED)))) return rc;
+    if ((rc = check_batch_args(ctx, flags, B, ndim, colmap))) return rc;       // before any allocation
+    if (B == 0) return MS_OK;
+    if (!theta_host || !lnL_host) { ms_set_error("bad arguments"); return MS_EINVAL; }
+    MS_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ensure_scratch(ctx, &ctx->scr_theta, &ctx->scr_theta_n, (size_t)B * ndim, ctx->own_stream))) return rc;
+    if ((rc = ensure_scratch(ctx, &ctx->scr_out, &ctx->scr_out_n, (size_t)B * (1 + MS_NDERIVED), ctx->own_stream))) return rc;
     double *lnl_d = ctx->scr_out, *der_d = derived_host ? ctx->scr_out + B : nullptr;
     // Chunked three-stream pipeline: the host->device copy of chunk k+1 and the device->host
     // copy of chunk k-1 overlap the kernels of chunk k (pinned host buffers make the copies
@@ -571,27 +592,64 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
         ctx->ev_pool.push_back(e);
     }
     // pre-size the per-batch scratch once so the chunk calls never reallocate mid-pipeline
-    if ((rc = ensure_scratch(&ctx->scr_pars, &ctx->scr_pars_n, (size_t)chunk * MS_NPARS))) return rc;
-    if ((rc = ensure_scratch(&ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)chunk))) return rc;
+    if ((rc = ensure_scratch(ctx, &ctx->scr_pars, &ctx->scr_pars_n, (size_t)chunk * MS_NPARS, ctx->own_stream))) return rc;
+    if ((rc = ensure_scratch(ctx, &ctx->scr_chi2, &ctx->scr_chi2_n, (size_t)chunk, ctx->own_stream))) return rc;
+    // on an error in the middle of the pipeline: let the copies already queued into caller buffers finish
+    // before returning, so the caller may free them
+    auto fail = [&](int code) {
+        cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->own_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+        return code;
+    };
+#define MS_CUDA_PIPE(call)                                                                       \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            ms_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+            return fail(MS_ECUDA);                                                               \
+        }                                                                                        \
+    } while (0)
     for (int k = 0; k < nchunks; ++k) {
         const int64_t b0 = cuts[k], nb = cuts[k + 1] - cuts[k];
         cudaEvent_t up = ctx->ev_pool[2 * k], done = ctx->ev_pool[2 * k + 1];
-        MS_CUDA(cudaMemcpyAsync(ctx->scr_theta + b0 * ndim, theta_host + b0 * ndim,
-                                (size_t)nb * ndim * sizeof(double), cudaMemcpyHostToDevice, ctx->h2d_stream));
-        MS_CUDA(cudaEventRecord(up, ctx->h2d_stream));
-        MS_CUDA(cudaStreamWaitEvent(ctx->own_stream, up, 0));
+        MS_CUDA_PIPE(cudaMemcpyAsync(ctx->scr_theta + b0 * ndim, theta_host + b0 * ndim,
+                                     (size_t)nb * ndim * sizeof(double), cudaMemcpyHostToDevice, ctx->h2d_stream));
+        MS_CUDA_PIPE(cudaEventRecord(up, ctx->h2d_stream));
+        MS_CUDA_PIPE(cudaStreamWaitEvent(ctx->own_stream, up, 0));
         if ((rc = ms_lnlike_batch(ctx, flags, ctx->scr_theta + b0 * ndim, nullptr, nb, ndim, colmap, fixed,
                                   lnl_d + b0, der_d ? der_d + b0 * MS_NDERIVED : nullptr, nullptr,
-                                  ctx->own_stream))) return rc;
-        MS_CUDA(cudaEventRecord(done, ctx->own_stream));
-        MS_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, done, 0));
-        MS_CUDA(cudaMemcpyAsync(lnL_host + b0, lnl_d + b0, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost,
-                                ctx->d2h_stream));
+                                  ctx->own_stream))) return fail(rc);
+        MS_CUDA_PIPE(cudaEventRecord(done, ctx->own_stream));
+        MS_CUDA_PIPE(cudaStreamWaitEvent(ctx->d2h_stream, done, 0));
+        MS_CUDA_PIPE(cudaMemcpyAsync(lnL_host + b0, lnl_d + b0, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost,
+                                     ctx->d2h_stream));
         if (derived_host)
-            MS_CUDA(cudaMemcpyAsync(derived_host + b0 * MS_NDERIVED, der_d + b0 * MS_NDERIVED,
-                                    (size_t)nb * MS_NDERIVED * sizeof(double), cudaMemcpyDeviceToHost,
-                                    ctx->d2h_stream));
+            MS_CUDA_PIPE(cudaMemcpyAsync(derived_host + b0 * MS_NDERIVED, der_d + b0 * MS_NDERIVED,
+                                         (size_t)nb * MS_NDERIVED * sizeof(double), cudaMemcpyDeviceToHost,
+                                         ctx->d2h_stream));
     }
+#undef MS_CUDA_PIPE
     MS_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
+    return MS_OK;
+}
+
+// Pre-size every per-batch scratch buffer for batches of up to max_batch rows (and, with a spectral net, its
+// chunk buffers) so that no later call allocates; lock != 0 also pins them: a call that would need more then
+// fails with MS_ESTATE instead of freeing memory that a captured CUDA graph still replays into.  lock == 0
+// (with any max_batch, 0 included) lifts the pin.
+extern "C" int ms_reserve(ms_ctx *ctx, int64_t max_batch, int lock) {
+    if (!ctx || max_batch < 0) { ms_set_error("bad arguments"); return MS_EINVAL; }
+    MS_CUDA(cudaSetDevice(ctx->device));
+    ctx->scratch_locked = false;
+    int rc;
+    const size_t B = (size_t)max_batch;
+    if (B > 0) {
+        cudaStream_t st = nullptr;
+        if ((rc = ensure_scratch(ctx, &ctx->scr_pars, &ctx->scr_pars_n, B * MS_NPARS, st))) return rc;
+        if ((rc = ensure_scratch(ctx, &ctx->scr_chi2, &ctx->scr_chi2_n, B, st))) return rc;
+        if ((rc = ensure_scratch(ctx, &ctx->scr_chi2g, &ctx->scr_chi2g_n, B, st))) return rc;
+        if (ctx->spec.w0 && (rc = spec_reserve(ctx, max_batch))) return rc;
+    }
+    ctx->scratch_locked = lock != 0;
     return MS_OK;
 }

@@ -74,6 +74,7 @@ struct ms_ctx {
     int device = 0;
     int precision = MS_PREC_F32;
     int fuse_interp = 1;           // ms_set_fusion
+    bool scratch_locked = false;   // ms_reserve(..., lock = 1): per-batch scratch may no longer grow
     int sm_count = 148;
     GridDev grid;
     PhotNetDev phot;
@@ -161,6 +162,7 @@ struct PhotArgs {
     // and chi2 is only read
     double *lnL = nullptr;
     int ageweight = 0;
+    int slot0 = 0;                 // star slot of every row when star_slot is nullptr (ms_flags.slot)
 };
 int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
 int phot_tc_prepare(ms_ctx *ctx);          // pack weights for the tensor-core kernel
@@ -179,17 +181,35 @@ struct SpecArgs {
 };
 int launch_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st);
 int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d);
+int spec_reserve(ms_ctx *ctx, int64_t max_batch);      // allocate the chunk buffers of the spectrum path now
 int spec_tc_prepare(ms_ctx *ctx);           // pack W2 for the tensor-core output GEMM
 void spec_tc_release(ms_ctx *ctx);
 int launch_spec_out_tc(ms_ctx *ctx, const float *h2, int64_t B, float *flux, cudaStream_t st);
 
 
-template <typename T> int ensure_scratch(T **p, size_t *have, size_t need) {
+// Per-batch scratch of a ctx: grown on demand (free + malloc), which is only legal while nothing else can
+// still hold the old pointer.  Two guards: (a) a stream that is capturing a CUDA graph must not
+// see cudaFree / cudaMalloc, and the captured graph would bake the pointer in -- growth during capture is
+// refused with MS_ESTATE; (b) ms_reserve(ctx, max_batch, lock = 1) pre-sizes every buffer and pins them:
+// later calls that would need more fail loudly instead of freeing memory a captured graph replays into.
+template <typename T> int ensure_scratch(ms_ctx *ctx, T **p, size_t *have, size_t need, cudaStream_t st) {
     if (*have >= need) return MS_OK;
+    if (ctx->scratch_locked) {
+        ms_set_error("batch needs %zu scratch elements but the ctx was reserved for less (ms_reserve): "
+                     "reserve a larger max_batch before capturing graphs", need);
+        return MS_ESTATE;
+    }
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+        ms_set_error("scratch would be reallocated while the stream is capturing a CUDA graph: run one eager "
+                     "warm-up batch of the same size or call ms_reserve first");
+        return MS_ESTATE;
+    }
     if (*p) cudaFree(*p);
     *p = nullptr; *have = 0;
     size_t n = need + need / 4;
     if (cudaMalloc((void **)p, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
         ms_set_error("cudaMalloc of %zu bytes failed", n * sizeof(T));
         return MS_ENOMEM;
     }

@@ -21,6 +21,7 @@ template <> __device__ __forceinline__ double sigmoid_t<double>(double z) { retu
 struct PhotKArgs {
     const double *pars; const int32_t *star_slot;
     double *mags; double *chi2; double *lnL; int ageweight;
+    int slot0, nslots;
     const double *obs_mag, *obs_err2;
     const float *w1, *b1, *w2, *b2, *w3, *b3;
     double xmin[8], xscale[8];
@@ -67,7 +68,10 @@ phot_mlp_kernel(PhotKArgs a, int64_t B) {
             for (int d = 0; d < 6; ++d)
                 if (d < D) xs[d] = (T)((xin[d] - a.xmin[d]) * a.xscale[d] - 0.5);
         }
-        const int slot = (live && a.star_slot) ? a.star_slot[p] : 0;
+        // star slot of this row; a slot outside the loaded table makes the row NaN instead of reading out of bounds
+        int slot = (live && a.star_slot) ? a.star_slot[p] : a.slot0;
+        const bool slot_ok = (unsigned)slot < (unsigned)a.nslots;
+        if (!slot_ok) slot = 0;
         double chi2 = 0.0;
         for (int b = 0; b < a.nb; ++b) {
             __syncthreads();
@@ -128,10 +132,11 @@ phot_mlp_kernel(PhotKArgs a, int64_t B) {
             if (ok) {
                 l = -0.5 * ((a.chi2 ? a.chi2[p] : 0.0) + chi2);
                 if (a.ageweight) l += log(a.pars[p * MS_NPARS + PV_AGEWGT]);
+                if (!slot_ok) l = ms_nan();
             }
             a.lnL[p] = l;
         } else if (ok && a.chi2) {
-            a.chi2[p] += chi2;
+            a.chi2[p] += slot_ok ? chi2 : ms_nan();
         }
     }
 }
@@ -169,6 +174,7 @@ int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st) {
     if ((a.chi2 || a.lnL) && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
     PhotKArgs ka;
     ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.chi2 = a.chi2; ka.lnL = a.lnL; ka.ageweight = a.ageweight;
+    ka.slot0 = a.slot0; ka.nslots = ctx->nslots;
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     ka.w1 = n.w1; ka.b1 = n.b1; ka.w2 = n.w2; ka.b2 = n.b2; ka.w3 = n.w3; ka.b3 = n.b3;
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }

@@ -135,6 +135,7 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 struct TcArgs {
     const double *pars; const int32_t *star_slot;
     double *mags; double *chi2; double *lnL; int ageweight;
+    int slot0, nslots;                 // constant slot when star_slot is nullptr; loaded slots (bounds check)
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
     double xmin[8], xscale[8];
@@ -332,7 +333,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         for (int d = 0; d < 6; ++d)
                             if (d < a.d_in) xs[d] = (float)((xin[d] - a.xmin[d]) * a.xscale[d] - 0.5);
                     }
-                    if (a.star_slot) ps.slot = a.star_slot[p];
+                    // a slot outside the loaded table is marked -1: the row comes out NaN, nothing is read out of bounds
+                    const int sl = a.star_slot ? a.star_slot[p] : a.slot0;
+                    ps.slot = (unsigned)sl < (unsigned)a.nslots ? sl : -1;
                 }
                 xs[6] = 1.0f;                                                // bias column
                 // X tile row in the core-matrix layout: chunk c (8 k) at c*2048 + r*16
@@ -389,7 +392,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 const unsigned char *cb = smem + SM_CONST + b * CONST_BYTES;
                 // this band's observation, requested now and used after the two epilogues
                 double obs_o = 0.0, obs_e2 = 1.0;
-                if (half == 0 && (a.chi2 || a.lnL)) {
+                if (half == 0 && (a.chi2 || a.lnL) && slot >= 0) {
                     const size_t at = (size_t)slot * a.nb_total + a.b0 + b;
                     obs_o = a.obs_mag[at]; obs_e2 = a.obs_err2[at];
                 }
@@ -489,10 +492,11 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 if (ok) {
                     l = -0.5 * ((a.chi2 ? a.chi2[p] : 0.0) + chi2);
                     if (a.ageweight) l += log(agewgt);
+                    if (slot < 0) l = ms_nan();
                 }
                 a.lnL[p] = l;
             } else if (ok && a.chi2) {
-                a.chi2[p] += chi2;
+                a.chi2[p] += slot < 0 ? ms_nan() : chi2;
             }
         }
     }
@@ -588,6 +592,7 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
     if ((a.chi2 || a.lnL) && !ctx->obs_mag) { ms_set_error("no star observations set"); return MS_ESTATE; }
     TcArgs ka;
     ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.ageweight = a.ageweight;
+    ka.slot0 = a.slot0; ka.nslots = ctx->nslots;
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
     ka.d_in = n.d_in; ka.nb_total = n.nb;
@@ -608,7 +613,7 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
     if (ngroups > 1) {
         if (tv) { ms_set_error("fused interpolation + photometry needs <= %d bands", MAX_NB); return MS_ESTATE; }
         if (!carry && a.lnL) {
-            int rc = ensure_scratch(&ctx->scr_chi2g, &ctx->scr_chi2g_n, (size_t)B);
+            int rc = ensure_scratch(ctx, &ctx->scr_chi2g, &ctx->scr_chi2g_n, (size_t)B, st);
             if (rc) return rc;
             carry = ctx->scr_chi2g;
             MS_CUDA(cudaMemsetAsync(carry, 0, (size_t)B * sizeof(double), st));

@@ -216,10 +216,10 @@ int spec_tc_prepare(ms_ctx *ctx) {
             img[at] = hi;
             img[at + OPER_BYTES / 2] = lo;
         }
+    S.tc_pack = pk;                                        // owned by the ctx from here: ms_destroy releases it on any error
     MS_CUDA(cudaMalloc((void **)&pk->b_img, bytes));
     MS_CUDA(cudaMemcpy(pk->b_img, img.data(), bytes, cudaMemcpyHostToDevice));
     MS_CUDA(cudaFuncSetAttribute(spec_out_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
-    S.tc_pack = pk;
     return MS_OK;
 }
 

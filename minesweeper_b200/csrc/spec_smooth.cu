@@ -584,26 +584,42 @@ template <typename T>
 int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux,
                      const double *d_xmin_scale, cudaStream_t st);
 
-template <typename T>
-static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) {
+// chunk of points whose native flux is materialised between the MLP and the smoother:
+// L2-sized for the CUDA-core GEMM, whole waves of 128x128 tiles for the tensor-core GEMM
+static int64_t spec_chunk(const ms_ctx *ctx) { return (ctx->precision >= MS_PREC_TC) ? 8192 : 1024; }
+
+int spec_reserve(ms_ctx *ctx, int64_t max_batch) {
     const SpecNetDev &n = ctx->spec;
-    const StarDev &star = ctx->stars[a.star_slot];
-    // chunk of points whose native flux is materialised between the MLP and the smoother:
-    // L2-sized for the CUDA-core GEMM, whole waves of 128x128 tiles for the tensor-core GEMM
-    const int64_t chunk = (ctx->precision >= MS_PREC_TC) ? 8192 : 1024;
-    const size_t flux_bytes = (size_t)chunk * n.npix * sizeof(T);
-    const size_t hid_bytes = (size_t)chunk * (n.d_in + 2 * n.h) * sizeof(T);
+    const size_t esz = ctx->precision == MS_PREC_F64 ? 8 : 4;
+    int64_t chunk = spec_chunk(ctx);
+    if (max_batch < chunk) chunk = max_batch;
+    const size_t flux_bytes = (size_t)chunk * n.npix * esz;
+    const size_t hid_bytes = (size_t)chunk * (n.d_in + 2 * n.h) * esz;
     if (ctx->scr_flux_bytes < flux_bytes) {
+        if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
         if (ctx->scr_flux) cudaFree(ctx->scr_flux);
         ctx->scr_flux = nullptr; ctx->scr_flux_bytes = 0;
         MS_CUDA(cudaMalloc(&ctx->scr_flux, flux_bytes));
         ctx->scr_flux_bytes = flux_bytes;
     }
     if (ctx->scr_hid_bytes < hid_bytes) {
+        if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
         if (ctx->scr_hid) cudaFree(ctx->scr_hid);
         ctx->scr_hid = nullptr; ctx->scr_hid_bytes = 0;
         MS_CUDA(cudaMalloc(&ctx->scr_hid, hid_bytes));
         ctx->scr_hid_bytes = hid_bytes;
+    }
+    return MS_OK;
+}
+
+template <typename T>
+static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) {
+    const SpecNetDev &n = ctx->spec;
+    const StarDev &star = ctx->stars[a.star_slot];
+    const int64_t chunk = spec_chunk(ctx);
+    {
+        int rc = spec_reserve(ctx, B);
+        if (rc) return rc;
     }
     const size_t smem = (size_t)((sizeof(T) == 4 ? 2 : 1) * n.n1 + n.npix) * sizeof(T);
     if (smem > 226 * 1024) {

@@ -69,7 +69,10 @@ class Engine(object):
             if bands is None:
                 pick = list(range(len(names)))
             else:
-                pick = [names.index(str(b)) for b in bands if str(b) in names]
+                missing = [str(b) for b in bands if str(b) not in names]
+                if missing:          # the scalar genphot would raise KeyError on them; do not drop them silently
+                    raise KeyError('observed bands %s are not in the photometric net (%s)' % (missing, names))
+                pick = [names.index(str(b)) for b in bands]
             self.bands = [names[i] for i in pick]
             w = {k: _f32(photnet[k][pick]) for k in ('w1', 'b1', 'w2', 'b2', 'w3', 'b3')}
             xmin, xmax = _f64(photnet['xmin']), _f64(photnet['xmax'])
@@ -98,6 +101,7 @@ class Engine(object):
         del keep
         self.device = torch.device('cuda', self.device_index)
         self.n_obs = {}
+        self.nslots_phot = 0            # star slots with photometry loaded: 0 .. nslots_phot - 1
 
     def close(self):
         if getattr(self, '_ctx', None) is not None and self._ctx.value:
@@ -136,11 +140,29 @@ class Engine(object):
                                    _dp(err) if nb else None, nb, _dp(w) if n_obs else None,
                                    _dp(f) if n_obs else None, _dp(e) if n_obs else None, n_obs))
         self.n_obs[int(slot)] = n_obs
+        if nb:
+            self.nslots_phot = max(self.nslots_phot, int(slot) + 1)
 
     def set_stars_phot(self, obs_mag, obs_err, first_slot=0):
         """Catalog mode: obs_mag / obs_err[nstars, nb] (NaN = unobserved) into consecutive slots."""
         m, e = _f64(obs_mag), _f64(obs_err)
         check(self.lib.ms_set_stars_phot(self._ctx, int(first_slot), m.shape[0], _dp(m), _dp(e), m.shape[1]))
+        self.nslots_phot = max(self.nslots_phot, int(first_slot) + m.shape[0])
+
+    def check_star_slots(self, nstars, star_plx=None):
+        """Catalog callers (the samplers) address star slots 0 .. nstars - 1: they must all be loaded, and a
+        per-star parallax table must cover them (the kernels index both by slot)."""
+        if nstars > 1 and nstars > self.nslots_phot:
+            raise ValueError('%d stars requested but only %d star slots have photometry loaded '
+                             '(set_stars_phot / set_star)' % (nstars, self.nslots_phot))
+        if star_plx is not None and star_plx.shape[0] < nstars:
+            raise ValueError('star_plx has %d rows for %d stars' % (star_plx.shape[0], nstars))
+
+    def reserve(self, max_batch, lock=True):
+        """Pre-size the ctx's per-batch scratch for batches of up to ``max_batch`` rows and (lock=True) pin it, so
+        that CUDA graphs capturing lnlike_batch / lnprob_batch keep valid pointers; ``reserve(0, lock=False)`` lifts
+        the pin.  See ms_reserve in include/minesweeper_b200.h."""
+        check(self.lib.ms_reserve(self._ctx, int(max_batch), int(bool(lock))))
 
     # -- helpers -------------------------------------------------------------
     def _dev(self, a):
@@ -199,8 +221,8 @@ class Engine(object):
         return fx
 
     @staticmethod
-    def make_flags(spec=False, phot=True, modpoly=False, ageweight=True, mistdif=True, n_pc=0):
-        return Flags(int(spec), int(phot), int(modpoly), int(ageweight), int(mistdif), int(n_pc))
+    def make_flags(spec=False, phot=True, modpoly=False, ageweight=True, mistdif=True, n_pc=0, slot=0):
+        return Flags(int(spec), int(phot), int(modpoly), int(ageweight), int(mistdif), int(n_pc), int(slot))
 
     def lnlike_batch(self, theta, colmap, fixed, flags, star_slot=None, want_derived=True,
                      want_brackets=False, out=None, derived_out=None):

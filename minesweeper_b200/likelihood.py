@@ -73,7 +73,7 @@ class likelihood(object):
         self._fixed = Engine.make_fixed(self.fixedpars)
         self._flags = Engine.make_flags(spec=self.spec_bool, phot=self.phot_bool,
                                         modpoly=self.modpoly_bool, ageweight=self.ageweight,
-                                        mistdif=self.dif_bool, n_pc=len(self.pc_names))
+                                        mistdif=self.dif_bool, n_pc=len(self.pc_names), slot=self.slot)
         self.parsdict = {}
         self.MISTrename = {'log_age': 'log(Age)', 'star_mass': 'Mass', 'log_R': 'log(R)',
                            'log_L': 'log(L)', 'log_Teff': 'log(Teff)', 'log_g': 'log(g)'}

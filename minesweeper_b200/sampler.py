@@ -54,6 +54,7 @@ class BatchedNestedSampler(object):
         self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
         self.store = bool(store_samples)
         self.ncall = torch.zeros(self.S, dtype=torch.int64, device=self.dev)
+        self.eng.check_star_slots(self.S, self.star_plx)
 
     # one batched evaluation of lnprob for u[N, ndim] belonging to stars slot[N]
     def _lnprob(self, u, slot):
@@ -211,6 +212,13 @@ class BatchedNestedSampler(object):
 
     # ------------------------------------------------------------------------------------------
     def run_graphed(self, check_every=64, verbose=False, min_compact=512):
+        self.eng.reserve(self.S * self.K, lock=True)
+        try:
+            return self._run_graphed(check_every, verbose, min_compact)
+        finally:
+            self.eng.reserve(0, lock=False)
+
+    def _run_graphed(self, check_every=64, verbose=False, min_compact=512):
         """Same sampler with one nested-sampling iteration captured in a CUDA graph and replayed.
 
         Every tensor has a static shape (all stars of the current working set take part in every
@@ -420,9 +428,21 @@ class QueuedNestedSampler(object):
         self.dlogz, self.maxiter, self.seed = float(dlogz), int(maxiter), int(seed)
         self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
         self.store, self.dead_cap = bool(store_samples), int(dead_cap)
+        self.eng.check_star_slots(self.S, self.star_plx)
 
     def run(self, check_every=4, verbose=False, min_compact=512):
+        # the rounds are captured into CUDA graphs that bake the ctx's scratch pointers in: size the scratch for the
+        # largest batch of the run and pin it for its duration (another caller growing it would free it under us)
+        self.eng.reserve(self.S * max(self.K, self.Q), lock=True)
+        try:
+            return self._run(check_every, verbose, min_compact)
+        finally:
+            self.eng.reserve(0, lock=False)
+
+    def _run(self, check_every=4, verbose=False, min_compact=512):
         import ctypes as C
+        if self.store and min_compact < self.S:
+            raise ValueError('store_samples needs min_compact >= nstars (the dead-point buffer is not compacted)')
         S, K, Q, nd, nder, dev = self.S, self.K, self.Q, self.nd, self.nder, self.dev
         ncol = nd + nder
         f64 = torch.float64

@@ -29,8 +29,8 @@ def test_header_symbols_exported():
 
 def test_struct_layouts_match_header():
     from minesweeper_b200 import _lib
-    # ms_flags: six int32; ms_grid_desc: four int32 then six pointers
-    assert ctypes.sizeof(_lib.Flags) == 24
+    # ms_flags: seven int32; ms_grid_desc: four int32 then six pointers
+    assert ctypes.sizeof(_lib.Flags) == 28
     assert ctypes.sizeof(_lib.GridDesc) == 16 + 6 * ctypes.sizeof(ctypes.c_void_p)
     assert _lib.MS_NPARAM == 24 and _lib.MS_NDERIVED == 13
 

@@ -604,3 +604,99 @@ def test_headline_config_fused_vs_oracle_full_grid():
     # magnitudes of the tensor-core MLP at the interpolated parameters
     mags = L.engine.phot_sed(ref['photpars'][ok][:65536]).cpu().numpy()
     np.testing.assert_allclose(mags, ref['mags'][ok][:65536], rtol=1e-5, atol=1e-5)
+
+
+def _phot_fit(seed=32, h=32):
+    from minesweeper_b200 import synth
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
+    phot = synth.make_phot_net(h=h, seed=seed)
+    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
+    on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
+    fitpars = [names, {k: (k in on) for k in names}]
+    fitargs = dict(ageweight=True, mistdif=True, fixedpars={}, MISTpath=mist, photANNpath=phot,
+                   obs_phot=synth.demo_obs_phot())
+    th = synth.draw_theta_phot(700, seed=8, frac_out=0.03,
+                               box=dict(Dist=(1.0, 100.0), Av=(0.0, 0.1), EEP=(202.0, 261.0), feh=(-4.0, 0.0),
+                                        afe=(-0.2, 0.6), mass=(0.5, 1.25)))
+    return fitargs, fitpars, [False, True, False, False, False], th
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prec', ['f64', 'tc'])
+def test_two_likelihoods_share_one_engine_through_slots(prec):
+    """``likelihood(..., slot=s)`` must evaluate against slot s's observations.  Two stars with
+    different photometry on ONE engine give the same lnL as each star on its own engine."""
+    from minesweeper_b200.likelihood import likelihood
+    h = 128 if prec == 'tc' else 32
+    fitargs, fitpars, rb, th = _phot_fit(h=h)
+    fa2 = dict(fitargs, obs_phot={k: [v[0] + 0.3, v[1] * 1.5] for k, v in fitargs['obs_phot'].items()})
+    A = likelihood(fitargs, fitpars, rb, precision=prec, verbose=False)
+    B_own = likelihood(fa2, fitpars, rb, precision=prec, verbose=False)
+    B = likelihood(fa2, fitpars, rb, precision=prec, verbose=False, engine=A.engine, slot=3)
+    la, lb, lb_own = (x.lnlike_batch(th)[0].cpu().numpy() for x in (A, B, B_own))
+    np.testing.assert_array_equal(lb, lb_own)
+    fin = np.isfinite(la)
+    assert np.abs(la[fin] - lb[fin]).max() > 1.0                      # really different stars
+    assert B.lnlikefn(list(th[5])) == lb[5] and A.lnlikefn(list(th[5])) == la[5]
+    # slot 1 and 2 exist in the table but were never set: every band NaN -> an error, not a silent lnL = 0
+    from minesweeper_b200._lib import MSError
+    fl = A.engine.make_flags(slot=7)
+    with pytest.raises(MSError):
+        A.engine.lnlike_batch(th, A._colmap, A._fixed, fl)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('prec', ['f32', 'tc'])
+def test_out_of_range_star_slots_give_nan_not_garbage(prec):
+    from minesweeper_b200.likelihood import likelihood
+    fitargs, fitpars, rb, th = _phot_fit(h=128 if prec == 'tc' else 32)
+    L = likelihood(fitargs, fitpars, rb, precision=prec, verbose=False)
+    n = 148 * 256 * 4 if prec == 'tc' else len(th)                     # tc: reach the fused one-kernel form too
+    big = np.tile(th, (n // len(th) + 1, 1))[:n]
+    slots = np.zeros(n, dtype=np.int32)
+    slots[5::7] = 1 << 20                                              # far outside the table
+    slots[3::11] = -2
+    ref = L.lnlike_batch(big)[0].cpu().numpy()
+    got = L.lnlike_batch(big, star_slot=slots)[0].cpu().numpy()
+    bad = slots != 0
+    ok_rows = np.isfinite(ref)
+    assert np.all(np.isnan(got[bad & ok_rows])) and np.array_equal(got[~bad], ref[~bad])
+    assert np.all(np.isneginf(got[bad & ~ok_rows]))                    # out-of-grid rows stay -inf
+
+
+@pytest.mark.gpu
+def test_reserve_pins_scratch_and_capture_refuses_growth():
+    """scratch baked into a CUDA graph must not be freed by a later, larger eager call."""
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200._lib import MSError
+    fitargs, fitpars, rb, th = _phot_fit()
+    L = likelihood(fitargs, fitpars, rb, precision='f32', verbose=False)
+    eng = L.engine
+    eng.reserve(len(th), lock=True)
+    small = L.lnlike_batch(th)[0].cpu().numpy()
+    with pytest.raises(MSError, match='reserve'):
+        L.lnlike_batch(np.tile(th, (4, 1)))
+    eng.reserve(0, lock=False)
+    assert np.array_equal(L.lnlike_batch(np.tile(th, (4, 1)))[0].cpu().numpy()[:len(th)], small)
+    # growth during stream capture is refused (fresh engine: nothing allocated yet)
+    L2 = likelihood(fitargs, fitpars, rb, precision='f32', verbose=False)
+    tht = torch.from_numpy(th).to(L2.engine.device)
+    out = torch.empty(len(th), dtype=torch.float64, device=L2.engine.device)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(L2.engine.device)
+    with torch.cuda.stream(s):
+        with pytest.raises(MSError, match='captur'):
+            with torch.cuda.graph(g, stream=s):
+                L2.engine.lnlike_batch(tht, L2._colmap, L2._fixed, L2._flags, want_derived=False, out=out)
+    torch.cuda.synchronize()
+    # after a warm-up of the same size the capture works and replays correctly
+    L2.engine.lnlike_batch(tht, L2._colmap, L2._fixed, L2._flags, want_derived=False, out=out)
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        L2.engine.lnlike_batch(tht, L2._colmap, L2._fixed, L2._flags, want_derived=False, out=out)
+    out.zero_()
+    g2.replay()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), small)
