@@ -241,6 +241,12 @@ int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
  * the two-kernel sequence always (used by the tests and to time kernel (1) on its own); the default is 1. */
 int ms_set_fusion(ms_ctx *ctx, int enable);
 
+/* f32-class modes: the broadening chain of genspec (smoothing.py:202-264, 517-598) normally runs in the fast
+ * kernel (csrc/spec_fast.cu: radix-16 FFT for the rotational stage, direct Gaussian sum for the instrumental
+ * stage) with the generic FFT kernel (csrc/spec_smooth.cu) taking the rows it declines.  ms_set_spec_fast(ctx, 0)
+ * sends every row through the generic kernel (used by the tests to compare the two); the default is 1. */
+int ms_set_spec_fast(ms_ctx *ctx, int enable);
+
 /* Scratch policy.  A ctx grows its per-batch scratch on demand (cudaFree + cudaMalloc inside the call), which
  * is illegal while `stream` captures a CUDA graph and unsafe once a captured graph has baked the pointers in.
  * ms_reserve pre-sizes every scratch buffer for batches of up to max_batch rows; with lock != 0 the buffers are

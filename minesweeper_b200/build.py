@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmsb200.so')
 SOURCES = ['capi.cu', 'mist_interp.cu', 'pars.cu', 'prior.cu', 'sampler.cu', 'phot_mlp.cu', 'phot_mlp_tc.cu',
-           'spec_mlp.cu', 'spec_mlp_tc.cu', 'spec_smooth.cu']
+           'spec_mlp.cu', 'spec_mlp_tc.cu', 'spec_smooth.cu', 'spec_fast.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

@@ -302,7 +302,7 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(S.wave); cudaFree(S.a1_idx); cudaFree(S.a2_idx); cudaFree(S.a1_frac); cudaFree(S.a2_frac);
     cudaFree(S.a1_fracd); cudaFree(S.a2_fracd); cudaFree(S.twiddle32); cudaFree(S.twiddle64);
     cudaFree(S.xms); cudaFree(S.rot_tab); cudaFree(S.twlev32); spec_tc_release(ctx);
-    cudaFree(ctx->obs_mag); cudaFree(ctx->obs_err2);
+    cudaFree(ctx->obs_mag); cudaFree(ctx->obs_err2); cudaFree(ctx->stars_dev); cudaFree(ctx->scr_fb);
     for (StarDev &s : ctx->stars) {
         cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2);
         cudaFree(s.cheb_x);
@@ -319,6 +319,12 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
 
 extern "C" int ms_precision(const ms_ctx *ctx) { return ctx ? ctx->precision : MS_EINVAL; }
 extern "C" int64_t ms_launch_count(const ms_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ms_set_spec_fast(ms_ctx *ctx, int enable) {
+    if (!ctx) { ms_set_error("bad arguments"); return MS_EINVAL; }
+    ctx->spec_fast = enable ? 1 : 0;
+    return MS_OK;
+}
 
 extern "C" int ms_set_fusion(ms_ctx *ctx, int enable) {
     if (!ctx) { ms_set_error("bad arguments"); return MS_EINVAL; }
@@ -344,6 +350,27 @@ extern "C" int ms_profile_read(ms_ctx *ctx, double *ms_by_kind, int64_t *launche
         ms_by_kind[r.kind] += ms;
         launches_by_kind[r.kind] += 1;
     }
+    return MS_OK;
+}
+
+// device table of the per-slot spectrum views (what the broadening kernels index by star slot)
+static int refresh_star_views(ms_ctx *ctx) {
+    std::vector<StarView> v(ctx->stars.size());
+    for (size_t i = 0; i < v.size(); ++i) {
+        const StarDev &s = ctx->stars[i];
+        v[i] = StarView{s.n_obs, 0, s.obs_wave, s.obs_lnwave, s.obs_flux, s.obs_err2, s.cheb_x, s.wmin, s.wmax};
+    }
+    if ((int)v.size() > ctx->stars_dev_n) {
+        cudaFree(ctx->stars_dev);
+        ctx->stars_dev = nullptr; ctx->stars_dev_n = 0;
+        int cap = 1;
+        while (cap < (int)v.size()) cap *= 2;
+        MS_CUDA(cudaMalloc((void **)&ctx->stars_dev, (size_t)cap * sizeof(StarView)));
+        MS_CUDA(cudaMemset(ctx->stars_dev, 0, (size_t)cap * sizeof(StarView)));
+        ctx->stars_dev_n = cap;
+    }
+    if (!v.empty())
+        MS_CUDA(cudaMemcpy(ctx->stars_dev, v.data(), v.size() * sizeof(StarView), cudaMemcpyHostToDevice));
     return MS_OK;
 }
 
@@ -409,7 +436,7 @@ extern "C" int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, co
         if ((rc = upload(&s.cheb_x, cx.data(), n_obs))) return rc;
         s.n_obs = n_obs; s.wmin = wmin; s.wmax = wmax;
     }
-    return MS_OK;
+    return refresh_star_views(ctx);
 }
 
 extern "C" int ms_set_stars_phot(ms_ctx *ctx, int first_slot, int nstars, const double *obs_mag,
@@ -428,7 +455,7 @@ extern "C" int ms_set_stars_phot(ms_ctx *ctx, int first_slot, int nstars, const 
     for (size_t i = 0; i < e2.size(); ++i) e2[i] = obs_err[i] * obs_err[i];
     MS_CUDA(cudaMemcpy(ctx->obs_mag + (size_t)first_slot * nb, obs_mag, e2.size() * sizeof(double), cudaMemcpyHostToDevice));
     MS_CUDA(cudaMemcpy(ctx->obs_err2 + (size_t)first_slot * nb, e2.data(), e2.size() * sizeof(double), cudaMemcpyHostToDevice));
-    return MS_OK;
+    return refresh_star_views(ctx);
 }
 
 static void identity_view(ThetaView &tv, const double *theta, int ld) {
@@ -492,12 +519,9 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
     identity_view(tv, theta, ndim);
     if (fixed) for (int i = 0; i < MS_NPARAM; ++i) tv.fixed[i] = fixed[i];
     for (int c = 0; c < ndim; ++c) tv.col[colmap[c]] = c;
-    if (flags->spec && star_slot) {
-        ms_set_error("per-row star slots are supported for photometry-only batches; spectra use flags->slot");
-        return MS_EINVAL;
-    }
-    if (flags->phot && !star_slot && flags->slot >= ctx->nslots) {
-        ms_set_error("star slot %d has no photometry loaded (%d slots)", flags->slot, ctx->nslots);
+    if (flags->phot && !star_slot &&
+        (flags->slot >= ctx->nslots || flags->slot >= (int)ctx->stars.size() || !ctx->stars[flags->slot].set)) {
+        ms_set_error("star slot %d has no photometry loaded (ms_set_star)", flags->slot);
         return MS_ESTATE;
     }
     const bool iso = tv.col[MS_P_EEP] >= 0 || tv.fixed[MS_P_EEP] == tv.fixed[MS_P_EEP];
@@ -529,6 +553,7 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
     }
     if (flags->spec) {
         SpecArgs sa{ctx->scr_pars, flags->slot, flags->modpoly, flags->n_pc, nullptr, chi2};
+        sa.star_slots = star_slot;                     // per-row slots: every row against its own star's spectrum
         if ((rc = launch_spec(ctx, sa, B, st))) return rc;
     }
     const int agew = iso && flags->ageweight;

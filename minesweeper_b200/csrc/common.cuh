@@ -70,6 +70,13 @@ struct StarDev {
     double wmin = 0, wmax = 0;
 };
 
+// device-side view of one star slot's observed spectrum (table ctx->stars_dev, indexed by slot)
+struct StarView {
+    int n_obs, pad_;
+    const double *obs_wave, *obs_lnwave, *obs_flux, *obs_err2, *cheb_x;
+    double wmin, wmax;
+};
+
 struct ms_ctx {
     int device = 0;
     int precision = MS_PREC_F32;
@@ -83,6 +90,9 @@ struct ms_ctx {
     int nslots = 0;
     double *obs_mag = nullptr, *obs_err2 = nullptr;
     std::vector<StarDev> stars;
+    StarView *stars_dev = nullptr; int stars_dev_n = 0;      // device copy of the spectrum views, refreshed by ms_set_star
+    int spec_fast = 1;             // f32-class modes: use the fast broadening kernel (ms_set_spec_fast)
+    int *scr_fb = nullptr; size_t scr_fb_bytes = 0;          // fallback row list of the fast broadening kernel
     // scratch (grown on demand, stream-ordered use on one stream at a time)
     double *scr_derived = nullptr; size_t scr_derived_n = 0;
     double *scr_pars = nullptr;    size_t scr_pars_n = 0;
@@ -174,17 +184,19 @@ int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, do
 
 struct SpecArgs {
     const double *pars;            // [B][MS_NPARS]
-    int star_slot;                 // one slot per call
+    int star_slot;                 // slot of every row when star_slots is nullptr
     int modpoly, n_pc;
     double *flux;                  // [B][n_obs] or nullptr
     double *chi2;                  // [B] or nullptr: chi2[i] += chi2_spec
+    const int32_t *star_slots = nullptr;   // [B] per-row slots (catalog fits with spectra), device
 };
 int launch_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st);
 int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d);
 int spec_reserve(ms_ctx *ctx, int64_t max_batch);      // allocate the chunk buffers of the spectrum path now
 int spec_tc_prepare(ms_ctx *ctx);           // pack W2 for the tensor-core output GEMM
+int spec_tc_reserve(ms_ctx *ctx, int64_t chunk);   // operand-image scratch of the tensor-core GEMMs for `chunk` points
 void spec_tc_release(ms_ctx *ctx);
-int launch_spec_out_tc(ms_ctx *ctx, const float *h2, int64_t B, float *flux, cudaStream_t st);
+int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, cudaStream_t st);
 
 
 // Per-batch scratch of a ctx: grown on demand (free + malloc), which is only legal while nothing else can

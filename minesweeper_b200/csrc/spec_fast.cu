@@ -1,0 +1,547 @@
+// Kernel (3), f32 fast path: rotational + instrumental broadening, resampling onto the observed
+// pixels, blaze polynomial and the spectral chi-square for the fp32-class modes (MS_PREC_F32 / TC).
+// Same contract and reference lines as spec_smooth.cu (smoothing.py:92-114, 131-134, 202-264, 517-598;
+// fitutils.py:11-20; likelihood.py:188-195); that file keeps the generic kernel (f64, and the f32 rows
+// this kernel declines).  What is different here, and why it still reproduces the reference's numbers:
+//
+//  * Rotational stage (smooth_vsini_fft): the reference's kernel is DEFINED by its FFT construction (analytic
+//    transfer function sampled on the rfft frequencies of the power-of-two log grid: band-limited, 1/j^2 tails),
+//    so it stays an FFT -- but the real transform of n1 samples is one in-place complex transform of M = n1/2
+//    points in (padded) shared memory with radix-16 Stockham passes staged through registers (3 passes for
+//    M/2 = 4096 instead of 5 radix-8 ones, one buffer instead of two), and the last forward radix-2 stage, the
+//    real-spectrum split, the transfer function, the merge and the first inverse radix-2 stage are ONE pass over
+//    index quadruples {k, M/2-k, M/2+k, M-k}.  The first pass reads the native spectrum through the linear
+//    resampling (smoothing.py:587-597) instead of from a resampled copy.
+//  * Instrumental stage (smooth_vel_fft, a Gaussian of sigma = sqrt(sigma_out^2 - sigma_in^2)): the reference's
+//    transfer function exp(-2 pi^2 sigma^2 f^2) is the exact DFT of the periodised sampled Gaussian whenever it has
+//    decayed at the Nyquist frequency, i.e. the circular FFT convolution EQUALS the direct sum with taps
+//    exp(-t^2 / 2 s^2) / (s sqrt(2 pi)), s = sigma / dv in pixels of the resampled grid (Poisson summation;
+//    error exp(-pi^2 s^2 / 2) < 3e-9 for s >= 2; SURVEY.md Appendix A.11 measured 4e-16).  The taps are cut at
+//    5.5 s (tail 4e-8) and the sum is evaluated only at the two grid points that bracket each observed pixel.
+//    Rows with s < 2 or more than MAXTAP taps are not evaluated here: they are appended to a fallback list that
+//    the generic FFT kernel then processes.
+//  * Every resampling position is affine in the pixel index (log-uniform grids, Doppler shift = translation in
+//    ln lambda) and is computed in f64 from the index: no map tables are read.
+#include "spec_args.cuh"
+
+namespace {
+
+#ifndef MS_FAST_FT
+#define MS_FAST_FT 512
+#endif
+#ifndef MS_FAST_MINB
+#define MS_FAST_MINB 1
+#endif
+constexpr int FT = MS_FAST_FT;          // threads per CTA
+constexpr int MAXM = 8192;              // complex transform length limit (n1 <= 16384)
+constexpr int EPT = MAXM / FT;          // complex elements a thread stages per pass: 16
+constexpr int MAXTAP = 96;              // half-width limit of the Gaussian FIR
+
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }    // bank-conflict padding of the complex buffer
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }   // a conj(b)
+template <bool INV> __device__ __forceinline__ float2 mul_mi(float2 a) {       // a * (-i) forward, a * (+i) inverse
+    return INV ? float2{-a.y, a.x} : float2{a.y, -a.x};
+}
+
+// ---- small DFTs in registers, natural order in and out ---------------------------------------
+template <bool INV> __device__ __forceinline__ void dft2(float2 &a, float2 &b) {
+    const float2 s = cadd(a, b), d = csub(a, b);
+    a = s; b = d;
+}
+template <bool INV> __device__ __forceinline__ void dft4(float2 &x0, float2 &x1, float2 &x2, float2 &x3) {
+    const float2 a = cadd(x0, x2), b = csub(x0, x2), c = cadd(x1, x3), d = mul_mi<INV>(csub(x1, x3));
+    x0 = cadd(a, c); x1 = cadd(b, d); x2 = csub(a, c); x3 = csub(b, d);
+}
+// multiply by W8^m (forward: exp(-2 pi i m / 8)), m = 1, 2, 3
+template <bool INV, int m> __device__ __forceinline__ float2 mul_w8(float2 a) {
+    const float r = 0.70710678118654752440f;
+    if (m == 1) return INV ? float2{r * (a.x - a.y), r * (a.x + a.y)} : float2{r * (a.x + a.y), r * (a.y - a.x)};
+    if (m == 2) return mul_mi<INV>(a);
+    return INV ? float2{-r * (a.x + a.y), r * (a.x - a.y)} : float2{r * (a.y - a.x), -r * (a.x + a.y)};
+}
+// multiply by W16^m for the odd m that are not multiples of W8: m = 1, 3 (and 9 = -W16^1, handled by the caller)
+template <bool INV, int m> __device__ __forceinline__ float2 mul_w16(float2 a) {
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;   // cos, sin of pi / 8
+    const float c = (m == 1) ? c1 : s1, s = (m == 1) ? s1 : c1;                 // W16^m = c - i s (forward)
+    return INV ? float2{a.x * c - a.y * s, a.x * s + a.y * c} : float2{a.x * c + a.y * s, a.y * c - a.x * s};
+}
+
+template <int R, bool INV> struct Dft;
+template <bool INV> struct Dft<2, INV> {
+    static __device__ __forceinline__ void run(float2 (&v)[2]) { dft2<INV>(v[0], v[1]); }
+};
+template <bool INV> struct Dft<4, INV> {
+    static __device__ __forceinline__ void run(float2 (&v)[4]) { dft4<INV>(v[0], v[1], v[2], v[3]); }
+};
+template <bool INV> struct Dft<8, INV> {
+    // n = c + 2 n1 (c < 2, n1 < 4), k = q + 4 p:  X[q + 4p] = sum_c W2^(cp) W8^(cq) sum_n1 x[c + 2 n1] W4^(n1 q)
+    static __device__ __forceinline__ void run(float2 (&v)[8]) {
+        dft4<INV>(v[0], v[2], v[4], v[6]);                 // c = 0: q in v[0], v[2], v[4], v[6]
+        dft4<INV>(v[1], v[3], v[5], v[7]);                 // c = 1
+        v[3] = mul_w8<INV, 1>(v[3]); v[5] = mul_w8<INV, 2>(v[5]); v[7] = mul_w8<INV, 3>(v[7]);
+        // radix-2 over c for every q: outputs X[q] and X[q + 4]
+        float2 o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { o[q] = cadd(v[2 * q], v[2 * q + 1]); o[q + 4] = csub(v[2 * q], v[2 * q + 1]); }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = o[i];
+    }
+};
+template <bool INV> struct Dft<16, INV> {
+    // n = c + 4 n1, k = q + 4 p:  X[q + 4p] = sum_c W4^(cp) [ W16^(cq) sum_n1 x[c + 4 n1] W4^(n1 q) ]
+    static __device__ __forceinline__ void run(float2 (&v)[16]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dft4<INV>(v[c], v[c + 4], v[c + 8], v[c + 12]);      // result q at v[c + 4q]
+        // twiddles W16^(cq), c, q in 1..3
+        v[5] = mul_w16<INV, 1>(v[5]);                              // c1 q1: W16^1
+        v[9] = mul_w8<INV, 1>(v[9]);                               // c1 q2: W16^2 = W8^1
+        v[13] = mul_w16<INV, 3>(v[13]);                            // c1 q3: W16^3
+        v[6] = mul_w8<INV, 1>(v[6]);                               // c2 q1: W16^2
+        v[10] = mul_mi<INV>(v[10]);                                // c2 q2: W16^4 = -i
+        v[14] = mul_w8<INV, 3>(v[14]);                             // c2 q3: W16^6 = W8^3
+        v[7] = mul_w16<INV, 3>(v[7]);                              // c3 q1: W16^3
+        v[11] = mul_w8<INV, 3>(v[11]);                             // c3 q2: W16^6
+        { const float2 t = mul_w16<INV, 1>(v[15]); v[15] = {-t.x, -t.y}; }   // c3 q3: W16^9 = -W16^1
+        float2 o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 a = v[4 * q], b = v[4 * q + 1], c = v[4 * q + 2], d = v[4 * q + 3];
+            dft4<INV>(a, b, c, d);                                 // over c -> p
+            o[q] = a; o[q + 4] = b; o[q + 8] = c; o[q + 12] = d;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = o[i];
+    }
+};
+
+// ---- one Stockham pass, in place: every thread reads all its inputs, the CTA synchronises, then writes -------
+// Natural order in, natural order out after the last pass.  Butterfly j (< M / R) reads z[j + r M/R], multiplies
+// by exp(-+2 pi i k r / (Ns R)), k = j mod Ns, transforms, writes z[(j - k) R + k + r Ns].  `twlev` holds the
+// per-level tables: level l at offset 2^(l-1), entry k = exp(-2 pi i k / 2^l), k < 2^(l-1).
+// LOADER: source of the inputs (the shared buffer itself, or the resampled native spectrum for the first pass).
+struct LoadZ {
+    const float2 *z;
+    __device__ __forceinline__ float2 operator()(int m) const { return z[padi(m)]; }
+};
+// Affine resampling position pos(k) = k * ratio (0 < ratio < 4) in 2.30 fixed point: integer part and fraction
+// come out of one 64-bit multiply (rounding of the ratio: < 2^-31 per step, < 1e-5 pixel at k = 16384, i.e.
+// < 1e-6 of the local flux slope -- far below the fp32 tolerance; the f64 mode keeps exact positions).
+struct AffinePos {
+    unsigned long long step;          // round(ratio * 2^30)
+    __device__ __forceinline__ void set(double ratio) { step = (unsigned long long)(ratio * 1073741824.0 + 0.5); }
+    __device__ __forceinline__ int split(int k, float &t) const {
+        const unsigned long long fx = (unsigned long long)(unsigned)k * step;
+        t = (float)(unsigned)(fx & 0x3fffffffu) * (1.f / 1073741824.f);
+        return (int)(fx >> 30);
+    }
+};
+
+struct LoadResampled {            // z[m] = x[2m] + i x[2m+1], x[k] = native spectrum interpolated at k * ratio (linear in lambda)
+    const float *fr; AffinePos ap; float half_d; int last;
+    __device__ __forceinline__ float at(int k) const {
+        float t;
+        int i = ap.split(k, t);
+        if (i > last - 1) { i = last - 1; t = 1.f; }
+        const float f = t * (1.f + (t - 1.f) * half_d);
+        const float a = fr[i], b = fr[i + 1];
+        return a + (b - a) * f;
+    }
+    __device__ __forceinline__ float2 operator()(int m) const { return {at(2 * m), at(2 * m + 1)}; }
+};
+
+template <int R, bool INV, typename LOADER>
+__device__ __noinline__ void fft_pass(float2 *z, int M, int lNs, const float2 *__restrict__ twlev, const LOADER &ld) {
+    constexpr int LR = (R == 16) ? 4 : (R == 8 ? 3 : (R == 4 ? 2 : 1));
+    constexpr int NBT = EPT / R;                          // butterflies per thread when M = MAXM
+    const int nb = M >> LR, Ns = 1 << lNs;
+    float2 v[NBT][R];
+#pragma unroll
+    for (int b = 0; b < NBT; ++b) {
+        const int j = threadIdx.x + b * FT;
+        if (j < nb) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b][r] = ld(j + r * nb);
+            if (lNs > 0) {
+                float2 w1 = twlev[(1 << (lNs + LR - 1)) + (j & (Ns - 1))];
+                if (INV) w1.y = -w1.y;
+                if (R == 2) {
+                    v[b][1] = cmul(v[b][1], w1);
+                } else {
+                    const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                    v[b][1] = cmul(v[b][1], w1); v[b][2] = cmul(v[b][2], w2); v[b][3] = cmul(v[b][3], w3);
+                    if (R >= 8) {
+                        const float2 w4 = cmul(w2, w2), w5 = cmul(w4, w1), w6 = cmul(w3, w3), w7 = cmul(w4, w3);
+                        v[b][4] = cmul(v[b][4], w4); v[b][5] = cmul(v[b][5], w5);
+                        v[b][6] = cmul(v[b][6], w6); v[b][7] = cmul(v[b][7], w7);
+                        if (R == 16) {
+                            const float2 w8 = cmul(w4, w4);
+                            v[b][8] = cmul(v[b][8], w8);
+                            v[b][9] = cmul(v[b][9], cmul(w8, w1));
+                            v[b][10] = cmul(v[b][10], cmul(w5, w5));
+                            v[b][11] = cmul(v[b][11], cmul(w8, w3));
+                            v[b][12] = cmul(v[b][12], cmul(w6, w6));
+                            v[b][13] = cmul(v[b][13], cmul(w8, w5));
+                            v[b][14] = cmul(v[b][14], cmul(w7, w7));
+                            v[b][15] = cmul(v[b][15], cmul(w8, w7));
+                        }
+                    }
+                }
+            }
+            Dft<R, INV>::run(v[b]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NBT; ++b) {
+        const int j = threadIdx.x + b * FT;
+        if (j < nb) {
+            const int k = j & (Ns - 1);
+            const int j0 = ((j >> lNs) << (lNs + LR)) + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) z[padi(j0 + r * Ns)] = v[b][r];
+        }
+    }
+    __syncthreads();
+}
+
+// split / transfer / merge of one conjugate pair of the packed real transform (k, M - k):
+// in: A = Z[k], B = Z[M-k]; u = exp(-2 pi i k / n); tk, tm = transfer(k), transfer(M-k) (1/M folded in)
+__device__ __forceinline__ void real_pair(float2 &A, float2 &B, const float2 u, const float tk, const float tm) {
+    const float2 Bc = {B.x, -B.y};
+    const float2 E = {0.5f * (A.x + Bc.x), 0.5f * (A.y + Bc.y)};
+    const float2 dif = csub(A, Bc);
+    const float2 O = {0.5f * dif.y, -0.5f * dif.x};                   // -i/2 (A - conj B)
+    const float2 wO = cmul(u, O);
+    const float2 Yk = {tk * (E.x + wO.x), tk * (E.y + wO.y)};          // X'[k]
+    const float2 Ym = {tm * (E.x - wO.x), tm * (E.y - wO.y)};          // conj X'[M-k]
+    const float2 Ep = {0.5f * (Yk.x + Ym.x), 0.5f * (Yk.y + Ym.y)};
+    const float2 D = {0.5f * (Yk.x - Ym.x), 0.5f * (Yk.y - Ym.y)};
+    const float2 Op = cmulc(D, u);
+    A = {Ep.x - Op.y, Ep.y + Op.x};                                    // Ep + i Op
+    B = {Ep.x + Op.y, Op.x - Ep.y};                                    // conj(Ep) + i conj(Op)
+}
+
+struct RotTransfer {
+    double coef; const float *tab; float inv;
+    __device__ __forceinline__ float operator()(int k) const {
+        const double u = coef * (double)k;
+        if (!(u == u)) return __int_as_float(0x7fc00000);
+        return inv * rot_transfer_f((float)u, tab);
+    }
+};
+
+// Last forward radix-2 stage (Ns = M/2), real-spectrum split, transfer function, merge, first inverse radix-2
+// stage (Ns = 1) in one in-place pass over the quadruples {k, H-k, H+k, M-k}, H = M/2, 0 <= k <= M/4.
+__device__ __noinline__ void quad_pass(float2 *z, int M, const RotTransfer &tf, const float2 *__restrict__ twlev) {
+    const int H = M >> 1, Q = M >> 2;
+    const float2 *twM = twlev + (M >> 1);          // exp(-2 pi i k / M), k < M/2
+    const float2 *twN = twlev + M;                 // exp(-2 pi i k / (2M)), k < M
+    constexpr int NQ = MAXM / 4 / FT;              // quadruples per thread at M = MAXM: 4
+    float2 o[NQ][4];
+    float2 e0 = {0.f, 0.f}, e1 = {0.f, 0.f}, e2 = {0.f, 0.f}, e3 = {0.f, 0.f};      // thread 0: k = 0 and k = M/4
+#pragma unroll
+    for (int b = 0; b < NQ; ++b) {
+        const int k = threadIdx.x + b * FT;
+        if (k > 0 && k < Q) {
+            const float2 Ya = z[padi(k)], Yc = z[padi(k + H)], Yb = z[padi(H - k)], Yd = z[padi(M - k)];
+            const float2 w = twM[k];
+            const float2 t = cmul(w, Yc);
+            float2 Za = cadd(Ya, t), Zc = csub(Ya, t);                 // Z[k], Z[k + H]
+            const float2 wb = {-w.x, w.y};                             // exp(-2 pi i (H - k) / M) = -conj(w)
+            const float2 t2 = cmul(wb, Yd);
+            float2 Zb = cadd(Yb, t2), Zd = csub(Yb, t2);               // Z[H - k], Z[M - k]
+            const float2 u = twN[k];
+            real_pair(Za, Zd, u, tf(k), tf(M - k));
+            const float2 ub = {-u.y, -u.x};                            // exp(-2 pi i (H - k) / (2M)) = -i conj(u)
+            real_pair(Zb, Zc, ub, tf(H - k), tf(H + k));
+            o[b][0] = cadd(Za, Zc); o[b][1] = csub(Za, Zc);            // out[2k], out[2k + 1]
+            o[b][2] = cadd(Zb, Zd); o[b][3] = csub(Zb, Zd);            // out[M - 2k], out[M - 2k + 1]
+        }
+    }
+    if (threadIdx.x == 0) {
+        {   // k = 0: Z[0] pairs with itself, Z[H] with itself
+            const float2 Y0 = z[0], YH = z[padi(H)];
+            float2 Z0 = cadd(Y0, YH), ZH = csub(Y0, YH);
+            const float y0 = tf(0) * (Z0.x + Z0.y), ym = tf(M) * (Z0.x - Z0.y);
+            Z0 = {0.5f * (y0 + ym), 0.5f * (y0 - ym)};
+            float2 dup = ZH;
+            const float th = tf(H);
+            real_pair(ZH, dup, twN[H], th, th);
+            e0 = cadd(Z0, ZH); e1 = csub(Z0, ZH);                      // out[0], out[1]
+        }
+        if (Q > 0) {   // k = M/4: the pair (Q, 3Q)
+            const float2 Ya = z[padi(Q)], Yc = z[padi(Q + H)];
+            const float2 t = cmul(twM[Q], Yc);
+            float2 Za = cadd(Ya, t), Zc = csub(Ya, t);
+            real_pair(Za, Zc, twN[Q], tf(Q), tf(M - Q));
+            e2 = cadd(Za, Zc); e3 = csub(Za, Zc);                      // out[2Q], out[2Q + 1]
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NQ; ++b) {
+        const int k = threadIdx.x + b * FT;
+        if (k > 0 && k < Q) {
+            z[padi(2 * k)] = o[b][0]; z[padi(2 * k + 1)] = o[b][1];
+            z[padi(M - 2 * k)] = o[b][2]; z[padi(M - 2 * k + 1)] = o[b][3];
+        }
+    }
+    if (threadIdx.x == 0) {
+        z[0] = e0; z[padi(1)] = e1;
+        if (Q > 0) { z[padi(2 * Q)] = e2; z[padi(2 * Q + 1)] = e3; }
+    }
+    __syncthreads();
+}
+
+// y = irfft(rfft(x) * transfer) of the n1 = 2M samples obtained by resampling the native spectrum in `fr`;
+// result left in z as M complex numbers z[m] = y[2m] + i y[2m+1] (padded layout).
+__device__ __noinline__ void rotational_filter(float2 *z, const float *fr, int npix, int n1, double dlnw, double vrot,
+                                  const float *rot_tab, const float2 *__restrict__ twlev) {
+    const int M = n1 >> 1;
+    const int lM = 31 - __clz(M);
+    const int lH = lM - 1;                        // log2(M/2) = 4 a + lL
+    const int lL = lH & 3;                        // leftover radix 2^lL done first (Ns = 1: no twiddles)
+    LoadResampled src;
+    src.fr = fr; src.ap.set((double)(npix - 1) / (double)(n1 - 1)); src.half_d = (float)(0.5 * dlnw); src.last = npix - 1;
+    const LoadZ own{z};
+    int lNs = 0;
+    // ---- forward: [leftover] 16 ... 16, then radix 2 inside quad_pass
+    if (M == 2) {
+        // degenerate: the quad pass alone is the transform; load the two complex samples
+        if (threadIdx.x < 2) z[padi(threadIdx.x)] = src(threadIdx.x);
+        __syncthreads();
+    } else if (lL == 1) { fft_pass<2, false>(z, M, 0, twlev, src); lNs = 1; }
+    else if (lL == 2) { fft_pass<4, false>(z, M, 0, twlev, src); lNs = 2; }
+    else if (lL == 3) { fft_pass<8, false>(z, M, 0, twlev, src); lNs = 3; }
+    else if (lH >= 4) { fft_pass<16, false>(z, M, 0, twlev, src); lNs = 4; }
+    else {          // M/2 == 1 handled above; cannot get here with lL == 0 and lH < 4 unless lH == 0
+        if (threadIdx.x < M) z[padi(threadIdx.x)] = src(threadIdx.x);
+        __syncthreads();
+    }
+    while (lNs < lH) { fft_pass<16, false>(z, M, lNs, twlev, own); lNs += 4; }
+    // ---- last forward stage + split + transfer + merge + first inverse stage
+    const double step1 = (double)(npix - 1) * dlnw / (double)(n1 - 1);
+    RotTransfer tf;
+    tf.tab = rot_tab; tf.inv = 1.f / (float)M;
+    tf.coef = 2.0 * M_PI * sqrt(vrot * vrot) / ((double)n1 * MS_CKMS * step1);
+    quad_pass(z, M, tf, twlev);
+    // ---- inverse: Ns = 2 after the quad pass: [leftover] 16 ... 16
+    lNs = 1;
+    if (lL == 1) { fft_pass<2, true>(z, M, lNs, twlev, own); lNs += 1; }
+    else if (lL == 2) { fft_pass<4, true>(z, M, lNs, twlev, own); lNs += 2; }
+    else if (lL == 3) { fft_pass<8, true>(z, M, lNs, twlev, own); lNs += 3; }
+    while (lNs < lM) { fft_pass<16, true>(z, M, lNs, twlev, own); lNs += 4; }
+}
+
+__device__ __forceinline__ float conv_at(const float2 *z, int k) {          // real sample k of the filtered sequence
+    const float2 c = z[padi(k >> 1)];
+    return (k & 1) ? c.y : c.x;
+}
+
+__global__ void __launch_bounds__(FT, MS_FAST_MINB)
+spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restrict__ fb_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int npix = a.npix, n1 = a.n1, M = n1 >> 1;
+    float2 *z = reinterpret_cast<float2 *>(smem_raw);                        // padded complex buffer
+    float *s2 = reinterpret_cast<float *>(smem_raw);                         // later: the n2-point instrumental grid
+    float *fr = reinterpret_cast<float *>(smem_raw + (size_t)padi(M) * sizeof(float2) + 16);   // native / rotated spectrum
+    __shared__ float gtap[MAXTAP + 2];
+    __shared__ double red[FT / 32];
+    const float2 *twlev = static_cast<const float2 *>(a.twlev);
+
+    for (int p = blockIdx.x; p < nB; p += gridDim.x) {
+        const double *r = a.pars + (size_t)p * MS_NPARS;
+        int slot = a.star_slot ? a.star_slot[p] : a.slot0;
+        const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
+        const StarView sv = a.stars[slot_ok ? slot : 0];
+        const int nobs = slot_ok ? sv.n_obs : 0;
+        if (r[PV_TEFF] == ms_inf() || nobs <= 0) {                           // failed interpolation / no spectrum: uniform
+            if (a.flux_out && slot_ok)
+                for (int j = threadIdx.x; j < nobs; j += FT) a.flux_out[(size_t)p * nobs + j] = ms_nan();
+            if (a.chi2 && !slot_ok && threadIdx.x == 0 && r[PV_TEFF] != ms_inf()) a.chi2[p] = ms_nan();
+            continue;
+        }
+        const double vrad = r[PV_VRAD], vrot = r[PV_VROT];
+        const double inst = 2.355 * r[PV_INSTR];                             // genmod.py:74-75
+        const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
+        // ---- decide the instrumental stage first: rows this kernel declines cost nothing
+        int mode;             // 0: Gaussian FIR on the n2 grid; 1: plain interpolation; 2: all NaN; 3: fallback
+        int i_s = 0, i_e = npix - 1, n2 = 0, ntap = 0;
+        double d2 = 0.0, ratio2 = 0.0, spx = 0.0;
+        if (inst != 0.0) {
+            if (!(inst == inst) || !(scale == scale)) mode = 2;
+            else {
+                mask_window(a.wave, npix, a.lnw0, a.dlnw, scale, sv.wmin * (1.0 - 20.0 / inst), sv.wmax * (1.0 + 20.0 / inst),
+                            i_s, i_e);
+                const int nmask = i_e - i_s + 1;
+                const double so = MS_CKMS / inst, si = MS_CKMS / a.resolution;
+                const double sigma = sqrt(so * so - si * si);                // NaN when sharper than the net
+                if (nmask < 4) mode = 2;
+                else if (sigma <= 0.0) mode = 1;
+                else if (!(sigma == sigma)) mode = 3;                        // NaN kernel: let the generic kernel propagate it
+                else {
+                    n2 = 1; while (n2 < nmask) n2 <<= 1;
+                    ratio2 = (double)(i_e - i_s) / (double)(n2 - 1);
+                    d2 = ratio2 * a.dlnw;
+                    spx = sigma / (MS_CKMS * d2);                            // kernel width in pixels of the n2 grid
+                    ntap = (int)ceil(5.5 * spx);
+                    mode = (spx >= 2.0 && ntap <= MAXTAP && 2 * ntap + 2 < n2) ? 0 : 3;
+                }
+            }
+        } else {
+            mode = 1;
+        }
+        if (mode == 3) {
+            if (threadIdx.x == 0) fb_rows[atomicAdd(fb_count, 1)] = p;
+            continue;
+        }
+        // ---- native spectrum -> shared memory
+        const float *frow = static_cast<const float *>(a.flux_native) + (size_t)p * npix;
+        if ((npix & 3) == 0) {
+            const float4 *src4 = reinterpret_cast<const float4 *>(frow);
+            float4 *dst4 = reinterpret_cast<float4 *>(fr);
+            for (int i = threadIdx.x; i < (npix >> 2); i += FT) dst4[i] = __ldcs(src4 + i);
+        } else {
+            for (int i = threadIdx.x; i < npix; i += FT) fr[i] = __ldcs(frow + i);
+        }
+        if (mode == 0 && threadIdx.x <= ntap) {                               // Gaussian taps, t = 0 .. ntap
+            const double t = (double)threadIdx.x / spx;
+            gtap[threadIdx.x] = (float)(exp(-0.5 * t * t) / (spx * 2.5066282746310002));
+        }
+        __syncthreads();
+
+        // ---- rotational broadening on the full native grid (outwave = None), back onto the native pixels
+        if (vrot != 0.0) {
+            rotational_filter(z, fr, npix, n1, a.dlnw, vrot, a.rot_tab, twlev);
+            // smoothing.py:262: interpolation of the filtered n1 grid at the native wavelengths
+            AffinePos ap;
+            ap.set((double)(n1 - 1) / (double)(npix - 1));
+            const float half_s = (float)(0.5 * (double)(npix - 1) * a.dlnw / (double)(n1 - 1));
+            for (int i = threadIdx.x; i < npix; i += FT) {
+                float t;
+                int k = ap.split(i, t);
+                if (k > n1 - 2) { k = n1 - 2; t = 1.f; }
+                const float f = t * (1.f + (t - 1.f) * half_s);
+                const float v0 = conv_at(z, k), v1 = conv_at(z, k + 1);
+                fr[i] = v0 + (v1 - v0) * f;
+            }
+            __syncthreads();
+        }
+
+        // ---- Doppler shift + instrumental broadening + resampling to the observed pixels
+        const double lnscale = log(scale);
+        if (mode == 0) {
+            const float half_d = (float)(0.5 * a.dlnw);
+            AffinePos ap;
+            ap.set(ratio2);
+            const float *fs = fr + i_s;
+            const int last = i_e - i_s;
+            for (int k = threadIdx.x; k < n2; k += FT) {
+                float t;
+                int i = ap.split(k, t);
+                if (i > last - 1) { i = last - 1; t = 1.f; }
+                const float f = t * (1.f + (t - 1.f) * half_d);               // linear in lambda, not ln(lambda)
+                s2[k] = fs[i] + (fs[i + 1] - fs[i]) * f;
+            }
+            __syncthreads();
+        }
+        double csum = 0.0;
+        const double lnw_s = a.lnw0 + (double)i_s * a.dlnw;
+        const int mask2 = n2 - 1;
+        for (int j = threadIdx.x; j < nobs; j += FT) {
+            const double lx = sv.obs_lnwave[j] - lnscale;
+            double m;
+            if (mode == 0) {
+                const double q = (lx - lnw_s) / d2;
+                int i; double f;
+                if (q <= 0.0) { i = 0; f = 0.0; }
+                else if (q >= (double)(n2 - 1)) { i = n2 - 2; f = 1.0; }
+                else {
+                    i = (int)q;
+                    const double t = q - (double)i;
+                    f = t * (1.0 + (t - 1.0) * 0.5 * d2);
+                }
+                // conv[i] and conv[i + 1] of the circular Gaussian convolution, sharing the samples
+                float a0 = 0.f, a1 = 0.f;
+                const int base = i - ntap;
+                float x = s2[base & mask2];
+                for (int s = 0; s <= 2 * ntap; ++s) {
+                    const int t = ntap - s;
+                    const float g = gtap[t < 0 ? -t : t];
+                    a0 = fmaf(g, x, a0);                                      // sample i - t
+                    x = s2[(base + s + 1) & mask2];
+                    a1 = fmaf(g, x, a1);                                      // sample i + 1 - t
+                }
+                m = (double)a0 + ((double)a1 - (double)a0) * f;
+            } else if (mode == 1) {
+                const double q = (lx - a.lnw0) / a.dlnw;
+                const double qlo = (double)i_s, qhi = (double)i_e;
+                if (q < qlo || q > qhi) {
+                    // smoothing branch clamps (np.interp default); plain branch returns NaN outside
+                    m = (inst != 0.0) ? (double)fr[q < qlo ? i_s : i_e] : ms_nan();
+                } else {
+                    int i = (int)q;
+                    if (i > i_e - 1) i = i_e - 1;
+                    const double t = q - (double)i;
+                    const double f = t * (1.0 + (t - 1.0) * 0.5 * a.dlnw);
+                    const double v0 = (double)fr[i], v1 = (double)fr[i + 1];
+                    m = v0 + (v1 - v0) * f;
+                }
+            } else {
+                m = ms_nan();
+            }
+            if (a.modpoly) m *= cheb_eval(sv.cheb_x[j], r + PV_PC0, a.n_pc);  // genmod.py:90-93
+            if (a.flux_out) a.flux_out[(size_t)p * nobs + j] = m;
+            if (a.chi2) {
+                const double d = m - sv.obs_flux[j];
+                const double t = (d * d) / sv.obs_err2[j];
+                if (t == t) csum += t;                                        // nansum (likelihood.py:193)
+            }
+        }
+        if (a.chi2) {
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = csum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < FT / 32; ++w) tot += red[w];
+                a.chi2[p] += tot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+size_t fast_smem_bytes(int npix, int n1) {
+    const int M = n1 >> 1;
+    return (size_t)(M + (M >> 4)) * sizeof(float2) + 16 + (size_t)npix * sizeof(float) + 16;
+}
+
+}  // namespace
+
+bool spec_fast_usable(const ms_ctx *ctx) {
+    const SpecNetDev &n = ctx->spec;
+    return ctx->precision != MS_PREC_F64 && n.n1 >= 8 && (n.n1 >> 1) <= MAXM &&
+           fast_smem_bytes(n.npix, n.n1) <= 226 * 1024;
+}
+
+// Rows the kernel declines are appended to fb_rows / *fb_count (device; the caller zeroes the counter).
+int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, int *fb_rows, int *fb_count, cudaStream_t st) {
+    const size_t smem = fast_smem_bytes(sa.npix, sa.n1);
+    static size_t configured = 0;
+    if (configured < smem) {
+        MS_CUDA(cudaFuncSetAttribute(spec_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int per_sm = (MS_FAST_MINB >= 2 && 2 * (smem + 1024 + 2048) <= 227 * 1024) ? 2 : 1;
+    int grid = ctx->sm_count * per_sm;
+    if (grid > nB) grid = nB;
+    spec_fast_kernel<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}

@@ -100,6 +100,10 @@ template <typename T>
 int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux,
                      const double *d_xmin_scale, cudaStream_t st) {
     const SpecNetDev &n = ctx->spec;
+    if constexpr (std::is_same<T, float>::value) {
+        if (ctx->precision >= MS_PREC_TC)          // all three layers on the tensor-core path (spec_mlp_tc.cu)
+            return launch_spec_mlp_tc(ctx, pars, B, flux, st);
+    }
     KernelTimer timer_(ctx, MS_K_SPEC_MLP, st);
     T *xs = hid, *h1 = hid + (size_t)B * n.d_in, *h2 = h1 + (size_t)B * n.h;
     int blocks = (int)((B + 255) / 256);
@@ -109,10 +113,6 @@ int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux
     int rc;
     if ((rc = gemm<T>(ctx, xs, n.w0, n.b0, h1, (int)B, n.h, n.d_in, n.leak, st))) return rc;
     if ((rc = gemm<T>(ctx, h1, n.w1, n.b1, h2, (int)B, n.h, n.h, n.leak, st))) return rc;
-    if constexpr (std::is_same<T, float>::value) {
-        if (ctx->precision >= MS_PREC_TC)          // output layer on the tensor cores (spec_mlp_tc.cu)
-            return launch_spec_out_tc(ctx, h2, B, flux, st);
-    }
     if ((rc = gemm<T>(ctx, h2, n.w2, n.b2, flux, (int)B, n.npix, n.h, -1.0, st))) return rc;
     return MS_OK;
 }

@@ -1,20 +1,24 @@
-// Kernel (2b), tensor-core form (MS_PREC_TC): the output layer of the spectral MLP,
-// flux[B][P] = h2[B][H] . W2[P][H]^T + b2 -- 97 % of the spectral network's flops -- as a
-// persistent tcgen05 GEMM.  Same contract as the last gemm of spec_mlp.cu
-// (PayneSpecPredict.predictspec, external Payne, PARITY UNPINNED; call site genmod.py:80-84).
+// Kernel (2b), tensor-core form (MS_PREC_TC): the spectral MLP d_in -> H -> H -> P of
+// PayneSpecPredict.predictspec (external Payne, PARITY UNPINNED; call site genmod.py:80-84) as
+//   (i)   layer 0 (K = d_in <= 5) on CUDA cores, written straight into the fp16 hi/lo operand image of
+//   (ii)  layer 1 (H x H) as a tcgen05 GEMM whose epilogue (bias, leaky ReLU, fp16 hi/lo split) writes
+//         the operand image of
+//   (iii) the output layer flux[B][P] = h2[B][H] . W2[P][H]^T + b2 -- 97 % of the network's flops -- as the
+//         same persistent tcgen05 GEMM with an f32 epilogue.
+// No f32 hidden activations and no separate packing pass exist between the layers.
 //
 // Numerics as in phot_mlp_tc.cu: both operands are split into fp16 hi + lo and every product
-// is three kind::f16 MMAs (hi.hi + lo.hi + hi.lo) accumulated in fp32.  W2 is pre-scaled by a
+// is three kind::f16 MMAs (hi.hi + lo.hi + hi.lo) accumulated in fp32.  Weights are pre-scaled by a
 // power of two so that small weights stay in the fp16 normal range; the epilogue undoes it.
 //
-// Tiling: 128 points x 128 pixels per tile, K streamed in chunks of 64 through a 3-stage
+// Tiling: 128 points x 128 columns per tile, K streamed in chunks of 64 through a 3-stage
 // shared-memory ring filled by bulk async copies (A and B images are stored tile-major in
 // global memory in the UMMA K-major core-matrix layout, so a stage is two plain 32 KB
 // copies); two 128-column TMEM accumulators so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Warp 0 = producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers
 // -> + bias -> global).  Tiles are ordered m-fastest so concurrently running CTAs share the
-// same W2 tile through L2.  L2 -> shared operand traffic (64 KB per 64-wide K chunk) is what
-// bounds this kernel, not the tensor pipe.
+// same weight tile through L2.  L2 -> shared operand traffic (64 KB per 64-wide K chunk) is what
+// bounds the output-layer GEMM, not the tensor pipe.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -33,8 +37,13 @@ constexpr uint32_t IDESC = make_idesc_f16(BM, BN);
 
 enum { BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_ACC_FULL = 2 * STAGES, BAR_ACC_EMPTY = 2 * STAGES + 2 };
 
-// h2[B][H] f32 -> A image [m_tile][k_chunk][hi|lo][k8][row][8] fp16 (zero padded)
-__global__ void pack_a_kernel(const float *__restrict__ h2, int64_t B, int H, int nkc, __half *__restrict__ img) {
+// Layer 0 + operand packing: h1 = lrelu(W0 x + b0) for the scaled labels x of every point, written as the
+// A image [m_tile][k_chunk][hi|lo][k8][row][8] (fp16, zero padded in rows >= B and k >= H) of the layer-1 GEMM.
+// One thread per (row, group of 8 hidden units).
+__global__ void spec_l0_pack_kernel(const double *__restrict__ pars, int64_t B, int d_in, int logt,
+                                    const double *__restrict__ xms /*[16]: xmin | xscale*/,
+                                    const float *__restrict__ w0, const float *__restrict__ b0, int H, float leak,
+                                    int nkc, __half *__restrict__ img) {
     const int64_t ntask = (int64_t)((B + BM - 1) / BM) * BM * nkc * (BK / 8);
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ntask; t += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(t % BM);
@@ -44,9 +53,22 @@ __global__ void pack_a_kernel(const float *__restrict__ h2, int64_t B, int H, in
         const int64_t row = mt * BM + r;
         const int k0 = kc * BK + k8 * 8;
         __half hi[8], lo[8];
+        float xs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        bool live = row < B;
+        if (live) {
+            const double *q = pars + row * MS_NPARS;
+            live = q[PV_TEFF] != ms_inf();
+            const double lab[5] = {logt ? log10(q[PV_TEFF]) : q[PV_TEFF], q[PV_LOGG], q[PV_FEH], q[PV_AFE], q[PV_VMIC]};
+            for (int d = 0; d < d_in; ++d) xs[d] = live ? (float)((lab[d] - xms[d]) * xms[8 + d] - 0.5) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float v = (row < B && k0 + i < H) ? h2[row * H + k0 + i] : 0.f;
+            float v = 0.f;
+            if (row < B && k0 + i < H) {
+                v = b0[k0 + i];
+                for (int d = 0; d < d_in; ++d) v = fmaf(xs[d], w0[(k0 + i) * d_in + d], v);
+                v = v > 0.f ? v : leak * v;
+            }
             hi[i] = __float2half_rn(v);
             lo[i] = __float2half_rn(v - __half2float(hi[i]));
         }
@@ -60,14 +82,19 @@ struct GemmArgs {
     const unsigned char *a_img;      // [m_tiles][nkc][2][OPER_BYTES]
     const unsigned char *b_img;      // [n_tiles][nkc][2][OPER_BYTES]
     const float *bias;
-    float *out;                      // [B][P]
+    float *out;                      // PACK = false: [B][P] f32
+    unsigned char *out_img;          // PACK = true: operand image of the next layer, [m_tiles][nkc_out][2][OPER_BYTES]
     int64_t B;
-    int P, nkc, m_tiles, n_tiles;
-    float inv_scale;
+    int P, nkc, m_tiles, n_tiles;    // P = valid output columns
+    int nkc_out;
+    float inv_scale, leak;
 };
 
+// PACK = false: out = acc * inv_scale + bias (f32 rows).  PACK = true: hidden layer: leaky ReLU, then the fp16
+// hi / lo operand image of the next GEMM (a thread owns one point = one row of a core-matrix column block).
+template <bool PACK>
 __global__ void __launch_bounds__(NTHREADS, 1)
-spec_out_gemm_tc_kernel(GemmArgs a) {
+spec_gemm_tc_kernel(GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,7 +177,30 @@ spec_out_gemm_tc_kernel(GemmArgs a) {
                 TMEM_LD32(tmem + lane_base + buf * BN + 32 * j, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 const int col0 = nt * BN + 32 * j;
-                if (row < a.B) {
+                if constexpr (PACK) {
+                    // columns of this layer = K of the next: 8 consecutive ones are one 16-byte core-matrix row
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const int n0 = col0 + 8 * g8;
+                        const int kc_o = n0 / BK;
+                        if (kc_o >= a.nkc_out) continue;
+                        __half hi[8], lo[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float x = 0.f;
+                            if (n0 + i < a.P && row < a.B) {
+                                x = fmaf(__uint_as_float(v[8 * g8 + i]), a.inv_scale, __ldg(a.bias + n0 + i));
+                                x = x > 0.f ? x : a.leak * x;
+                            }
+                            hi[i] = __float2half_rn(x);
+                            lo[i] = __float2half_rn(x - __half2float(hi[i]));
+                        }
+                        unsigned char *dst = a.out_img + (((size_t)mt * a.nkc_out + kc_o) * 2) * OPER_BYTES +
+                                             (size_t)((n0 % BK) / 8) * 2048 + (size_t)(q * 32 + lane) * 16;
+                        *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                        *reinterpret_cast<uint4 *>(dst + OPER_BYTES) = *reinterpret_cast<const uint4 *>(lo);
+                    }
+                } else if (row < a.B) {
                     float *o = a.out + row * a.P + col0;
                     if (col0 + 32 <= a.P) {
 #pragma unroll
@@ -181,86 +231,121 @@ spec_out_gemm_tc_kernel(GemmArgs a) {
 
 }  // namespace
 
-struct SpecTcPack {
+struct TcLayer {                      // packed weights of one GEMM layer
     unsigned char *b_img = nullptr;
-    int nkc = 0, n_tiles = 0;
+    int nkc = 0, n_tiles = 0, N = 0;
     float inv_scale = 1.f;
-    __half *a_img = nullptr; size_t a_img_bytes = 0;
+};
+struct SpecTcPack {
+    TcLayer l1, l2;
+    unsigned char *a1_img = nullptr, *a2_img = nullptr;     // operand images of layer 1 and of the output layer
+    size_t a_img_rows = 0;                                   // rows (multiple of BM) both images hold
 };
 
-int spec_tc_prepare(ms_ctx *ctx) {
-    SpecNetDev &S = ctx->spec;
-    const int H = S.h, P = S.npix;
-    if (P % 4 != 0) { ms_set_error("MS_PREC_TC needs a pixel count that is a multiple of 4"); return MS_EINVAL; }
-    std::vector<float> w2((size_t)P * H);
-    MS_CUDA(cudaMemcpy(w2.data(), S.w2, w2.size() * 4, cudaMemcpyDeviceToHost));
+// W[N][K] f32 (device) -> B image [n_tile][k_chunk][hi|lo][k8][row][8], scaled by a power of two
+static int pack_weights(const float *w_dev, int N, int K, TcLayer *L) {
+    std::vector<float> w((size_t)N * K);
+    MS_CUDA(cudaMemcpy(w.data(), w_dev, w.size() * 4, cudaMemcpyDeviceToHost));
     float wmax = 0.f;
-    for (float v : w2) wmax = std::fabs(v) > wmax ? std::fabs(v) : wmax;
+    for (float v : w) wmax = std::fabs(v) > wmax ? std::fabs(v) : wmax;
     int e = 0;
     if (wmax > 0.f) { std::frexp(wmax, &e); }
     const int shift = 14 - e;                               // max |w| * 2^shift in [2^13, 2^14)
     const double scale = std::ldexp(1.0, shift);
-    SpecTcPack *pk = new SpecTcPack();
-    pk->nkc = (H + BK - 1) / BK;
-    pk->n_tiles = (P + BN - 1) / BN;
-    pk->inv_scale = (float)std::ldexp(1.0, -shift);
-    const size_t bytes = (size_t)pk->n_tiles * pk->nkc * 2 * OPER_BYTES;
+    L->N = N;
+    L->nkc = (K + BK - 1) / BK;
+    L->n_tiles = (N + BN - 1) / BN;
+    L->inv_scale = (float)std::ldexp(1.0, -shift);
+    const size_t bytes = (size_t)L->n_tiles * L->nkc * 2 * OPER_BYTES;
     std::vector<__half> img(bytes / 2, __float2half_rn(0.f));
-    for (int n = 0; n < P; ++n)
-        for (int k = 0; k < H; ++k) {
-            const double v = scale * (double)w2[(size_t)n * H + k];
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            const double v = scale * (double)w[(size_t)n * K + k];
             const __half hi = __float2half_rn((float)v);
             const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
-            const size_t at = (((size_t)(n / BN) * pk->nkc + k / BK) * 2) * (OPER_BYTES / 2) +
+            const size_t at = (((size_t)(n / BN) * L->nkc + k / BK) * 2) * (OPER_BYTES / 2) +
                               (size_t)((k % BK) / 8) * 1024 + (size_t)(n % BN) * 8 + (k % 8);
             img[at] = hi;
             img[at + OPER_BYTES / 2] = lo;
         }
+    MS_CUDA(cudaMalloc((void **)&L->b_img, bytes));
+    MS_CUDA(cudaMemcpy(L->b_img, img.data(), bytes, cudaMemcpyHostToDevice));
+    return MS_OK;
+}
+
+int spec_tc_prepare(ms_ctx *ctx) {
+    SpecNetDev &S = ctx->spec;
+    if (S.npix % 4 != 0) { ms_set_error("MS_PREC_TC needs a pixel count that is a multiple of 4"); return MS_EINVAL; }
+    SpecTcPack *pk = new SpecTcPack();
     S.tc_pack = pk;                                        // owned by the ctx from here: ms_destroy releases it on any error
-    MS_CUDA(cudaMalloc((void **)&pk->b_img, bytes));
-    MS_CUDA(cudaMemcpy(pk->b_img, img.data(), bytes, cudaMemcpyHostToDevice));
-    MS_CUDA(cudaFuncSetAttribute(spec_out_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    int rc;
+    if ((rc = pack_weights(S.w1, S.h, S.h, &pk->l1))) return rc;
+    if ((rc = pack_weights(S.w2, S.npix, S.h, &pk->l2))) return rc;
+    MS_CUDA(cudaFuncSetAttribute(spec_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
+    MS_CUDA(cudaFuncSetAttribute(spec_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     return MS_OK;
 }
 
 void spec_tc_release(ms_ctx *ctx) {
     SpecTcPack *pk = static_cast<SpecTcPack *>(ctx->spec.tc_pack);
     if (!pk) return;
-    cudaFree(pk->b_img); cudaFree(pk->a_img);
+    cudaFree(pk->l1.b_img); cudaFree(pk->l2.b_img); cudaFree(pk->a1_img); cudaFree(pk->a2_img);
     delete pk;
     ctx->spec.tc_pack = nullptr;
 }
 
-// flux[B][P] (f32) from h2[B][H] (f32) on the tensor cores
-int launch_spec_out_tc(ms_ctx *ctx, const float *h2, int64_t B, float *flux, cudaStream_t st) {
+// operand-image scratch for chunks of up to `chunk` points
+int spec_tc_reserve(ms_ctx *ctx, int64_t chunk) {
+    SpecTcPack *pk = static_cast<SpecTcPack *>(ctx->spec.tc_pack);
+    if (!pk) { ms_set_error("spectral net not packed for MS_PREC_TC"); return MS_ESTATE; }
+    const size_t rows = (size_t)((chunk + BM - 1) / BM) * BM;
+    if (pk->a_img_rows >= rows) return MS_OK;
+    if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
+    cudaFree(pk->a1_img); cudaFree(pk->a2_img);
+    pk->a1_img = pk->a2_img = nullptr; pk->a_img_rows = 0;
+    MS_CUDA(cudaMalloc((void **)&pk->a1_img, rows / BM * pk->l1.nkc * 2 * OPER_BYTES));
+    MS_CUDA(cudaMalloc((void **)&pk->a2_img, rows / BM * pk->l2.nkc * 2 * OPER_BYTES));
+    pk->a_img_rows = rows;
+    return MS_OK;
+}
+
+// native flux[B][P] (f32) of a chunk of points from their parameter block: the three layers on one stream
+int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, cudaStream_t st) {
     SpecNetDev &S = ctx->spec;
     SpecTcPack *pk = static_cast<SpecTcPack *>(S.tc_pack);
     if (!pk) { ms_set_error("spectral net not packed for MS_PREC_TC"); return MS_ESTATE; }
+    int rc;
+    if ((rc = spec_tc_reserve(ctx, B))) return rc;
     const int m_tiles = (int)((B + BM - 1) / BM);
-    const size_t need = (size_t)m_tiles * pk->nkc * 2 * OPER_BYTES;
-    if (pk->a_img_bytes < need) {
-        if (pk->a_img) cudaFree(pk->a_img);
-        pk->a_img = nullptr; pk->a_img_bytes = 0;
-        MS_CUDA(cudaMalloc((void **)&pk->a_img, need));
-        pk->a_img_bytes = need;
-    }
     KernelTimer timer_(ctx, MS_K_SPEC_MLP, st);
     {
-        const int64_t ntask = (int64_t)m_tiles * BM * pk->nkc * (BK / 8);
+        const int64_t ntask = (int64_t)m_tiles * BM * pk->l1.nkc * (BK / 8);
         int blocks = (int)((ntask + 255) / 256);
         if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-        pack_a_kernel<<<blocks, 256, 0, st>>>(h2, B, S.h, pk->nkc, pk->a_img);
+        spec_l0_pack_kernel<<<blocks, 256, 0, st>>>(pars, B, S.d_in, S.logt_input, S.xms, S.w0, S.b0, S.h, (float)S.leak,
+                                                    pk->l1.nkc, reinterpret_cast<__half *>(pk->a1_img));
         ctx->launches++;
         MS_CUDA(cudaGetLastError());
     }
     GemmArgs ga;
-    ga.a_img = reinterpret_cast<const unsigned char *>(pk->a_img);
-    ga.b_img = pk->b_img; ga.bias = S.b2; ga.out = flux; ga.B = B; ga.P = S.npix;
-    ga.nkc = pk->nkc; ga.m_tiles = m_tiles; ga.n_tiles = pk->n_tiles; ga.inv_scale = pk->inv_scale;
-    const int ntiles = m_tiles * pk->n_tiles;
-    const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
-    spec_out_gemm_tc_kernel<<<grid, NTHREADS, SM_TOTAL, st>>>(ga);
-    ctx->launches++;
-    MS_CUDA(cudaGetLastError());
+    ga.B = B; ga.m_tiles = m_tiles; ga.leak = (float)S.leak;
+    // layer 1: H -> H, epilogue packs the operand image of the output layer
+    ga.a_img = pk->a1_img; ga.b_img = pk->l1.b_img; ga.bias = S.b1; ga.out = nullptr; ga.out_img = pk->a2_img;
+    ga.P = S.h; ga.nkc = pk->l1.nkc; ga.n_tiles = pk->l1.n_tiles; ga.nkc_out = pk->l2.nkc; ga.inv_scale = pk->l1.inv_scale;
+    {
+        const int ntiles = m_tiles * ga.n_tiles;
+        spec_gemm_tc_kernel<true><<<ntiles < ctx->sm_count ? ntiles : ctx->sm_count, NTHREADS, SM_TOTAL, st>>>(ga);
+        ctx->launches++;
+        MS_CUDA(cudaGetLastError());
+    }
+    // output layer
+    ga.a_img = pk->a2_img; ga.b_img = pk->l2.b_img; ga.bias = S.b2; ga.out = flux; ga.out_img = nullptr;
+    ga.P = S.npix; ga.nkc = pk->l2.nkc; ga.n_tiles = pk->l2.n_tiles; ga.nkc_out = 0; ga.inv_scale = pk->l2.inv_scale;
+    {
+        const int ntiles = m_tiles * ga.n_tiles;
+        spec_gemm_tc_kernel<false><<<ntiles < ctx->sm_count ? ntiles : ctx->sm_count, NTHREADS, SM_TOTAL, st>>>(ga);
+        ctx->launches++;
+        MS_CUDA(cudaGetLastError());
+    }
     return MS_OK;
 }

@@ -20,12 +20,8 @@
 // log-uniform and a Doppler shift is a translation in ln(lambda), every
 // resampling position is an affine function of the pixel index; no per-pixel
 // logarithm or exponential is evaluated.
-#include "common.cuh"
+#include "spec_args.cuh"
 
-#define MS_CKMS 2.998e5            // smoothing.py:14
-#define MS_C_KMS 299792.458        // Payne's Doppler shift (scipy.constants.c / 1000)
-#define MS_ROT_TAB_H (1.0 / 32.0)  // spacing of the rotational-transfer table
-#define MS_ROT_TAB_N 8200
 // one CTA per SM; 32 warps in f32 (64 registers), 16 in f64 (the f64 kernel needs > 64 registers)
 template <typename T> struct SmoothCfg { static constexpr int THREADS = sizeof(T) == 4 ? 1024 : 512; };
 
@@ -56,26 +52,6 @@ __device__ __forceinline__ int ld_stream(const int *p) {
     int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 
-struct SmoothArgs {
-    const double *pars;            // [B][MS_NPARS] (already offset to the chunk)
-    const void *flux_native;       // [B][npix] T
-    int npix, n1;
-    double lnw0, dlnw, resolution;
-    const double *wave;            // native wavelengths
-    const int *a1_idx, *a2_idx;
-    const void *a1_frac, *a2_frac; // T
-    const void *twiddle;           // T2 [n1/2]: exp(-2 pi i k / n1)
-    const void *twlev;             // float2 per-level compact tables (Stockham path)
-    const float *rot_tab;          // S(u) on a uniform grid (float mode)
-    // star
-    int n_obs;
-    const double *obs_wave, *obs_lnwave, *obs_flux, *obs_err2, *cheb_x;
-    double ow_min, ow_max;
-    int modpoly, n_pc;
-    double *flux_out;              // [B][n_obs] or nullptr
-    double *chi2;                  // [B] or nullptr
-};
-
 // Transfer function of the rotational profile, smoothing.py:541-548.
 __device__ __forceinline__ double rot_transfer(double u) {
     if (u == 0.0) return 1.0;
@@ -84,28 +60,6 @@ __device__ __forceinline__ double rot_transfer(double u) {
     const double u2 = u * u;
     return j1(u) / u - 3.0 * c / (2.0 * u2) + 3.0 * s / (2.0 * u2 * u);
 }
-__device__ __forceinline__ float rot_transfer_f(float u, const float *__restrict__ tab) {
-    const float x = u * (float)(1.0 / MS_ROT_TAB_H);
-    int i = (int)x;
-    if (i >= 1 && i < MS_ROT_TAB_N - 3) {          // 4-point Lagrange on the uniform table
-        const float t = x - (float)i;
-        const float p0 = __ldg(tab + i - 1), p1 = __ldg(tab + i), p2 = __ldg(tab + i + 1), p3 = __ldg(tab + i + 2);
-        const float c0 = -t * (t - 1.f) * (t - 2.f) * (1.f / 6.f);
-        const float c1 = (t + 1.f) * (t - 1.f) * (t - 2.f) * 0.5f;
-        const float c2 = -(t + 1.f) * t * (t - 2.f) * 0.5f;
-        const float c3 = (t + 1.f) * t * (t - 1.f) * (1.f / 6.f);
-        return c0 * p0 + c1 * p1 + c2 * p2 + c3 * p3;
-    }
-    if (i < 1) {                                    // series about 0: 1 - u^2/10 + u^4/280
-        const float u2 = u * u;
-        return 1.f - u2 * 0.1f + u2 * u2 * (1.f / 280.f);
-    }
-    float s, c;
-    sincosf(u, &s, &c);
-    const float u2 = u * u;
-    return j1f(u) / u - 3.f * c / (2.f * u2) + 3.f * s / (2.f * u2 * u);
-}
-
 template <typename T> struct Transfer {
     int kind;            // 0 gaussian, 1 rotation
     double coef;         // gaussian: 2 pi^2 sigma^2 / (n dv)^2 ; rotation: 2 pi vsini / (n dv)
@@ -389,20 +343,6 @@ __device__ void fft_filter_stockham(typename Cx<T>::type *z0, typename Cx<T>::ty
     stockham_fft<T, true>(z0, z1, where, M, L, tw, tw_n);     // same number of passes -> ends in z0
 }
 
-// numpy.polynomial.chebyshev.chebval recurrence (Clenshaw), n coefficients
-__device__ __forceinline__ double cheb_eval(double x, const double *c, int n) {
-    if (n == 1) return c[0];
-    if (n == 2) return c[0] + c[1] * x;
-    const double x2 = 2.0 * x;
-    double c0 = c[n - 2], c1 = c[n - 1];
-    for (int i = 3; i <= n; ++i) {
-        const double tmp = c0;
-        c0 = c[n - i] - c1;
-        c1 = tmp + c1 * x2;
-    }
-    return c0 + c1 * x;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(SmoothCfg<T>::THREADS, 1)
 spec_smooth_kernel(SmoothArgs a, int nB) {
@@ -416,15 +356,23 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
     __shared__ double red[32];
     const T *a1f = static_cast<const T *>(a.a1_frac), *a2f = static_cast<const T *>(a.a2_frac);
     const T2 *tw = static_cast<const T2 *>(a.twiddle);
-    const int npix = a.npix, n1 = a.n1, nobs = a.n_obs;
+    const int npix = a.npix, n1 = a.n1;
+    // all rows of the chunk, or (fallback launch behind the fast kernel) the listed ones
+    const int nrows = a.rows ? *a.nrows : nB;
 
-    for (int p = blockIdx.x; p < nB; p += gridDim.x) {
+    for (int pi = blockIdx.x; pi < nrows; pi += gridDim.x) {
+        const int p = a.rows ? a.rows[pi] : pi;
         const double *r = a.pars + (size_t)p * MS_NPARS;
+        const int slot = a.star_slot ? a.star_slot[p] : a.slot0;
+        const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
+        const StarView sv = a.stars[slot_ok ? slot : 0];
+        const int nobs = slot_ok ? sv.n_obs : 0;
         const bool ok = r[PV_TEFF] != ms_inf();
-        if (!ok) {                                            // uniform across the CTA
-            if (a.flux_out)
+        if (!ok || nobs <= 0) {                               // uniform across the CTA
+            if (a.flux_out && slot_ok)
                 for (int j = threadIdx.x; j < nobs; j += blockDim.x)
                     a.flux_out[(size_t)p * nobs + j] = ms_nan();
+            if (a.chi2 && ok && !slot_ok && threadIdx.x == 0) a.chi2[p] = ms_nan();   // slot outside the table
             continue;
         }
         const double vrad = r[PV_VRAD], vrot = r[PV_VROT];
@@ -486,7 +434,7 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
         int i_s = 0, i_e = npix - 1, n2 = 0;
         double d2 = 0.0;
         if (inst != 0.0) {
-            const double lo = a.ow_min * (1.0 - 20.0 / inst), hi = a.ow_max * (1.0 + 20.0 / inst);
+            const double lo = sv.wmin * (1.0 - 20.0 / inst), hi = sv.wmax * (1.0 + 20.0 / inst);
             int l = 0, h = npix;                              // first i with wave[i]*scale > lo
             while (l < h) { int m = (l + h) >> 1; if (a.wave[m] * scale > lo) h = m; else l = m + 1; }
             i_s = l;
@@ -526,7 +474,7 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
         double csum = 0.0;
         const double lnw_s = a.lnw0 + (double)i_s * a.dlnw;
         for (int j = threadIdx.x; j < nobs; j += blockDim.x) {
-            const double lx = a.obs_lnwave[j] - lnscale;
+            const double lx = sv.obs_lnwave[j] - lnscale;
             double m;
             if (mode == 0) {
                 const double q = (lx - lnw_s) / d2;
@@ -556,11 +504,11 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
             } else {
                 m = ms_nan();
             }
-            if (a.modpoly) m *= cheb_eval(a.cheb_x[j], r + PV_PC0, a.n_pc);   // genmod.py:90-93
+            if (a.modpoly) m *= cheb_eval(sv.cheb_x[j], r + PV_PC0, a.n_pc);   // genmod.py:90-93
             if (a.flux_out) a.flux_out[(size_t)p * nobs + j] = m;
             if (a.chi2) {
-                const double d = m - a.obs_flux[j];
-                const double t = (d * d) / a.obs_err2[j];
+                const double d = m - sv.obs_flux[j];
+                const double t = (d * d) / sv.obs_err2[j];
                 if (t == t) csum += t;                        // nansum (likelihood.py:193)
             }
         }
@@ -584,9 +532,18 @@ template <typename T>
 int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux,
                      const double *d_xmin_scale, cudaStream_t st);
 
-// chunk of points whose native flux is materialised between the MLP and the smoother:
-// L2-sized for the CUDA-core GEMM, whole waves of 128x128 tiles for the tensor-core GEMM
-static int64_t spec_chunk(const ms_ctx *ctx) { return (ctx->precision >= MS_PREC_TC) ? 8192 : 1024; }
+// Chunk of points whose native flux sits between the MLP and the smoother.  Sized so that the chunk's flux
+// (chunk x npix x 4 B) stays resident in the 126 MB L2: the GEMM's stores and the smoother's loads then never
+// reach HBM (11 row tiles of 128 points x 80 pixel tiles = 880 tiles = 5.95 waves of 148 CTAs at npix = 10240).
+// f64 (validation mode): small chunks, CUDA-core GEMM.
+static int64_t spec_chunk(const ms_ctx *ctx) {
+    if (ctx->precision == MS_PREC_F64) return 1024;
+    const int64_t by_l2 = (int64_t)(60u << 20) / ((int64_t)ctx->spec.npix * 4);      // <= 60 MB of flux in flight
+    int64_t c = (by_l2 / 128) * 128;
+    if (c > 8192) c = 8192;
+    if (c < 128) c = 128;
+    return c;
+}
 
 int spec_reserve(ms_ctx *ctx, int64_t max_batch) {
     const SpecNetDev &n = ctx->spec;
@@ -595,40 +552,50 @@ int spec_reserve(ms_ctx *ctx, int64_t max_batch) {
     if (max_batch < chunk) chunk = max_batch;
     const size_t flux_bytes = (size_t)chunk * n.npix * esz;
     const size_t hid_bytes = (size_t)chunk * (n.d_in + 2 * n.h) * esz;
-    if (ctx->scr_flux_bytes < flux_bytes) {
+    const size_t fb_bytes = ((size_t)chunk + 4) * sizeof(int);
+    auto grow = [&](void **p, size_t *have, size_t need) -> int {
+        if (*have >= need) return MS_OK;
         if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
-        if (ctx->scr_flux) cudaFree(ctx->scr_flux);
-        ctx->scr_flux = nullptr; ctx->scr_flux_bytes = 0;
-        MS_CUDA(cudaMalloc(&ctx->scr_flux, flux_bytes));
-        ctx->scr_flux_bytes = flux_bytes;
-    }
-    if (ctx->scr_hid_bytes < hid_bytes) {
-        if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
-        if (ctx->scr_hid) cudaFree(ctx->scr_hid);
-        ctx->scr_hid = nullptr; ctx->scr_hid_bytes = 0;
-        MS_CUDA(cudaMalloc(&ctx->scr_hid, hid_bytes));
-        ctx->scr_hid_bytes = hid_bytes;
-    }
+        if (*p) cudaFree(*p);
+        *p = nullptr; *have = 0;
+        MS_CUDA(cudaMalloc(p, need));
+        *have = need;
+        return MS_OK;
+    };
+    int rc;
+    if ((rc = grow(&ctx->scr_flux, &ctx->scr_flux_bytes, flux_bytes))) return rc;
+    if ((rc = grow(&ctx->scr_hid, &ctx->scr_hid_bytes, hid_bytes))) return rc;
+    if ((rc = grow((void **)&ctx->scr_fb, &ctx->scr_fb_bytes, fb_bytes))) return rc;
+    if (ctx->precision >= MS_PREC_TC && (rc = spec_tc_reserve(ctx, chunk))) return rc;
     return MS_OK;
 }
 
 template <typename T>
 static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) {
     const SpecNetDev &n = ctx->spec;
-    const StarDev &star = ctx->stars[a.star_slot];
     const int64_t chunk = spec_chunk(ctx);
     {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        const bool capturing = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+        const int64_t need = B < chunk ? B : chunk;
+        const size_t esz = sizeof(T);
+        if (capturing && (ctx->scr_flux_bytes < (size_t)need * n.npix * esz || !ctx->scr_fb)) {
+            ms_set_error("spectrum scratch would be allocated during stream capture: call ms_reserve first");
+            return MS_ESTATE;
+        }
         int rc = spec_reserve(ctx, B);
         if (rc) return rc;
     }
     const size_t smem = (size_t)((sizeof(T) == 4 ? 2 : 1) * n.n1 + n.npix) * sizeof(T);
-    if (smem > 226 * 1024) {
+    const bool generic_fits = smem <= 226 * 1024;
+    const bool fast = sizeof(T) == 4 && ctx->spec_fast && spec_fast_usable(ctx);
+    if (!generic_fits && !fast) {
         ms_set_error("spectral net with %d pixels does not fit the shared-memory smoother", n.npix);
         return MS_EINVAL;
     }
     auto kern = spec_smooth_kernel<T>;
-    MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per_sm = 1;
+    if (generic_fits) MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int *fb_count = ctx->scr_fb, *fb_rows = ctx->scr_fb + 4;
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
         int rc = spec_mlp_chunk_t<T>(ctx, a.pars + b0 * MS_NPARS, nb, (T *)ctx->scr_hid,
@@ -642,16 +609,24 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         if (sizeof(T) == 4) { sa.a1_frac = n.a1_frac; sa.a2_frac = n.a2_frac; sa.twiddle = n.twiddle32; }
         else { sa.a1_frac = n.a1_fracd; sa.a2_frac = n.a2_fracd; sa.twiddle = n.twiddle64; }
         sa.rot_tab = n.rot_tab; sa.twlev = n.twlev32;
-        sa.n_obs = star.n_obs; sa.obs_wave = star.obs_wave; sa.obs_lnwave = star.obs_lnwave;
-        sa.obs_flux = star.obs_flux; sa.obs_err2 = star.obs_err2; sa.cheb_x = star.cheb_x;
-        sa.ow_min = star.wmin; sa.ow_max = star.wmax;
+        sa.stars = ctx->stars_dev; sa.nstars = ctx->stars_dev_n;
+        sa.star_slot = a.star_slots ? a.star_slots + b0 : nullptr; sa.slot0 = a.star_slot;
         sa.modpoly = a.modpoly; sa.n_pc = a.n_pc;
-        sa.flux_out = a.flux ? a.flux + b0 * star.n_obs : nullptr;
+        sa.flux_out = a.flux ? a.flux + b0 * ctx->stars[a.star_slot].n_obs : nullptr;
         sa.chi2 = a.chi2 ? a.chi2 + b0 : nullptr;
-        int64_t grid = (int64_t)ctx->sm_count * per_sm;
-        if (grid > nb) grid = nb;
-        {
-            KernelTimer timer_(ctx, MS_K_SPEC_SMOOTH, st);
+        sa.rows = nullptr; sa.nrows = nullptr;
+        KernelTimer timer_(ctx, MS_K_SPEC_SMOOTH, st);
+        if (fast) {
+            // fast kernel; rows it declines (unusual broadening widths) go through the generic FFT kernel
+            MS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
+            if ((rc = launch_spec_fast(ctx, sa, (int)nb, fb_rows, fb_count, st))) return rc;
+            if (!generic_fits) continue;
+            sa.rows = fb_rows; sa.nrows = fb_count;
+            const int64_t grid = nb < ctx->sm_count ? nb : ctx->sm_count;
+            kern<<<(unsigned)grid, SmoothCfg<T>::THREADS, smem, st>>>(sa, (int)nb);
+        } else {
+            int64_t grid = (int64_t)ctx->sm_count;
+            if (grid > nb) grid = nb;
             kern<<<(unsigned)grid, SmoothCfg<T>::THREADS, smem, st>>>(sa, (int)nb);
         }
         ctx->launches++;
@@ -662,11 +637,15 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
 
 int launch_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) {
     if (!ctx->spec.w0) { ms_set_error("spectral net not configured"); return MS_ESTATE; }
-    if (a.star_slot < 0 || a.star_slot >= (int)ctx->stars.size() || !ctx->stars[a.star_slot].set ||
-        ctx->stars[a.star_slot].n_obs <= 0) {
-        ms_set_error("star slot %d has no observed spectrum", a.star_slot);
-        return MS_ESTATE;
+    if (!a.star_slots || a.flux) {
+        if (a.star_slot < 0 || a.star_slot >= (int)ctx->stars.size() || !ctx->stars[a.star_slot].set ||
+            ctx->stars[a.star_slot].n_obs <= 0) {
+            ms_set_error("star slot %d has no observed spectrum", a.star_slot);
+            return MS_ESTATE;
+        }
     }
+    if (a.star_slots && a.flux) { ms_set_error("model spectra with per-row star slots are ragged: not supported"); return MS_EINVAL; }
+    if (!ctx->stars_dev) { ms_set_error("no star observations set"); return MS_ESTATE; }
     if (a.modpoly && (a.n_pc < 1 || a.n_pc > MS_MAX_PC)) { ms_set_error("n_pc out of range"); return MS_EINVAL; }
     if (B <= 0) return MS_OK;
     if (ctx->precision == MS_PREC_F64) return run_spec<double>(ctx, a, B, st);

@@ -271,6 +271,10 @@ class Engine(object):
         interpolation kernel followed by the MLP kernel."""
         check(self.lib.ms_set_fusion(self._ctx, int(bool(on))))
 
+    def set_spec_fast(self, on=True):
+        """f32-class modes: fast broadening kernel (default) or the generic FFT kernel for every row."""
+        check(self.lib.ms_set_spec_fast(self._ctx, int(bool(on))))
+
     def profile(self, on=True):
         check(self.lib.ms_profile_enable(self._ctx, int(on)))
 
