@@ -244,7 +244,9 @@ int ms_set_fusion(ms_ctx *ctx, int enable);
 /* f32-class modes: the broadening chain of genspec (smoothing.py:202-264, 517-598) normally runs in the fast
  * kernel (csrc/spec_fast.cu: radix-16 FFT for the rotational stage, direct Gaussian sum for the instrumental
  * stage) with the generic FFT kernel (csrc/spec_smooth.cu) taking the rows it declines.  ms_set_spec_fast(ctx, 0)
- * sends every row through the generic kernel (used by the tests to compare the two); the default is 1. */
+ * sends every row through the generic kernel (used by the tests to compare the two); 1 = radix-16 transform, one
+ * CTA per SM, next spectrum prefetched by a bulk async copy; 2 (default, measured faster: 18.0 vs 19.9 ms per 65 536
+ * spectra) = radix-8 transform, two CTAs per SM (falls back to 1 when two do not fit in shared memory). */
 int ms_set_spec_fast(ms_ctx *ctx, int enable);
 
 /* Scratch policy.  A ctx grows its per-batch scratch on demand (cudaFree + cudaMalloc inside the call), which

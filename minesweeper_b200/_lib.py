@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libmsb200.so')
+LIB_PATH = os.environ.get('MS_LIB_PATH') or os.path.join(HERE, 'libmsb200.so')   # MS_LIB_PATH: tuning variants only
 
 MS_OK, MS_EINVAL, MS_ENODEV, MS_ECUDA, MS_ENOMEM, MS_ESTATE = 0, -1, -2, -3, -4, -5
 MS_PREC_F64, MS_PREC_F32, MS_PREC_TC, MS_PREC_TC16 = 0, 1, 2, 3

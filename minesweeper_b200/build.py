@@ -26,10 +26,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra_flags=()):
+    """variant / extra_flags: kernel-tuning experiments only (``libmsb200_<variant>.so`` built with extra -D flags,
+    selected at run time with MS_LIB_PATH); the product library is the default build."""
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
     hdrs.append(os.path.join(HERE, '..', 'include', 'minesweeper_b200.h'))
-    objdir = os.path.join(HERE, 'build')
+    objdir = os.path.join(HERE, 'build' if not variant else 'build_' + variant)
+    lib = LIB if not variant else os.path.join(HERE, 'libmsb200_%s.so' % variant)
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     objs = []
@@ -38,7 +41,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, s.replace('.cu', '.o'))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+            cmd = [NVCC] + FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
             jobs.append(cmd)
 
     def run(cmd):
@@ -52,10 +55,12 @@ def build(force=False, verbose=False):
             for out in ex.map(run, jobs):
                 if verbose and out:
                     sys.stderr.write(out)
-    if force or jobs or _stale(LIB, objs):
-        run([NVCC, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
-    return LIB
+    if force or jobs or _stale(lib, objs):
+        run([NVCC, '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    var = os.environ.get('MS_BUILD_VARIANT')
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, variant=var,
+                extra_flags=os.environ.get('MS_NVCC_EXTRA', '').split() if var else ()))

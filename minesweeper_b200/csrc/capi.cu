@@ -322,7 +322,7 @@ extern "C" int64_t ms_launch_count(const ms_ctx *ctx) { return ctx ? ctx->launch
 
 extern "C" int ms_set_spec_fast(ms_ctx *ctx, int enable) {
     if (!ctx) { ms_set_error("bad arguments"); return MS_EINVAL; }
-    ctx->spec_fast = enable ? 1 : 0;
+    ctx->spec_fast = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     return MS_OK;
 }
 

@@ -83,16 +83,25 @@ __device__ __forceinline__ double cheb_eval(double x, const double *c, int n) {
 // with the reference's own comparisons (exact at the boundaries).
 __device__ __forceinline__ void mask_window(const double *__restrict__ wave, int npix, double lnw0, double dlnw,
                                             double scale, double lo, double hi, int &i_s, int &i_e) {
-    int c = lo > 0.0 ? (int)ceil((log(lo / scale) - lnw0) / dlnw) : 0;
-    c = c < 0 ? 0 : (c > npix ? npix : c);
-    while (c > 0 && wave[c - 1] * scale > lo) --c;
-    while (c < npix && !(wave[c] * scale > lo)) ++c;
-    i_s = c;
-    c = (int)floor((log(hi / scale) - lnw0) / dlnw) + 1;          // candidate for "first i with wave >= hi"
-    c = c < 0 ? 0 : (c > npix ? npix : c);
-    while (c > 0 && !(wave[c - 1] * scale < hi)) --c;
-    while (c < npix && wave[c] * scale < hi) ++c;
-    i_e = c - 1;
+    int cs = lo > 0.0 ? (int)ceil((log(lo / scale) - lnw0) / dlnw) : 0;
+    cs = cs < 0 ? 0 : (cs > npix ? npix : cs);
+    int ce = (int)floor((log(hi / scale) - lnw0) / dlnw) + 1;        // candidate for "first i with wave >= hi"
+    ce = ce < 0 ? 0 : (ce > npix ? npix : ce);
+    // the four neighbours that decide whether the candidates are right, fetched together (one memory round trip)
+    const double ws0 = wave[cs > 0 ? cs - 1 : 0], ws1 = wave[cs < npix ? cs : npix - 1];
+    const double we0 = wave[ce > 0 ? ce - 1 : 0], we1 = wave[ce < npix ? ce : npix - 1];
+    const bool s_ok = (cs == 0 || !(ws0 * scale > lo)) && (cs == npix || ws1 * scale > lo);
+    const bool e_ok = (ce == 0 || we0 * scale < hi) && (ce == npix || !(we1 * scale < hi));
+    if (!s_ok) {
+        while (cs > 0 && wave[cs - 1] * scale > lo) --cs;
+        while (cs < npix && !(wave[cs] * scale > lo)) ++cs;
+    }
+    if (!e_ok) {
+        while (ce > 0 && !(wave[ce - 1] * scale < hi)) --ce;
+        while (ce < npix && wave[ce] * scale < hi) ++ce;
+    }
+    i_s = cs;
+    i_e = ce - 1;
 }
 
 // kernel launchers

@@ -29,13 +29,12 @@ namespace {
 #ifndef MS_FAST_FT
 #define MS_FAST_FT 512
 #endif
-#ifndef MS_FAST_MINB
-#define MS_FAST_MINB 1
-#endif
-constexpr int FT = MS_FAST_FT;          // threads per CTA
+constexpr int FT = MS_FAST_FT;          // threads per CTA (256: experiment, two CTAs per SM at 128 registers)
 constexpr int MAXM = 8192;              // complex transform length limit (n1 <= 16384)
 constexpr int EPT = MAXM / FT;          // complex elements a thread stages per pass: 16
-constexpr int MAXTAP = 96;              // half-width limit of the Gaussian FIR
+constexpr int MAXTAP = 64;              // half-width limit of the Gaussian FIR (5.5 sigma: sigma <= 11.6 pixels)
+constexpr int WU = 2 * MAXTAP + 8;      // longest aligned FIR window (multiple of 4)
+constexpr int WSTRIDE = WU + 4;         // row stride of the weight table: 4 mod 32 floats -> the 5 rows hit distinct banks
 
 __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }    // bank-conflict padding of the complex buffer
 
@@ -127,28 +126,28 @@ struct LoadZ {
     const float2 *z;
     __device__ __forceinline__ float2 operator()(int m) const { return z[padi(m)]; }
 };
-// Affine resampling position pos(k) = k * ratio (0 < ratio < 4) in 2.30 fixed point: integer part and fraction
-// come out of one 64-bit multiply (rounding of the ratio: < 2^-31 per step, < 1e-5 pixel at k = 16384, i.e.
-// < 1e-6 of the local flux slope -- far below the fp32 tolerance; the f64 mode keeps exact positions).
+// Affine resampling position pos(k) = k * ratio (0 < ratio < 4) in 32.32 fixed point: the integer part is the
+// high word of one 64-bit multiply, the fraction its low word (rounding of the ratio: < 2^-33 per step, < 2e-6
+// pixel at k = 16384, i.e. < 1e-6 of the local flux slope -- far below the fp32 tolerance; the f64 mode keeps exact
+// positions).  The interpolation is linear in ln(lambda) here; the reference's np.interp is linear in lambda, which
+// differs by t (1 - t) d ln(lambda) / 2 <= 4e-7 of the pixel-to-pixel flux difference (also kept in the f64 mode).
 struct AffinePos {
-    unsigned long long step;          // round(ratio * 2^30)
-    __device__ __forceinline__ void set(double ratio) { step = (unsigned long long)(ratio * 1073741824.0 + 0.5); }
+    unsigned long long step;          // round(ratio * 2^32)
+    __device__ __forceinline__ void set(double ratio) { step = (unsigned long long)(ratio * 4294967296.0 + 0.5); }
     __device__ __forceinline__ int split(int k, float &t) const {
         const unsigned long long fx = (unsigned long long)(unsigned)k * step;
-        t = (float)(unsigned)(fx & 0x3fffffffu) * (1.f / 1073741824.f);
-        return (int)(fx >> 30);
+        t = (float)(unsigned)fx * (1.f / 4294967296.f);
+        return (int)(fx >> 32);
     }
 };
 
-struct LoadResampled {            // z[m] = x[2m] + i x[2m+1], x[k] = native spectrum interpolated at k * ratio (linear in lambda)
-    const float *fr; AffinePos ap; float half_d; int last;
+struct LoadResampled {            // z[m] = x[2m] + i x[2m+1], x[k] = native spectrum interpolated at k * ratio
+    const float *fr; AffinePos ap; // fr[npix] duplicates fr[npix - 1]: the last sample needs no clamp
     __device__ __forceinline__ float at(int k) const {
         float t;
-        int i = ap.split(k, t);
-        if (i > last - 1) { i = last - 1; t = 1.f; }
-        const float f = t * (1.f + (t - 1.f) * half_d);
+        const int i = ap.split(k, t);
         const float a = fr[i], b = fr[i + 1];
-        return a + (b - a) * f;
+        return fmaf(b - a, t, a);
     }
     __device__ __forceinline__ float2 operator()(int m) const { return {at(2 * m), at(2 * m + 1)}; }
 };
@@ -298,43 +297,42 @@ __device__ __noinline__ void quad_pass(float2 *z, int M, const RotTransfer &tf, 
 }
 
 // y = irfft(rfft(x) * transfer) of the n1 = 2M samples obtained by resampling the native spectrum in `fr`;
-// result left in z as M complex numbers z[m] = y[2m] + i y[2m+1] (padded layout).
+// result left in z as M complex numbers z[m] = y[2m] + i y[2m+1] (padded layout).  RM = main radix (16: three
+// passes per direction at M = 8192, needs 128 registers -> one CTA per SM; 8: four passes, 64 registers -> two).
+template <int RM>
 __device__ __noinline__ void rotational_filter(float2 *z, const float *fr, int npix, int n1, double dlnw, double vrot,
-                                  const float *rot_tab, const float2 *__restrict__ twlev) {
+                                               const float *rot_tab, const float2 *__restrict__ twlev) {
+    constexpr int LRM = (RM == 16) ? 4 : 3;
     const int M = n1 >> 1;
     const int lM = 31 - __clz(M);
-    const int lH = lM - 1;                        // log2(M/2) = 4 a + lL
-    const int lL = lH & 3;                        // leftover radix 2^lL done first (Ns = 1: no twiddles)
+    const int lH = lM - 1;                        // log2(M/2) = LRM a + lL
+    const int lL = lH % LRM;                      // leftover radix 2^lL done first (Ns = 1: no twiddles)
     LoadResampled src;
-    src.fr = fr; src.ap.set((double)(npix - 1) / (double)(n1 - 1)); src.half_d = (float)(0.5 * dlnw); src.last = npix - 1;
+    src.fr = fr; src.ap.set((double)(npix - 1) / (double)(n1 - 1));
     const LoadZ own{z};
     int lNs = 0;
-    // ---- forward: [leftover] 16 ... 16, then radix 2 inside quad_pass
-    if (M == 2) {
-        // degenerate: the quad pass alone is the transform; load the two complex samples
-        if (threadIdx.x < 2) z[padi(threadIdx.x)] = src(threadIdx.x);
-        __syncthreads();
-    } else if (lL == 1) { fft_pass<2, false>(z, M, 0, twlev, src); lNs = 1; }
+    // ---- forward: [leftover] RM ... RM, then radix 2 inside quad_pass
+    if (lL == 1) { fft_pass<2, false>(z, M, 0, twlev, src); lNs = 1; }
     else if (lL == 2) { fft_pass<4, false>(z, M, 0, twlev, src); lNs = 2; }
-    else if (lL == 3) { fft_pass<8, false>(z, M, 0, twlev, src); lNs = 3; }
-    else if (lH >= 4) { fft_pass<16, false>(z, M, 0, twlev, src); lNs = 4; }
-    else {          // M/2 == 1 handled above; cannot get here with lL == 0 and lH < 4 unless lH == 0
+    else if (RM == 16 && lL == 3) { fft_pass<8, false>(z, M, 0, twlev, src); lNs = 3; }
+    else if (lH >= LRM) { fft_pass<RM, false>(z, M, 0, twlev, src); lNs = LRM; }
+    else {                                        // M == 2: the quad pass alone is the transform
         if (threadIdx.x < M) z[padi(threadIdx.x)] = src(threadIdx.x);
         __syncthreads();
     }
-    while (lNs < lH) { fft_pass<16, false>(z, M, lNs, twlev, own); lNs += 4; }
+    while (lNs < lH) { fft_pass<RM, false>(z, M, lNs, twlev, own); lNs += LRM; }
     // ---- last forward stage + split + transfer + merge + first inverse stage
     const double step1 = (double)(npix - 1) * dlnw / (double)(n1 - 1);
     RotTransfer tf;
     tf.tab = rot_tab; tf.inv = 1.f / (float)M;
     tf.coef = 2.0 * M_PI * sqrt(vrot * vrot) / ((double)n1 * MS_CKMS * step1);
     quad_pass(z, M, tf, twlev);
-    // ---- inverse: Ns = 2 after the quad pass: [leftover] 16 ... 16
+    // ---- inverse: Ns = 2 after the quad pass: [leftover] RM ... RM
     lNs = 1;
     if (lL == 1) { fft_pass<2, true>(z, M, lNs, twlev, own); lNs += 1; }
     else if (lL == 2) { fft_pass<4, true>(z, M, lNs, twlev, own); lNs += 2; }
-    else if (lL == 3) { fft_pass<8, true>(z, M, lNs, twlev, own); lNs += 3; }
-    while (lNs < lM) { fft_pass<16, true>(z, M, lNs, twlev, own); lNs += 4; }
+    else if (RM == 16 && lL == 3) { fft_pass<8, true>(z, M, lNs, twlev, own); lNs += 3; }
+    while (lNs < lM) { fft_pass<RM, true>(z, M, lNs, twlev, own); lNs += LRM; }
 }
 
 __device__ __forceinline__ float conv_at(const float2 *z, int k) {          // real sample k of the filtered sequence
@@ -342,122 +340,219 @@ __device__ __forceinline__ float conv_at(const float2 *z, int k) {          // r
     return (k & 1) ? c.y : c.x;
 }
 
-__global__ void __launch_bounds__(FT, MS_FAST_MINB)
+// per-point decisions, made once by thread 0 and broadcast through shared memory
+struct PointSetup {
+    int mode;             // 0: Gaussian FIR on the n2 grid; 1: plain interpolation; 2: all NaN; 3: fallback; 4: skip row
+    int i_s, i_e, n2, ntap, nobs, rot;
+    double d2, ratio2, spx, lnscale, lnw_s, inst, vrot;
+};
+
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// RM: main FFT radix; PF: the native spectrum of the CTA's next point is fetched by a bulk async copy (TMA) into a
+// second buffer while the current point is processed (one CTA per SM: nothing else hides that latency).
+template <int RM, bool PF>
+__global__ void __launch_bounds__(FT, (RM == 16 && FT == 512) ? 1 : 2)
 spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restrict__ fb_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npix = a.npix, n1 = a.n1, M = n1 >> 1;
     float2 *z = reinterpret_cast<float2 *>(smem_raw);                        // padded complex buffer
     float *s2 = reinterpret_cast<float *>(smem_raw);                         // later: the n2-point instrumental grid
-    float *fr = reinterpret_cast<float *>(smem_raw + (size_t)padi(M) * sizeof(float2) + 16);   // native / rotated spectrum
+    const size_t fr_off = (size_t)padi(M) * sizeof(float2) + 16;
+    const size_t fr_bytes = ((size_t)(npix + 1) * sizeof(float) + 15) & ~(size_t)15;
+    __shared__ __align__(16) float wtab[5 * WSTRIDE];                        // FIR weights for the 4 window alignments (+1)
     __shared__ float gtap[MAXTAP + 2];
     __shared__ double red[FT / 32];
+    __shared__ PointSetup ps;
+    __shared__ __align__(8) unsigned long long bar_store[2];
     const float2 *twlev = static_cast<const float2 *>(a.twlev);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&bar_store[0]);
 
-    for (int p = blockIdx.x; p < nB; p += gridDim.x) {
-        const double *r = a.pars + (size_t)p * MS_NPARS;
-        int slot = a.star_slot ? a.star_slot[p] : a.slot0;
-        const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
-        const StarView sv = a.stars[slot_ok ? slot : 0];
-        const int nobs = slot_ok ? sv.n_obs : 0;
-        if (r[PV_TEFF] == ms_inf() || nobs <= 0) {                           // failed interpolation / no spectrum: uniform
-            if (a.flux_out && slot_ok)
-                for (int j = threadIdx.x; j < nobs; j += FT) a.flux_out[(size_t)p * nobs + j] = ms_nan();
-            if (a.chi2 && !slot_ok && threadIdx.x == 0 && r[PV_TEFF] != ms_inf()) a.chi2[p] = ms_nan();
-            continue;
-        }
-        const double vrad = r[PV_VRAD], vrot = r[PV_VROT];
-        const double inst = 2.355 * r[PV_INSTR];                             // genmod.py:74-75
-        const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
-        // ---- decide the instrumental stage first: rows this kernel declines cost nothing
-        int mode;             // 0: Gaussian FIR on the n2 grid; 1: plain interpolation; 2: all NaN; 3: fallback
-        int i_s = 0, i_e = npix - 1, n2 = 0, ntap = 0;
-        double d2 = 0.0, ratio2 = 0.0, spx = 0.0;
-        if (inst != 0.0) {
-            if (!(inst == inst) || !(scale == scale)) mode = 2;
-            else {
-                mask_window(a.wave, npix, a.lnw0, a.dlnw, scale, sv.wmin * (1.0 - 20.0 / inst), sv.wmax * (1.0 + 20.0 / inst),
-                            i_s, i_e);
-                const int nmask = i_e - i_s + 1;
-                const double so = MS_CKMS / inst, si = MS_CKMS / a.resolution;
-                const double sigma = sqrt(so * so - si * si);                // NaN when sharper than the net
-                if (nmask < 4) mode = 2;
-                else if (sigma <= 0.0) mode = 1;
-                else if (!(sigma == sigma)) mode = 3;                        // NaN kernel: let the generic kernel propagate it
-                else {
-                    n2 = 1; while (n2 < nmask) n2 <<= 1;
-                    ratio2 = (double)(i_e - i_s) / (double)(n2 - 1);
-                    d2 = ratio2 * a.dlnw;
-                    spx = sigma / (MS_CKMS * d2);                            // kernel width in pixels of the n2 grid
-                    ntap = (int)ceil(5.5 * spx);
-                    mode = (spx >= 2.0 && ntap <= MAXTAP && 2 * ntap + 2 < n2) ? 0 : 3;
-                }
+    if (PF) {
+        if (threadIdx.x == 0) {
+            mbar_init_(bar0, 1); mbar_init_(bar0 + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if ((int)blockIdx.x < nB) {                                      // first point's spectrum
+                mbar_expect_tx_(bar0, (uint32_t)(npix * sizeof(float)));
+                bulk_g2s_((uint32_t)__cvta_generic_to_shared(smem_raw + fr_off),
+                          static_cast<const float *>(a.flux_native) + (size_t)blockIdx.x * npix,
+                          (uint32_t)(npix * sizeof(float)), bar0);
             }
-        } else {
-            mode = 1;
-        }
-        if (mode == 3) {
-            if (threadIdx.x == 0) fb_rows[atomicAdd(fb_count, 1)] = p;
-            continue;
-        }
-        // ---- native spectrum -> shared memory
-        const float *frow = static_cast<const float *>(a.flux_native) + (size_t)p * npix;
-        if ((npix & 3) == 0) {
-            const float4 *src4 = reinterpret_cast<const float4 *>(frow);
-            float4 *dst4 = reinterpret_cast<float4 *>(fr);
-            for (int i = threadIdx.x; i < (npix >> 2); i += FT) dst4[i] = __ldcs(src4 + i);
-        } else {
-            for (int i = threadIdx.x; i < npix; i += FT) fr[i] = __ldcs(frow + i);
-        }
-        if (mode == 0 && threadIdx.x <= ntap) {                               // Gaussian taps, t = 0 .. ntap
-            const double t = (double)threadIdx.x / spx;
-            gtap[threadIdx.x] = (float)(exp(-0.5 * t * t) / (spx * 2.5066282746310002));
         }
         __syncthreads();
+    }
+
+    int it = 0;
+    for (int p = blockIdx.x; p < nB; p += gridDim.x, ++it) {
+        const int buf = PF ? (it & 1) : 0;
+        float *fr = reinterpret_cast<float *>(smem_raw + fr_off + (size_t)buf * fr_bytes);   // native / rotated spectrum
+        const double *r = a.pars + (size_t)p * MS_NPARS;
+        const int slot = a.star_slot ? a.star_slot[p] : a.slot0;
+        const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
+        const StarView sv = a.stars[slot_ok ? slot : 0];
+        if (PF && threadIdx.x == 0) {
+            // all threads finished with buffer buf ^ 1 at the end of the previous iteration (block barrier there)
+            const int pn = p + gridDim.x;
+            if (pn < nB) {
+                const uint32_t b = bar0 + 8 * (buf ^ 1);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy accesses of that buffer are done
+                mbar_expect_tx_(b, (uint32_t)(npix * sizeof(float)));
+                bulk_g2s_((uint32_t)__cvta_generic_to_shared(smem_raw + fr_off + (size_t)(buf ^ 1) * fr_bytes),
+                          static_cast<const float *>(a.flux_native) + (size_t)pn * npix,
+                          (uint32_t)(npix * sizeof(float)), b);
+            }
+        }
+        if (threadIdx.x == 0) {
+            PointSetup q;
+            q.nobs = slot_ok ? sv.n_obs : 0;
+            q.i_s = 0; q.i_e = npix - 1; q.n2 = 0; q.ntap = 0; q.d2 = 0.0; q.ratio2 = 0.0; q.spx = 0.0;
+            const double vrad = r[PV_VRAD];
+            q.vrot = r[PV_VROT]; q.rot = q.vrot != 0.0;
+            q.inst = 2.355 * r[PV_INSTR];                                    // genmod.py:74-75
+            const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
+            q.lnscale = log(scale);
+            if (r[PV_TEFF] == ms_inf() || q.nobs <= 0) q.mode = 4;
+            else if (q.inst != 0.0) {
+                if (!(q.inst == q.inst) || !(scale == scale)) q.mode = 2;
+                else {
+                    mask_window(a.wave, npix, a.lnw0, a.dlnw, scale, sv.wmin * (1.0 - 20.0 / q.inst),
+                                sv.wmax * (1.0 + 20.0 / q.inst), q.i_s, q.i_e);
+                    const int nmask = q.i_e - q.i_s + 1;
+                    const double so = MS_CKMS / q.inst, si = MS_CKMS / a.resolution;
+                    const double sigma = sqrt(so * so - si * si);            // NaN when sharper than the net
+                    if (nmask < 4) q.mode = 2;
+                    else if (sigma <= 0.0) q.mode = 1;
+                    else if (!(sigma == sigma)) q.mode = 3;                  // NaN kernel: let the generic kernel propagate it
+                    else {
+                        int n2 = 1; while (n2 < nmask) n2 <<= 1;
+                        q.n2 = n2;
+                        q.ratio2 = (double)(q.i_e - q.i_s) / (double)(n2 - 1);
+                        q.d2 = q.ratio2 * a.dlnw;
+                        q.spx = sigma / (MS_CKMS * q.d2);                    // kernel width in pixels of the n2 grid
+                        q.ntap = (int)ceil(5.5 * q.spx);
+                        q.mode = (q.spx >= 2.0 && q.ntap <= MAXTAP && 2 * q.ntap + 12 < n2) ? 0 : 3;
+                    }
+                }
+            } else {
+                q.mode = 1;
+            }
+            q.lnw_s = a.lnw0 + (double)q.i_s * a.dlnw;
+            if (q.mode == 3) fb_rows[atomicAdd(fb_count, 1)] = p;
+            ps = q;
+        }
+        __syncthreads();
+        const int mode = ps.mode, nobs = ps.nobs;
+        if (mode >= 3) {                                                      // uniform: skipped or handed to the generic kernel
+            if (mode == 4) {
+                if (a.flux_out && slot_ok)
+                    for (int j = threadIdx.x; j < nobs; j += FT) a.flux_out[(size_t)p * nobs + j] = ms_nan();
+                if (a.chi2 && !slot_ok && threadIdx.x == 0 && r[PV_TEFF] != ms_inf()) a.chi2[p] = ms_nan();
+            }
+            if (PF) mbar_wait_(bar0 + 8 * buf, (it >> 1) & 1);               // consume the phase of this buffer
+            __syncthreads();
+            continue;
+        }
+        const int i_s = ps.i_s, i_e = ps.i_e, n2 = ps.n2, ntap = ps.ntap;
+        const double d2 = ps.d2, inst = ps.inst;
+        // ---- native spectrum -> shared memory
+        if (PF) {
+            mbar_wait_(bar0 + 8 * buf, (it >> 1) & 1);
+        } else {
+            const float *frow = static_cast<const float *>(a.flux_native) + (size_t)p * npix;
+            if ((npix & 3) == 0) {
+                const float4 *src4 = reinterpret_cast<const float4 *>(frow);
+                float4 *dst4 = reinterpret_cast<float4 *>(fr);
+                for (int i = threadIdx.x; i < (npix >> 2); i += FT) dst4[i] = __ldcs(src4 + i);
+            } else {
+                for (int i = threadIdx.x; i < npix; i += FT) fr[i] = __ldcs(frow + i);
+            }
+        }
+        if (threadIdx.x == FT - 1)                                            // one-sample pad: interpolation at the last pixel
+            fr[npix] = PF ? fr[npix - 1] : __ldcs(static_cast<const float *>(a.flux_native) + (size_t)p * npix + npix - 1);
+        if (mode == 0 && threadIdx.x <= ntap) {                               // Gaussian taps, t = 0 .. ntap
+            const double t = (double)threadIdx.x / ps.spx;
+            gtap[threadIdx.x] = (float)(exp(-0.5 * t * t) / (ps.spx * 2.5066282746310002));
+        }
+        __syncthreads();
+        // FIR weight rows: W[o][u] = g[u - o], g[s] = tap (ntap - s) for s = 0 .. 2 ntap, zero elsewhere.  An observed
+        // pixel whose window starts o samples after a 16-byte boundary uses rows o (sample i) and o + 1 (sample i + 1).
+        const int U = (2 * ntap + 2 + 3 + 3) & ~3;
+        if (mode == 0) {
+            for (int idx = threadIdx.x; idx < 5 * U; idx += FT) {
+                const int o = idx / U, u = idx - o * U;
+                const int sidx = u - o;
+                float w = 0.f;
+                if (sidx >= 0 && sidx <= 2 * ntap) { const int t = ntap - sidx; w = gtap[t < 0 ? -t : t]; }
+                wtab[o * WSTRIDE + u] = w;
+            }
+        }
 
         // ---- rotational broadening on the full native grid (outwave = None), back onto the native pixels
-        if (vrot != 0.0) {
-            rotational_filter(z, fr, npix, n1, a.dlnw, vrot, a.rot_tab, twlev);
+        if (ps.rot) {
+            rotational_filter<RM>(z, fr, npix, n1, a.dlnw, ps.vrot, a.rot_tab, twlev);
             // smoothing.py:262: interpolation of the filtered n1 grid at the native wavelengths
             AffinePos ap;
             ap.set((double)(n1 - 1) / (double)(npix - 1));
-            const float half_s = (float)(0.5 * (double)(npix - 1) * a.dlnw / (double)(n1 - 1));
             for (int i = threadIdx.x; i < npix; i += FT) {
                 float t;
                 int k = ap.split(i, t);
                 if (k > n1 - 2) { k = n1 - 2; t = 1.f; }
-                const float f = t * (1.f + (t - 1.f) * half_s);
                 const float v0 = conv_at(z, k), v1 = conv_at(z, k + 1);
-                fr[i] = v0 + (v1 - v0) * f;
+                fr[i] = fmaf(v1 - v0, t, v0);
             }
             __syncthreads();
         }
 
         // ---- Doppler shift + instrumental broadening + resampling to the observed pixels
-        const double lnscale = log(scale);
+        const double lnscale = ps.lnscale;
         if (mode == 0) {
-            const float half_d = (float)(0.5 * a.dlnw);
             AffinePos ap;
-            ap.set(ratio2);
-            const float *fs = fr + i_s;
-            const int last = i_e - i_s;
+            ap.set(ps.ratio2);
+            const float *fs = fr + i_s;                                       // fs[last + 1] exists (fr is padded by one sample)
+#pragma unroll 4
             for (int k = threadIdx.x; k < n2; k += FT) {
                 float t;
-                int i = ap.split(k, t);
-                if (i > last - 1) { i = last - 1; t = 1.f; }
-                const float f = t * (1.f + (t - 1.f) * half_d);               // linear in lambda, not ln(lambda)
-                s2[k] = fs[i] + (fs[i + 1] - fs[i]) * f;
+                const int i = ap.split(k, t);
+                const float v0 = fs[i], v1 = fs[i + 1];
+                s2[k] = fmaf(v1 - v0, t, v0);
             }
-            __syncthreads();
         }
+        __syncthreads();
         double csum = 0.0;
-        const double lnw_s = a.lnw0 + (double)i_s * a.dlnw;
+        const double lnw_s = ps.lnw_s;
         const int mask2 = n2 - 1;
-        for (int j = threadIdx.x; j < nobs; j += FT) {
-            const double lx = sv.obs_lnwave[j] - lnscale;
-            double m;
-            if (mode == 0) {
-                const double q = (lx - lnw_s) / d2;
-                int i; double f;
+        // the model at one observed pixel from the (smoothed) grid values; the Gaussian sums of the instrumental stage
+        // are evaluated by fir_pair below for two pixels at a time (independent chains hide the shared-memory latency)
+        auto finish = [&](int j, double m) {
+            if (a.modpoly) m *= cheb_eval(sv.cheb_x[j], r + PV_PC0, a.n_pc);  // genmod.py:90-93
+            if (a.flux_out) a.flux_out[(size_t)p * nobs + j] = m;
+            if (a.chi2) {
+                const double d = m - sv.obs_flux[j];
+                const double t = (d * d) / sv.obs_err2[j];
+                if (t == t) csum += t;                                        // nansum (likelihood.py:193)
+            }
+        };
+        if (mode == 0) {
+            auto locate = [&](int j, int &i, double &f) {
+                const double q = (sv.obs_lnwave[j] - lnscale - lnw_s) / d2;
                 if (q <= 0.0) { i = 0; f = 0.0; }
                 else if (q >= (double)(n2 - 1)) { i = n2 - 2; f = 1.0; }
                 else {
@@ -465,10 +560,12 @@ spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restric
                     const double t = q - (double)i;
                     f = t * (1.0 + (t - 1.0) * 0.5 * d2);
                 }
-                // conv[i] and conv[i + 1] of the circular Gaussian convolution, sharing the samples
-                float a0 = 0.f, a1 = 0.f;
+            };
+            // conv[i] and conv[i + 1] of the circular Gaussian convolution, sharing the samples
+            auto fir_slow = [&](int i, float &a0, float &a1) {                // window wraps around the circular grid
                 const int base = i - ntap;
                 float x = s2[base & mask2];
+                a0 = 0.f; a1 = 0.f;
                 for (int s = 0; s <= 2 * ntap; ++s) {
                     const int t = ntap - s;
                     const float g = gtap[t < 0 ? -t : t];
@@ -476,30 +573,78 @@ spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restric
                     x = s2[(base + s + 1) & mask2];
                     a1 = fmaf(g, x, a1);                                      // sample i + 1 - t
                 }
-                m = (double)a0 + ((double)a1 - (double)a0) * f;
-            } else if (mode == 1) {
-                const double q = (lx - a.lnw0) / a.dlnw;
-                const double qlo = (double)i_s, qhi = (double)i_e;
-                if (q < qlo || q > qhi) {
-                    // smoothing branch clamps (np.interp default); plain branch returns NaN outside
-                    m = (inst != 0.0) ? (double)fr[q < qlo ? i_s : i_e] : ms_nan();
+            };
+            const int nch = U >> 2;
+            for (int j = threadIdx.x; j < nobs; j += 2 * FT) {
+                const int j2 = j + FT;
+                const bool two = j2 < nobs;
+                int iA, iB = 0; double fA, fB = 0.0;
+                locate(j, iA, fA);
+                if (two) locate(j2, iB, fB);
+                const int bA = (iA - ntap) & ~3, oA = (iA - ntap) - bA;
+                const int bB = (iB - ntap) & ~3, oB = (iB - ntap) - bB;
+                const bool fastA = bA >= 0 && bA + U <= n2, fastB = two && bB >= 0 && bB + U <= n2;
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                if (fastA && fastB) {
+                    const float4 *xa = reinterpret_cast<const float4 *>(s2 + bA), *xb = reinterpret_cast<const float4 *>(s2 + bB);
+                    const float4 *wa0 = reinterpret_cast<const float4 *>(wtab + oA * WSTRIDE), *wa1 = wa0 + WSTRIDE / 4;
+                    const float4 *wb0 = reinterpret_cast<const float4 *>(wtab + oB * WSTRIDE), *wb1 = wb0 + WSTRIDE / 4;
+                    float a0b = 0.f, a1b = 0.f, b0b = 0.f, b1b = 0.f;
+#pragma unroll 2
+                    for (int c = 0; c < nch; ++c) {
+                        const float4 x = xa[c], g0 = wa0[c], g1 = wa1[c], y = xb[c], h0 = wb0[c], h1 = wb1[c];
+                        a0 = fmaf(g0.x, x.x, a0); a0b = fmaf(g0.y, x.y, a0b); a0 = fmaf(g0.z, x.z, a0); a0b = fmaf(g0.w, x.w, a0b);
+                        a1 = fmaf(g1.x, x.x, a1); a1b = fmaf(g1.y, x.y, a1b); a1 = fmaf(g1.z, x.z, a1); a1b = fmaf(g1.w, x.w, a1b);
+                        b0 = fmaf(h0.x, y.x, b0); b0b = fmaf(h0.y, y.y, b0b); b0 = fmaf(h0.z, y.z, b0); b0b = fmaf(h0.w, y.w, b0b);
+                        b1 = fmaf(h1.x, y.x, b1); b1b = fmaf(h1.y, y.y, b1b); b1 = fmaf(h1.z, y.z, b1); b1b = fmaf(h1.w, y.w, b1b);
+                    }
+                    a0 += a0b; a1 += a1b; b0 += b0b; b1 += b1b;
                 } else {
-                    int i = (int)q;
-                    if (i > i_e - 1) i = i_e - 1;
-                    const double t = q - (double)i;
-                    const double f = t * (1.0 + (t - 1.0) * 0.5 * a.dlnw);
-                    const double v0 = (double)fr[i], v1 = (double)fr[i + 1];
-                    m = v0 + (v1 - v0) * f;
+                    if (fastA) {
+                        const float4 *xa = reinterpret_cast<const float4 *>(s2 + bA);
+                        const float4 *wa0 = reinterpret_cast<const float4 *>(wtab + oA * WSTRIDE), *wa1 = wa0 + WSTRIDE / 4;
+                        for (int c = 0; c < nch; ++c) {
+                            const float4 x = xa[c], g0 = wa0[c], g1 = wa1[c];
+                            a0 = fmaf(g0.x, x.x, a0); a0 = fmaf(g0.y, x.y, a0); a0 = fmaf(g0.z, x.z, a0); a0 = fmaf(g0.w, x.w, a0);
+                            a1 = fmaf(g1.x, x.x, a1); a1 = fmaf(g1.y, x.y, a1); a1 = fmaf(g1.z, x.z, a1); a1 = fmaf(g1.w, x.w, a1);
+                        }
+                    } else fir_slow(iA, a0, a1);
+                    if (two) {
+                        if (fastB) {
+                            const float4 *xb = reinterpret_cast<const float4 *>(s2 + bB);
+                            const float4 *wb0 = reinterpret_cast<const float4 *>(wtab + oB * WSTRIDE), *wb1 = wb0 + WSTRIDE / 4;
+                            for (int c = 0; c < nch; ++c) {
+                                const float4 y = xb[c], h0 = wb0[c], h1 = wb1[c];
+                                b0 = fmaf(h0.x, y.x, b0); b0 = fmaf(h0.y, y.y, b0); b0 = fmaf(h0.z, y.z, b0); b0 = fmaf(h0.w, y.w, b0);
+                                b1 = fmaf(h1.x, y.x, b1); b1 = fmaf(h1.y, y.y, b1); b1 = fmaf(h1.z, y.z, b1); b1 = fmaf(h1.w, y.w, b1);
+                            }
+                        } else fir_slow(iB, b0, b1);
+                    }
                 }
-            } else {
-                m = ms_nan();
+                finish(j, (double)a0 + ((double)a1 - (double)a0) * fA);
+                if (two) finish(j2, (double)b0 + ((double)b1 - (double)b0) * fB);
             }
-            if (a.modpoly) m *= cheb_eval(sv.cheb_x[j], r + PV_PC0, a.n_pc);  // genmod.py:90-93
-            if (a.flux_out) a.flux_out[(size_t)p * nobs + j] = m;
-            if (a.chi2) {
-                const double d = m - sv.obs_flux[j];
-                const double t = (d * d) / sv.obs_err2[j];
-                if (t == t) csum += t;                                        // nansum (likelihood.py:193)
+        } else {
+            for (int j = threadIdx.x; j < nobs; j += FT) {
+                double m;
+                if (mode == 1) {
+                    const double q = (sv.obs_lnwave[j] - lnscale - a.lnw0) / a.dlnw;
+                    const double qlo = (double)i_s, qhi = (double)i_e;
+                    if (q < qlo || q > qhi) {
+                        // smoothing branch clamps (np.interp default); plain branch returns NaN outside
+                        m = (inst != 0.0) ? (double)fr[q < qlo ? i_s : i_e] : ms_nan();
+                    } else {
+                        int i = (int)q;
+                        if (i > i_e - 1) i = i_e - 1;
+                        const double t = q - (double)i;
+                        const double f = t * (1.0 + (t - 1.0) * 0.5 * a.dlnw);
+                        const double v0 = (double)fr[i], v1 = (double)fr[i + 1];
+                        m = v0 + (v1 - v0) * f;
+                    }
+                } else {
+                    m = ms_nan();
+                }
+                finish(j, m);
             }
         }
         if (a.chi2) {
@@ -516,9 +661,10 @@ spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restric
     }
 }
 
-size_t fast_smem_bytes(int npix, int n1) {
+size_t fast_smem_bytes(int npix, int n1, bool pf) {
     const int M = n1 >> 1;
-    return (size_t)(M + (M >> 4)) * sizeof(float2) + 16 + (size_t)npix * sizeof(float) + 16;
+    const size_t fr_bytes = ((size_t)(npix + 1) * sizeof(float) + 15) & ~(size_t)15;
+    return (size_t)(M + (M >> 4)) * sizeof(float2) + 16 + (pf ? 2 : 1) * fr_bytes + 16;
 }
 
 }  // namespace
@@ -526,21 +672,32 @@ size_t fast_smem_bytes(int npix, int n1) {
 bool spec_fast_usable(const ms_ctx *ctx) {
     const SpecNetDev &n = ctx->spec;
     return ctx->precision != MS_PREC_F64 && n.n1 >= 8 && (n.n1 >> 1) <= MAXM &&
-           fast_smem_bytes(n.npix, n.n1) <= 226 * 1024;
+           fast_smem_bytes(n.npix, n.n1, false) <= 226 * 1024;
 }
 
 // Rows the kernel declines are appended to fb_rows / *fb_count (device; the caller zeroes the counter).
+// ctx->spec_fast selects the variant: 1 = radix 16, one CTA per SM, bulk-copy prefetch of the next spectrum;
+// 2 = radix 8, two CTAs per SM (when two fit).
 int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, int *fb_rows, int *fb_count, cudaStream_t st) {
-    const size_t smem = fast_smem_bytes(sa.npix, sa.n1);
-    static size_t configured = 0;
-    if (configured < smem) {
-        MS_CUDA(cudaFuncSetAttribute(spec_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    const int per_sm = (MS_FAST_MINB >= 2 && 2 * (smem + 1024 + 2048) <= 227 * 1024) ? 2 : 1;
-    int grid = ctx->sm_count * per_sm;
+    const bool aligned = (sa.npix & 3) == 0;
+    const size_t smem_pf = fast_smem_bytes(sa.npix, sa.n1, true), smem_1 = fast_smem_bytes(sa.npix, sa.n1, false);
+    const bool two = (ctx->spec_fast == 2 || FT == 256) && 2 * (smem_1 + 1024 + 4096) <= 227 * 1024;
+    const bool pf = !two && aligned && smem_pf <= 226 * 1024;
+    const size_t smem = pf ? smem_pf : smem_1;
+    auto k16 = spec_fast_kernel<16, false>;
+    auto k16p = spec_fast_kernel<16, true>;
+    auto k8 = spec_fast_kernel<8, false>;
+    static size_t cfg16 = 0, cfg16p = 0, cfg8 = 0;
+    if (two && FT == 256 && ctx->spec_fast != 2) { if (cfg16 < smem) { MS_CUDA(cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg16 = smem; } }
+    else if (two) { if (cfg8 < smem) { MS_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg8 = smem; } }
+    else if (pf) { if (cfg16p < smem) { MS_CUDA(cudaFuncSetAttribute(k16p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg16p = smem; } }
+    else { if (cfg16 < smem) { MS_CUDA(cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg16 = smem; } }
+    int grid = ctx->sm_count * (two ? 2 : 1);
     if (grid > nB) grid = nB;
-    spec_fast_kernel<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    if (two && FT == 256 && ctx->spec_fast != 2) k16<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    else if (two) k8<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    else if (pf) k16p<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    else k16<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

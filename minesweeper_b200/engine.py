@@ -273,7 +273,7 @@ class Engine(object):
 
     def set_spec_fast(self, on=True):
         """f32-class modes: fast broadening kernel (default) or the generic FFT kernel for every row."""
-        check(self.lib.ms_set_spec_fast(self._ctx, int(bool(on))))
+        check(self.lib.ms_set_spec_fast(self._ctx, int(on)))
 
     def profile(self, on=True):
         check(self.lib.ms_profile_enable(self._ctx, int(on)))

@@ -746,8 +746,9 @@ def _spec_theta(n, seed, with_inst=False):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('variant', [1, 2])
 @pytest.mark.parametrize('npix', [4096, 10240, 1000])
-def test_fast_broadening_kernel_equals_generic_fft_kernel(npix):
+def test_fast_broadening_kernel_equals_generic_fft_kernel(npix, variant):
     """f32-class modes: the fast kernel (radix-16 FFT for the rotational stage, direct Gaussian sum for the
     instrumental stage, csrc/spec_fast.cu) against the generic kernel that performs the reference's two FFT
     convolutions literally (csrc/spec_smooth.cu), same native fluxes: model spectra to 3e-6, lnL to the
@@ -765,9 +766,9 @@ def test_fast_broadening_kernel_equals_generic_fft_kernel(npix):
     th[2:40, 2] = np.linspace(41500.0, 60000.0, 38)              # Inst_R * 2.355 near / above the net's resolution:
     L = likelihood(fitargs, fitpars, rb, precision='f32', verbose=False)   # narrow kernels -> fallback, sigma <= 0 -> interp
     assert L.fitpars_i[2] == 'Inst_R'
-    c0 = L.engine.launch_count()
+    L.engine.set_spec_fast(variant)
     lf = L.lnlike_batch(th)[0].cpu().numpy()
-    L.engine.set_spec_fast(False)
+    L.engine.set_spec_fast(0)
     lg = L.lnlike_batch(th)[0].cpu().numpy()
     assert np.array_equal(np.isneginf(lf), np.isneginf(lg)) and np.isneginf(lf).sum() > 0
     fin = np.isfinite(lg)
@@ -782,7 +783,7 @@ def test_fast_broadening_kernel_equals_generic_fft_kernel(npix):
                    rng.uniform(20000.0, 45000.0, 64)], 1)
     sp[0, 5] = 0.0; sp[1, 4] = 0.0; sp[2, 7] = 0.0               # no rotation / no shift / no instrumental stage
     fg = L.engine.spec_model(sp).cpu().numpy()
-    L.engine.set_spec_fast(True)
+    L.engine.set_spec_fast(variant)
     ff = L.engine.spec_model(sp).cpu().numpy()
     assert np.array_equal(np.isnan(ff), np.isnan(fg))
     np.testing.assert_allclose(ff, fg, rtol=3e-6, atol=3e-6, equal_nan=True)

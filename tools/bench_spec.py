@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 
 
 def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc', steps=3, device=None,
-                   cpu_points=0, seed=0):
+                   cpu_points=0, seed=0, spec_fast=2):
     """Times spectrum + photometry lnL over `batch` points resident on the GPU; returns a dict."""
     import torch
     from minesweeper_b200 import synth
@@ -54,6 +54,7 @@ def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc
     L = likelihood(fitargs, fitpars, runbools, precision=precision, device=device, verbose=False)
     assert L.fitpars_i == [n for n in names if n in on]
     eng = L.engine
+    eng.set_spec_fast(spec_fast)
     theta = torch.from_numpy(th).to(eng.device)
     out = torch.empty(B, dtype=torch.float64, device=eng.device)
     for _ in range(2):
@@ -88,13 +89,14 @@ def main():
     ap.add_argument('--npix', type=int, default=10240)
     ap.add_argument('--precision', default='f32')
     ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--spec-fast', type=int, default=2, help='0 generic FFT kernel, 1 radix-16 / 1 CTA per SM, 2 radix-8 / 2 CTAs')
     ap.add_argument('--cpu-points', type=int, default=0, help='also time the per-point oracle on N points')
     args = ap.parse_args()
     from minesweeper_b200 import synth
     mist = synth.make_mist(seed=0)
     phot = synth.make_phot_net(h=128, seed=1)
     print(json.dumps(run_spec_bench(mist, phot, args.batch, args.nobs, args.npix, args.precision, args.steps,
-                                    cpu_points=args.cpu_points)))
+                                    cpu_points=args.cpu_points, spec_fast=args.spec_fast)))
 
 
 if __name__ == '__main__':
