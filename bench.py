@@ -32,6 +32,7 @@ PHOT_ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mas
 KIND_TEXT = {'reference': "the reference's own likelihood.likelihood class, unmodified modules from oracle/_ref",
              'port': 'the oracle port oracle/like_port.py (no reference copy present)'}
 PARITY_ROWS = 4096
+SPEC_PARITY_ROWS = 48
 
 
 def parse():
@@ -236,6 +237,31 @@ def main():
         parity_ref = lnlike_phot_dense(fitargs['MISTpath'], fitargs['photANNpath'], fitargs['obs_phot'],
                                        synth.draw_theta_phot(args.batch, seed=3, box=box)[:PARITY_ROWS])
 
+    # ---- CPU leg of the spectrum + photometry configuration (configs[2]): the reference's per-point loop on all
+    # cores, and its lnL on the first rows of the batch as the parity reference of the GPU run below
+    spec_cpu = spec_parity_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.spec_batch > 0:
+        from bench_spec import make_spec_workload
+        from oracle.cpu_baseline import CpuArm
+        sfa, sfp, srb, sth = make_spec_workload(fitargs['MISTpath'], fitargs['photANNpath'], args.spec_batch, 1536,
+                                                seed=rank)
+        arm = CpuArm(sfa, sfp, srb, sth[:8192])
+        r1 = arm.calibrate(1.0)
+        n = int(max(r1 * arm.cores * 0.8 * args.cpu_seconds * 0.6, 4 * arm.cores))
+        arm.step(max(n // 10, arm.cores))
+        ne, te = arm.step(n)
+        rows = np.arange(SPEC_PARITY_ROWS)
+        lref = arm.eval_rows(rows)
+        arm.close()
+        spec_cpu = dict(value=ne / te, unit=UNIT, cores=arm.cores, kind=arm.kind,
+                        sample='%d per-point lnlikefn evaluations (spectrum 1536 px + 10 bands) over %d worker '
+                               'processes (%.1f s; %s); single-core probe %.0f evals/s'
+                               % (ne, arm.cores, te, KIND_TEXT[arm.kind], r1))
+        # |d lnL| a 1e-5 relative model-flux error can cause at S/N 150 (chi-square sensitivity), + the photometric part
+        tol = 1e-5 * 150.0 * np.sqrt(2.0 * 2.0 * np.abs(lref) * 1536) + 1e-5 * np.abs(lref) + 1e-3
+        spec_parity_ref = (len(rows), lref, tol)
+        del arm
+
     # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION (read when the library loads); stdout carries
     # the one JSON line
     if world > 1 and os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
@@ -319,6 +345,26 @@ def main():
     ms = float(t.item())
     value = B * world * args.steps / (ms * 1e-3)
 
+    # ---- second timed variant: lnL AND the derived[B, 13] block the prior consumes
+    der_buf = torch.empty((B, 13), dtype=torch.float64, device=dev)
+    for _ in range(3):
+        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=True, out=lnl_bufs[0], derived_out=der_buf)
+    barrier()
+    dv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in dv:
+        flush.zero_()
+        e0.record()
+        eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=True, out=lnl_bufs[0], derived_out=der_buf)
+        e1.record()
+    barrier()
+    tdv = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in dv)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tdv, op=dist.ReduceOp.MAX)
+    derived_variant = dict(value=B * world * args.steps / (float(tdv.item()) * 1e-3), unit=UNIT,
+                           ms_per_step=float(tdv.item()) / args.steps,
+                           extra_bytes_per_eval=13 * 8, note='same step, also writing derived[B,13] f64 to HBM')
+    del der_buf
+
     # ---- end to end through the host-buffer C-ABI call: pinned host theta in, lnL out, every step
     th_pin = torch.from_numpy(theta_np).pin_memory()
     out_pin = torch.empty(B, dtype=torch.float64).pin_memory()
@@ -371,20 +417,36 @@ def main():
         except Exception as e:                                           # never lose the main line
             catalog = dict(error=repr(e))
 
-    # ---- auxiliary: spectrum + photometry likelihood (BASELINE.json metric, configs[2])
+    # ---- spectrum + photometry likelihood (BASELINE.json metric, configs[2]): 1536 observed pixels (the demo
+    # spectrum) with roofline, CPU arm and an in-run parity sample, and the 10 000-pixel variant of the config text
     specblk = None
     if args.spec_batch > 0:
         try:
             from bench_spec import run_spec_bench
+            sprec = args.precision if args.precision != 'f64' else 'f32'
             r = run_spec_bench(fitargs['MISTpath'], fitargs['photANNpath'], batch=args.spec_batch, nobs=1536,
-                               precision=args.precision if args.precision != 'f64' else 'f32', steps=3, device=local,
-                               seed=rank)
-            tsp = torch.tensor([r['ms_per_step']], dtype=torch.float64, device=dev)
+                               precision=sprec, steps=3, device=local, seed=rank, parity_ref=spec_parity_ref)
+            r10 = run_spec_bench(fitargs['MISTpath'], fitargs['photANNpath'], batch=args.spec_batch, nobs=10000,
+                                 precision=sprec, steps=3, device=local, seed=rank)
+            tsp = torch.tensor([r['ms_per_step'], r10['ms_per_step']], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tsp, op=dist.ReduceOp.MAX)
-            specblk = dict(value=args.spec_batch * world / (float(tsp.item()) * 1e-3), unit='evals/s',
-                           ms_per_step=float(tsp.item()), batch_per_gpu=args.spec_batch, workload=r['workload'],
-                           kernel_ms=r['kernel_ms'], spec_mlp_tflops=r['spec_mlp_tflops'])
+            ms15, ms10 = float(tsp[0].item()), float(tsp[1].item())
+            val = args.spec_batch * world / (ms15 * 1e-3)
+            pk = peaks()
+            tf_step = r['flop_per_eval'] * val / world / 1e12            # per GPU, whole step
+            specblk = dict(value=val, unit='evals/s', ms_per_step=ms15, batch_per_gpu=args.spec_batch,
+                           workload=r['workload'], kernel_ms=r['kernel_ms'],
+                           roofline=dict(bound='tensor', kernel='whole spectrum + photometry step (spectral MLP on tcgen05; '
+                                         'the broadening kernel, CUDA-core FFT + FIR, is the long pole)',
+                                         flop_per_eval=r['flop_per_eval'], achieved=tf_step, peak=pk['tf_burst'],
+                                         unit='TFLOP/s', frac=tf_step / pk['tf_burst'], peak_source=pk['src'],
+                                         mlp_kernels_alone_tflops=r['spec_mlp_tflops'],
+                                         mlp_kernels_alone_frac=r['spec_mlp_tflops'] / pk['tf_burst'],
+                                         share_of_step={k: v / ms15 for k, v in r['kernel_ms'].items()}),
+                           cpu_baseline=spec_cpu, parity_check=r['parity_check'],
+                           n_obs_10000=dict(value=args.spec_batch * world / (ms10 * 1e-3), unit='evals/s',
+                                            ms_per_step=ms10, kernel_ms=r10['kernel_ms'], workload=r10['workload']))
         except Exception as e:
             specblk = dict(error=repr(e))
 
@@ -442,6 +504,7 @@ def main():
             kernel_ms={k: v[0] / args.steps for k, v in prof.items() if v[1]},
             kernel_ms_two_kernel_sequence={k: v[0] / 5 for k, v in prof2.items() if v[1]},
             parity_check=parity,
+            with_derived=derived_variant,
             catalog=catalog,
             spec_phot=specblk,
             cpu_baseline=cpu)

@@ -81,6 +81,11 @@ class CpuArm(object):
         self.rate1 = n / (time.perf_counter() - t0)
         return self.rate1
 
+    def eval_rows(self, rows):
+        """lnL of theta[rows] evaluated in this process by the same likelihood object (parity reference)."""
+        with np.errstate(all='ignore'):
+            return np.array([_PORT.lnlikefn(list(_THETA[i])) for i in rows])
+
     def step(self, n_total):
         """n_total evaluations split over the workers; returns (evals, wall seconds)."""
         per = max(n_total // self.cores, 1)

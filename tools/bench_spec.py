@@ -17,18 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc', steps=3, device=None,
-                   cpu_points=0, seed=0, spec_fast=2):
-    """Times spectrum + photometry lnL over `batch` points resident on the GPU; returns a dict."""
-    import torch
+NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
+         'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1', 'pc_2', 'pc_3']
+ON = {'Vrad', 'Vrot', 'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass',
+      'pc_0', 'pc_1', 'pc_2', 'pc_3'}
+
+
+def make_spec_workload(mist, phot, batch, nobs=1536, npix=10240, seed=0):
+    """configs[2] of BASELINE.json (SURVEY.md section 8d "Config 3"): (fitargs, fitpars, runbools, theta[batch, 12])."""
     from minesweeper_b200 import synth
-    from minesweeper_b200.likelihood import likelihood
     spec = synth.make_spec_net(npix=npix, h=300, seed=2)
-    names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
-             'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass', 'pc_0', 'pc_1', 'pc_2', 'pc_3']
-    on = {'Vrad', 'Vrot', 'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass',
-          'pc_0', 'pc_1', 'pc_2', 'pc_3'}
-    fitpars = [names, {n: (n in on) for n in names}]
+    fitpars = [NAMES, {n: (n in ON) for n in NAMES}]
     obs = synth.make_obs_spectrum(spec, n_obs=nobs, seed=4)
     fitargs = dict(ageweight=True, mistdif=True, fixedpars={'Inst_R': 35000.0}, MISTpath=mist,
                    photANNpath=phot, specANNpath=spec, NNtype='YST1', obs_phot=synth.demo_obs_phot(),
@@ -43,6 +42,18 @@ def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc
     th = np.stack([rng.uniform(-5, 5, B), rng.uniform(0, 10, B), base[:, 0], base[:, 1], base[:, 2], base[:, 3],
                    base[:, 4], base[:, 5], rng.normal(1.0, 0.05, B), rng.normal(0, 0.02, B),
                    rng.normal(0, 0.01, B), rng.normal(0, 0.005, B)], 1)
+    return fitargs, fitpars, runbools, th
+
+
+def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc', steps=3, device=None,
+                   cpu_points=0, seed=0, spec_fast=2, parity_ref=None):
+    """Times spectrum + photometry lnL over `batch` points resident on the GPU; returns a dict.  parity_ref:
+    (rows, lnl_ref, tol) from the CPU leg -- the first rows of this batch evaluated by the per-point reference."""
+    import torch
+    from minesweeper_b200.likelihood import likelihood
+    fitargs, fitpars, runbools, th = make_spec_workload(mist, phot, batch, nobs, npix, seed)
+    names, on = NAMES, ON
+    B = batch
     cpu = None
     if cpu_points:
         from oracle.like_port import LikelihoodPort
@@ -70,12 +81,22 @@ def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc
     ms = e0.elapsed_time(e1) / steps
     prof = eng.profile_read()
     eng.profile(False)
+    parity = None
+    if parity_ref is not None:
+        nrow, lref, tol = parity_ref
+        got = out[:nrow].cpu().numpy()
+        fin = np.isfinite(lref)
+        assert np.array_equal(np.isneginf(got), np.isneginf(lref)), 'spec parity: -inf rows differ'
+        err = np.abs(got[fin] - lref[fin])
+        parity = dict(rows=int(nrow), max_dlnL=float(err.max()), max_dlnL_over_bound=float((err / tol[fin]).max()))
+        assert np.all(err <= tol[fin]), 'spec parity: lnL outside the bound (%g x)' % (err / tol[fin]).max()
     flop = 2.0 * (4 * 300 + 300 * 300 + 300 * npix)
     res = dict(metric='spec_phot_loglike_evals_per_sec', value=B / (ms * 1e-3), unit='evals/s', ms_per_step=ms,
                batch=B, n_obs=nobs, npix=npix, precision=precision,
                kernel_ms={k: v[0] / steps for k, v in prof.items() if v[1]},
                spec_mlp_tflops=flop * B / (prof['spec_mlp'][0] / steps * 1e-3) / 1e12,
-               finite=int(torch.isfinite(out).sum().item()), cpu_evals_per_sec_1core=cpu,
+               finite=int(torch.isfinite(out).sum().item()), cpu_evals_per_sec_1core=cpu, parity_check=parity,
+               flop_per_eval=flop,
                workload='configs[2]: spectrum + photometry loglike, spectral ANN 4-300-300-%d px, vsini + Doppler + '
                         'R smoothing, %d observed pixels, batch %d' % (npix, nobs, B))
     eng.close()
