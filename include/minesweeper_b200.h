@@ -209,6 +209,7 @@ int ms_lnprob_batch_stars(ms_ctx *ctx, const ms_flags *flags, const double *thet
  * Replaces the sequential part of dynesty's static sampler as driven by fitstar._runsampler
  * (fitstar.py:337-369): S stars x Q queued random-walk walkers, K live points per star.  All
  * pointers are device memory owned by the caller (see minesweeper_b200/sampler.py). */
+#define MS_NS_TRAIL 7
 typedef struct {
     int32_t S, K, Q, nd, nder, walks;
     int64_t maxiter, dead_cap;
@@ -220,8 +221,10 @@ typedef struct {
     double *lmin, *sigma, *scale;                     /* [S], [S][nd][nd] Cholesky factor of the live-point covariance, [S] */
     double *logz, *hacc, *wmax, *wtot, *wsum, *wsq;   /* evidence / information / posterior moments  */
     int64_t *niter, *ncall;                           /* [S] iterations, likelihood calls            */
-    int32_t *done;                                    /* [S] 0 running, 1 converged, 2 finalised     */
-    double *dead;                                     /* [S][dead_cap][nd+nder+3] or NULL            */
+    int32_t *done;                                    /* [S] 0 running, 1 converged (dlogz), 2 finalised, 3 stopped at
+                                                         maxiter, 4 finalised after maxiter             */
+    double *dead;                                     /* [S][dead_cap][nd+nder+MS_NS_TRAIL] or NULL: the row, then
+                                                         log(lk) log(vol) log(wt) h nc log(z) delta(log(z))  */
     uint64_t *rng_round;                              /* device counter of completed rounds (graph-replay safe RNG stream) */
 } ms_ns_state;
 /* step = walk step inside the current round (0 .. walks-1); the round number is read from rng_round */

@@ -79,6 +79,7 @@ PRIOR_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'exp': 3, 'logunifor
 TERM_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'tgaussian_bounds': 3}
 MS_V_LOGAGE, MS_V_AGE, MS_V_PARALLAX = MS_NPARAM, MS_NPARAM + 1, MS_NPARAM + 2
 MS_MAX_PRIOR_TERMS = 32
+MS_NS_TRAIL = 7                     # trailing columns of a dead-point record (ms_ns_state.dead)
 
 class NsState(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ('S', 'K', 'Q', 'nd', 'nder', 'walks')] +

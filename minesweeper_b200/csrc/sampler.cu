@@ -160,7 +160,7 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
     const int64_t lbase = (int64_t)star * K;
     for (int k = lane; k < K; k += 32) lp[k] = s.live_lp[lbase + k];
     __syncwarp();
-    bool done = s.done[star] != 0;
+    bool done = s.done[star] != 0, hit_max = false;
     int nacc_tot = 0;
     if (!done) {
         // everything the update chain needs, requested together
@@ -179,8 +179,11 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
             const double logvol = -((double)it + 1.0) / K;
             const double logwt = lmin + (logvol + 1.0 / K + log_shrink);
             const double *row_w = s.live_row + (lbase + w) * ncol;
-            if (s.dead && it < s.dead_cap) {                        // optional dead-point record
-                double *o = s.dead + ((int64_t)star * s.dead_cap + it) * (ncol + 3);
+            // optional dead-point record: the row, then the seven trailing columns of the reference's samples file
+            // (fitstar.py:424-425): log(lk) log(vol) log(wt) h nc log(z) delta(log(z))
+            double *o = (s.dead && it < s.dead_cap) ? s.dead + ((int64_t)star * s.dead_cap + it) * (ncol + MS_NS_TRAIL)
+                                                    : nullptr;
+            if (o) {
                 for (int c = lane; c < ncol; c += 32) o[c] = row_w[c];
                 if (lane == 0) { o[ncol] = lmin; o[ncol + 1] = logvol; o[ncol + 2] = logwt; }
             }
@@ -194,11 +197,15 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
             __syncwarp();
             lmax = fmax(lmax, lpq);
             const double dl = logaddexp_d(ev.logz, lmax + logvol) - ev.logz;
-            if (dl < s.dlogz || it >= s.maxiter) { done = true; break; }
+            if (o && lane == 0) {                                   // running information, calls, evidence, remaining evidence
+                o[ncol + 3] = ev.hacc - ev.logz; o[ncol + 4] = (double)s.walks; o[ncol + 5] = ev.logz; o[ncol + 6] = dl;
+            }
+            if (dl < s.dlogz) { done = true; break; }
+            if (it >= s.maxiter) { done = true; hit_max = true; break; }
         }
         if (lane == 0) {
             if (it != it_in) { ev.store(s, star); s.niter[star] = it; }
-            s.done[star] = done ? 1 : 0;
+            s.done[star] = done ? (hit_max ? 3 : 1) : 0;     // 1 converged (dlogz), 3 stopped at maxiter
             // dynesty's rwalk scale update towards 50 % acceptance
             const double facc = (double)nacc_tot / ((double)Q * s.walks);
             const double sc = scale_in * exp((facc - 0.5) / nd / 0.5);
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(32 * NS_WARPS)
 ns_finalize_kernel(ms_ns_state s) {
     const int lane = threadIdx.x & 31;
     const int star = blockIdx.x * NS_WARPS + (threadIdx.x >> 5);
-    if (star >= s.S || s.done[star] != 1) return;      // only stars that finished and are not yet finalised
+    if (star >= s.S || (s.done[star] != 1 && s.done[star] != 3)) return;   // only stars that stopped and are not yet finalised
     const int K = s.K, ncol = s.nd + s.nder;
     const double logvol_f = -((double)s.niter[star]) / K - log((double)K);
     NsEv ev; ev.load(s, star);
@@ -278,7 +285,7 @@ ns_finalize_kernel(ms_ns_state s) {
         ns_accumulate(s, ev, star, l, l + logvol_f, s.live_row + ((int64_t)star * K + k) * ncol, ncol, lane);
     }
     __syncwarp();
-    if (lane == 0) { ev.store(s, star); s.done[star] = 2; }
+    if (lane == 0) { ev.store(s, star); s.done[star] = s.done[star] == 3 ? 4 : 2; }    // 2 finalised, 4 finalised after maxiter
 }
 
 int check_state(const ms_ns_state *s) {

@@ -24,6 +24,24 @@ SPEC_KEYS = ('Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst
 FAIL_KEYS = ('Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'log(R)', 'log(Age)', 'Agewgt', 'Mass', 'log(L)')
 
 
+def parsdict_keys(fitpars_i, fixedpars, iso=True, ageweight=True):
+    """Key order of the ``parsdict`` the reference's ``lnlikefn`` leaves behind after a successful call
+    (likelihood.py:95-141): sampled parameters, fixed parameters, then -- isochrone fits -- Teff, log(g), log(R),
+    [Fe/H], [a/Fe], log(Age), Mass, log(L) and Agewgt, each appended only if not already present.  This is the
+    column order of the samples file (fitstar.py:392-402)."""
+    keys = list(fitpars_i)
+    for k in fixedpars.keys():
+        if k not in keys:
+            keys.append(k)
+    if iso:
+        for k in ('Teff', 'log(g)', 'log(R)', '[Fe/H]', '[a/Fe]', 'EEP', 'log(Age)', 'Mass', 'log(L)'):
+            if k not in keys:
+                keys.append(k)
+        if ageweight and 'Agewgt' not in keys:
+            keys.append('Agewgt')
+    return keys
+
+
 class likelihood(object):
     def __init__(self, fitargs, fitpars, runbools, **kwargs):
         self.verbose = kwargs.get('verbose', True)

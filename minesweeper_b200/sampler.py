@@ -48,8 +48,9 @@ class BatchedNestedSampler(object):
         self.S, self.K, self.walks = int(nstars), int(nlive), int(walks)
         self.ndim = likeobj.ndim
         self.dlogz, self.maxiter, self.max_extend = float(dlogz), int(maxiter), int(max_extend)
+        self.seed = int(seed)
         self.gen = torch.Generator(device=self.dev)
-        self.gen.manual_seed(int(seed))
+        self.gen.manual_seed(self.seed)
         self.per_star = self.S > 1 or star_plx is not None
         self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
         self.store = bool(store_samples)
@@ -236,6 +237,9 @@ class BatchedNestedSampler(object):
         S, K, nd, dev = self.S, self.K, self.ndim, self.dev
         f64 = torch.float64
         ninf = -float('inf')
+        # the captured iteration draws from the device's default generator (graph-safe): seed it so runs reproduce
+        with torch.cuda.device(dev):
+            torch.cuda.manual_seed(self.seed)
         star0 = torch.arange(S, device=dev)
         # ---- initial live points, eagerly (redrawn until finite) ----
         U = self._rand(S, K, nd)
@@ -481,7 +485,7 @@ class QueuedNestedSampler(object):
                  niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), done=z(S, dt=torch.int32),
                  rng_round=z(1, dt=torch.int64))
         if self.store:
-            t['dead'] = z(S, self.dead_cap, ncol + 3)
+            t['dead'] = z(S, self.dead_cap, ncol + _lib.MS_NS_TRAIL)
         orig = torch.arange(S, device=dev)
         out = dict(logz=z(S), H=z(S), niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), mean=z(S, ncol),
                    std=z(S, ncol), converged=z(S, dt=torch.bool))
@@ -554,12 +558,12 @@ class QueuedNestedSampler(object):
                         break
                 del graph
                 if rounds >= self.maxiter + 16:
-                    t['done'].clamp_(min=1)               # give up on the rest: finalise as they are
+                    t['done'][t['done'] == 0] = 3         # give up on the rest: finalise as they are, NOT converged
                     nrun = 0
-                out['converged'][orig[t['done'] != 0]] = rounds < self.maxiter + 16
                 _lib.check(lib.ms_ns_finalize(eng._ctx, C.byref(st), stream()))
-                fin = t['done'] == 2
+                fin = (t['done'] == 2) | (t['done'] == 4)
                 harvest(fin)
+                out['converged'][orig[fin]] = t['done'][fin] == 2        # 2: stopped by the dlogz test; 4: at maxiter
                 if self.store and 'dead' in t:
                     pass                                  # dead points are read back below (single working set)
                 if nrun == 0:
@@ -583,34 +587,93 @@ class QueuedNestedSampler(object):
                    std=out['std'].cpu().numpy(), converged=out['converged'].cpu().numpy(), rounds=rounds,
                    graph_captures=captures)
         if self.store:
-            if captures > 1:
-                raise RuntimeError('store_samples needs min_compact >= nstars (no compaction)')
             d = t['dead'].cpu().numpy()
             res['dead'] = [d[s_, :min(int(res['niter'][s_]), self.dead_cap)] for s_ in range(S)]
+            # the final live points (the reference appends them to the samples file, fitstar.py:466-501)
+            res['live_rows'] = t['live_row'].reshape(S, K, ncol).cpu().numpy()
+            res['live_lnprob'] = t['live_lp'].reshape(S, K).cpu().numpy()
+            res['nlive'] = K
         return res
 
 
-def write_samples_file(path, res, star=0):
-    """Dead points of one star in the reference's samples-file layout (header fitstar.py:235-242:
-    ``Iter <pars...> log(lk) log(vol) log(wt) h nc log(z) delta(log(z))``); needs store_samples.
-    Accepts the records of both samplers: per-iteration tuples (BatchedNestedSampler) or one
-    ``[niter, ncol + 3]`` array per star (QueuedNestedSampler: row, ln L, ln X, ln w)."""
-    names = res['names']
+def _running_evidence(lnl, logwt, logz0=-np.inf, hacc0=0.0):
+    """Running ln Z and information H after each point (same recursion as ns_accumulate in csrc/sampler.cu)."""
+    logz, h = np.empty(len(lnl)), np.empty(len(lnl))
+    lz, ha = logz0, hacc0
+    for i, (l, w) in enumerate(zip(lnl, logwt)):
+        lz_new = np.logaddexp(lz, w)
+        ha = (ha * np.exp(lz - lz_new) if np.isfinite(lz) else 0.0) + np.exp(w - lz_new) * l
+        lz = lz_new
+        logz[i], h[i] = lz, ha - lz
+    return logz, h
+
+
+def samples_table(res, star=0, likeobj=None):
+    """(column names, rows[n, ncols]) of one star's samples file: every dead point in order, then the final live
+    points sorted by ln L (the reference appends them, fitstar.py:466-501), with the seven trailing columns
+    ``log(lk) log(vol) log(wt) h nc log(z) delta(log(z))`` (fitstar.py:235-242, 424-425).
+
+    With ``likeobj`` the parameter columns are the keys of the reference's ``parsdict`` in its insertion order
+    (likelihood.py:95-141: sampled parameters, fixed parameters, then Teff, log(g), log(R), [Fe/H], [a/Fe],
+    log(Age), Mass, log(L), Agewgt for isochrone fits) -- the header ``fitstar._initoutput`` writes and
+    ``demo/postproc.py:142-160`` reads; without it the raw sampler columns are kept.
+    Accepts the records of both samplers: one ``[niter, ncol + 7]`` array per star (QueuedNestedSampler, running
+    values from ``ns_consume``) or per-iteration tuples (BatchedNestedSampler; running values recomputed here)."""
+    names = list(res['names'])
+    ncol = len(names)
     dead = res['dead']
+    if len(dead) and isinstance(dead[0], np.ndarray) and dead[0].ndim == 2:
+        d = np.asarray(dead[star])
+        rows, lnl, logvol, logwt = d[:, :ncol], d[:, ncol], d[:, ncol + 1], d[:, ncol + 2]
+        if d.shape[1] >= ncol + 7:
+            h, nc, logz, dlz = d[:, ncol + 3], d[:, ncol + 4], d[:, ncol + 5], d[:, ncol + 6]
+        else:
+            logz, h = _running_evidence(lnl, logwt)
+            nc, dlz = np.full(len(d), np.nan), np.full(len(d), np.nan)
+    else:
+        pick = [(row[np.flatnonzero(act == star)[0]], l[np.flatnonzero(act == star)[0]],
+                 v[np.flatnonzero(act == star)[0]], w[np.flatnonzero(act == star)[0]])
+                for act, row, l, v, w in dead if np.any(act == star)]
+        rows = np.array([p[0] for p in pick]).reshape(len(pick), ncol)
+        lnl, logvol, logwt = (np.array([p[i] for p in pick]) for i in (1, 2, 3))
+        logz, h = _running_evidence(lnl, logwt)
+        nc = np.full(len(pick), float(res.get('walks', np.nan)))
+        dlz = np.full(len(pick), np.nan)
+    if 'live_rows' in res:                                   # final live points, ascending ln L
+        K = int(res['nlive'])
+        lp = np.asarray(res['live_lnprob'][star])
+        order = np.argsort(lp, kind='stable')
+        lrows, llnl = np.asarray(res['live_rows'][star])[order], lp[order]
+        lv_f = (logvol[-1] if len(logvol) else 0.0)
+        llogvol = lv_f + np.log1p(-(np.arange(K) + 1.0) / (K + 1.0))
+        llogwt = llnl + lv_f - np.log(K)                   # every live point carries X_final / K (ns_finalize)
+        lz0 = logz[-1] if len(logz) else -np.inf
+        llogz, lh = _running_evidence(llnl, llogwt, lz0, (h[-1] + lz0) if len(h) else 0.0)
+        rest = np.append(np.logaddexp.accumulate(llogwt[::-1])[::-1][1:], -np.inf)
+        ldlz = np.logaddexp(llogz, rest) - llogz
+        rows = np.concatenate([rows, lrows]); lnl = np.concatenate([lnl, llnl])
+        logvol = np.concatenate([logvol, llogvol]); logwt = np.concatenate([logwt, llogwt])
+        h = np.concatenate([h, lh]); nc = np.concatenate([nc, np.ones(K)])
+        logz = np.concatenate([logz, llogz]); dlz = np.concatenate([dlz, ldlz])
+    if likeobj is not None:
+        nd = likeobj.ndim
+        dicts = [likeobj.parsdict_from(r[:nd], r[nd:] if likeobj.iso_bool else None) for r in rows]
+        names = list(dicts[0].keys()) if dicts else list(likeobj.parsdict_from(np.zeros(nd), np.ones(ncol - nd)
+                                                                               if likeobj.iso_bool else None).keys())
+        rows = np.array([[float(dd[k]) if isinstance(dd[k], (int, float, np.floating)) else np.nan for k in names]
+                         for dd in dicts]).reshape(len(dicts), len(names))
+    trail = np.column_stack([lnl, logvol, logwt, h, nc, logz, dlz])
+    cols = ['Iter'] + names + ['log(lk)', 'log(vol)', 'log(wt)', 'h', 'nc', 'log(z)', 'delta(log(z))']
+    return cols, np.column_stack([np.arange(len(rows)), rows, trail])
+
+
+def write_samples_file(path, res, star=0, likeobj=None):
+    """One star's samples file in the reference's layout (see ``samples_table``); needs store_samples."""
+    cols, tab = samples_table(res, star=star, likeobj=likeobj)
     with open(path, 'w') as f:
-        f.write('Iter ' + ' '.join(names) + ' log(lk) log(vol) log(wt) h nc log(z) delta(log(z))\n')
-        if len(dead) and isinstance(dead[0], np.ndarray) and dead[0].ndim == 2:
-            ncol = len(names)
-            for it, r in enumerate(dead[star]):
-                f.write('%d ' % it + ' '.join('%.10g' % v for v in r[:ncol]) +
-                        ' %.10g %.10g %.10g nan nan nan nan\n' % (r[ncol], r[ncol + 1], r[ncol + 2]))
-            return
-        it = 0
-        for act, row, lnl, logvol, logwt in dead:
-            k = np.flatnonzero(act == star)
-            if len(k) == 0:
-                continue
-            k = k[0]
-            f.write('%d ' % it + ' '.join('%.10g' % v for v in row[k]) +
-                    ' %.10g %.10g %.10g nan nan nan nan\n' % (lnl[k], logvol[k], logwt[k]))
-            it += 1
+        f.write(' '.join(cols) + '\n')                      # header of fitstar._initoutput (fitstar.py:235-242)
+        for r in tab:
+            f.write('%d ' % int(r[0]) + ' '.join(repr(float(v)) for v in r[1:-7]) +
+                    ' {0} {1} {2} {3} {4} {5} {6} \n'.format(*[repr(float(v)) for v in r[-7:-3]] +
+                                                              [repr(int(r[-3])) if np.isfinite(r[-3]) else 'nan'] +
+                                                              [repr(float(v)) for v in r[-2:]]))

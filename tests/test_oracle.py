@@ -198,3 +198,24 @@ def test_reference_copy_and_cpu_arm_object():
     a = np.array([R.lnlikefn(list(t)) for t in th])
     b = np.array([P.lnlikefn(list(t)) for t in th])
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('which', ['phot', 'spec'])
+def test_samples_file_header_is_the_references_parsdict_order(which, g_like_phot, g_like_spec):
+    """The samples-file columns (sampler.samples_table with a likelihood object) follow the key order of the
+    reference's own ``likeobj.parsdict`` after a successful call -- what ``fitstar._initoutput`` writes
+    (fitstar.py:235-242, 392-402) and demo/postproc.py:142-160 reads."""
+    from oracle import refshim
+    from oracle.cpu_baseline import make_likeobj
+    from minesweeper_b200.likelihood import parsdict_keys
+    if not refshim.available():
+        pytest.skip('no reference checkout and no oracle/_ref copy')
+    g = g_like_phot if which == 'phot' else g_like_spec
+    fitargs, fitpars, runbools = fit_setup(g)
+    R, kind = make_likeobj(fitargs, fitpars, runbools)
+    assert kind == 'reference'
+    i = int(np.flatnonzero(np.isfinite(g['lnl']))[0])
+    R.lnlikefn(list(g['theta'][i]))
+    want = list(R.parsdict.keys())
+    fitpars_i = [p for p in fitpars[0] if fitpars[1][p]]
+    assert parsdict_keys(fitpars_i, fitargs['fixedpars'], iso=True, ageweight=True) == want
