@@ -212,6 +212,7 @@ def test_catalog_sampler_accuracy_gate_at_benched_settings():
     good, demo = out[GATE_WALKS], out[5]
     assert good['bruteforce_ess_median'] > 200
     assert good['gate']['passed'], good
+    assert not demo['gate']['passed'], demo
     # shorter walks give narrower posteriors (insufficient decorrelation inside the likelihood constraint)
     assert np.median(list(demo['std_ratio_median'].values())) < np.median(list(good['std_ratio_median'].values())) + 0.02
     # the truth z-score of the exact (brute-force) posterior agrees with the sampler's and is not ~1 for every parameter
