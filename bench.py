@@ -281,10 +281,28 @@ def main():
     B = args.batch
     theta_np = synth.draw_theta_phot(B, seed=3 + rank, box=box)
     theta = torch.from_numpy(theta_np).to(dev)
-    # Results are double-buffered and the one collective of the path (the gather of lnL) runs on a side stream,
-    # so the gather of step k overlaps the kernels of step k + 1; the last timed step waits for every gather.
+    # Results are double-buffered.  The one collective of the path (the gather of lnL) is fused into the likelihood
+    # kernel: its epilogue stores lnL into every rank's gather buffer through peer-mapped symmetric memory
+    # (distributed.PeerGather); only a small symmetric-memory barrier follows, on a side stream, overlapping the next
+    # step.  Fallback when symmetric memory is unavailable: all_gather_into_tensor (NCCL) on the side stream.
     lnl_bufs = [torch.empty(B, dtype=torch.float64, device=dev) for _ in range(2)]
-    gathered = [torch.empty(B * world, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    peer = None
+    gathered = None
+    gather_kind = 'none'
+    if world > 1:
+        try:
+            if os.environ.get('MS_BENCH_GATHER', 'peer') != 'peer' or args.precision not in ('tc', 'tc16'):
+                raise RuntimeError('peer gather not selected')
+            from minesweeper_b200.distributed import PeerGather
+            peer = PeerGather(B, dev)
+            gather_kind = ('fused into the photometry kernel: its epilogue stores lnL into every rank\'s gather buffer over '
+                           'NVLink (peer-mapped symmetric memory, %d bytes per rank per step out and in); a '
+                           'symmetric-memory barrier on a side stream orders the ranks' % peer.bytes_per_rank_per_step)
+        except Exception as e:
+            peer = None
+            gathered = [torch.empty(B * world, dtype=torch.float64, device=dev) for _ in range(2)]
+            gather_kind = 'all_gather_into_tensor(lnL) per step (NCCL), on a side stream, overlapping the next step [%s]' % (
+                type(e).__name__)
     comm = torch.cuda.Stream(dev) if world > 1 else None
     gather_done = [None, None]
     nstep = [0]
@@ -295,14 +313,19 @@ def main():
         nstep[0] += 1
         main = torch.cuda.current_stream()
         if gather_done[i] is not None:
-            main.wait_event(gather_done[i])                             # this buffer's previous gather has read it
+            main.wait_event(gather_done[i])                             # this buffer's previous gather is complete
+        if peer is not None:
+            peer.arm(eng, i)
         eng.lnlike_batch(theta, L._colmap, L._fixed, L._flags, want_derived=False, out=lnl_bufs[i])
-        if world > 1:                                                   # the only collective: gather results
+        if world > 1:
             ready = torch.cuda.Event()
             ready.record(main)
             with torch.cuda.stream(comm):
                 comm.wait_event(ready)
-                dist.all_gather_into_tensor(gathered[i], lnl_bufs[i])
+                if peer is not None:
+                    peer.complete(i)                                    # every rank's stores into buffer i have landed
+                else:
+                    dist.all_gather_into_tensor(gathered[i], lnl_bufs[i])
                 gather_done[i] = torch.cuda.Event()
                 gather_done[i].record(comm)
 
@@ -334,6 +357,19 @@ def main():
         e1.record()
     barrier()
     lnl = lnl_bufs[(nstep[0] - 1) & 1]
+    if peer is not None:
+        # the fused gather delivered this rank's block to itself and every peer's block here
+        gi = (nstep[0] - 1) & 1
+        torch.cuda.synchronize()
+        dist.barrier()
+        gat = peer.gathered(gi)
+        assert torch.equal(gat[rank * B:(rank + 1) * B], lnl), 'fused gather: own block differs'
+        chk = torch.stack([gat[r * B:(r + 1) * B][torch.isfinite(gat[r * B:(r + 1) * B])].sum() for r in range(world)])
+        ref = torch.zeros(world, dtype=torch.float64, device=dev)
+        ref[rank] = lnl[torch.isfinite(lnl)].sum()
+        dist.all_reduce(ref)
+        assert torch.allclose(chk, ref, rtol=1e-12), 'fused gather: a peer block differs from its owner\'s result'
+        eng.set_lnl_peers()
     ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
     launches = eng.launch_count() - l0
     prof = eng.profile_read()
@@ -496,7 +532,7 @@ def main():
                    'tc16': 'f16 (fp32 accumulate)'}[args.precision], data='synthetic',
             config=dict(workload=workload_name(args, fitargs['MISTpath']), precision=args.precision,
                         l2='flushed between steps (256 MiB memset outside the timed events)',
-                        collective='all_gather_into_tensor(lnL) per step, on a side stream, overlapping the next step' if world > 1 else 'none',
+                        collective=gather_kind,
                         host_affinity=('%d cores local to the GPU' % len(numa_cores)) if numa_cores else 'default',
                         flop_per_eval=flop_pt),
             clocks=clocks,

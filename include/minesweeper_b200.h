@@ -252,6 +252,16 @@ int ms_set_fusion(ms_ctx *ctx, int enable);
  * spectra) = radix-8 transform, two CTAs per SM (falls back to 1 when two do not fit in shared memory). */
 int ms_set_spec_fast(ms_ctx *ctx, int enable);
 
+/* Multi-GPU gather fused into the likelihood kernel (the path's one collective is the gather of
+ * lnL).  peers[0 .. n) are device pointers, valid in THIS process, to every rank's gather buffer (peer memory mapped
+ * over NVLink, e.g. torch symmetric memory); while set, the tensor-core photometry kernel stores each lnL[p] also at
+ * peers[r][offset + p] for every r, so the gathered vector materialises on all GPUs as the tiles finish -- no NCCL
+ * kernel takes SMs from the persistent kernel and no separate copy runs.  The caller orders the ranks afterwards (a
+ * barrier on the stream).  n = 0 clears.  Only MS_PREC_TC / TC16 photometry batches honour it; other paths return
+ * MS_ESTATE while peers are set. */
+#define MS_MAX_PEERS 8
+int ms_set_lnl_peers(ms_ctx *ctx, const uint64_t *peers, int n, int64_t offset);
+
 /* Scratch policy.  A ctx grows its per-batch scratch on demand (cudaFree + cudaMalloc inside the call), which
  * is illegal while `stream` captures a CUDA graph and unsafe once a captured graph has baked the pointers in.
  * ms_reserve pre-sizes every scratch buffer for batches of up to max_batch rows; with lock != 0 the buffers are

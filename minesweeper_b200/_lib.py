@@ -125,6 +125,7 @@ PROTOTYPES = {
     'ms_reserve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
     'ms_set_fusion': (C.c_int, [C.c_void_p, C.c_int]),
+    'ms_set_lnl_peers': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int64]),
     'ms_set_spec_fast': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_enable': (C.c_int, [C.c_void_p, C.c_int]),
     'ms_profile_read': (C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int64)]),

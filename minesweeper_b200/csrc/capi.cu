@@ -326,6 +326,13 @@ extern "C" int ms_set_spec_fast(ms_ctx *ctx, int enable) {
     return MS_OK;
 }
 
+extern "C" int ms_set_lnl_peers(ms_ctx *ctx, const uint64_t *peers, int n, int64_t offset) {
+    if (!ctx || n < 0 || n > MS_MAX_PEERS || (n > 0 && !peers) || offset < 0) { ms_set_error("bad arguments"); return MS_EINVAL; }
+    for (int i = 0; i < MS_MAX_PEERS; ++i) ctx->peers[i] = i < n ? reinterpret_cast<double *>(peers[i]) : nullptr;
+    ctx->npeers = n; ctx->peer_off = offset;
+    return MS_OK;
+}
+
 extern "C" int ms_set_fusion(ms_ctx *ctx, int enable) {
     if (!ctx) { ms_set_error("bad arguments"); return MS_EINVAL; }
     ctx->fuse_interp = enable ? 1 : 0;
@@ -557,6 +564,10 @@ extern "C" int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double 
         if ((rc = launch_spec(ctx, sa, B, st))) return rc;
     }
     const int agew = iso && flags->ageweight;
+    if (ctx->npeers && !(flags->phot && ctx->precision >= MS_PREC_TC)) {
+        ms_set_error("lnL peers are set (ms_set_lnl_peers) but this batch does not end in the tensor-core photometry kernel");
+        return MS_ESTATE;
+    }
     if (flags->phot) {   // photometry is the last term: it also writes lnL
         PhotArgs pa{ctx->scr_pars, star_slot, nullptr, chi2};
         pa.lnL = lnL; pa.ageweight = agew; pa.slot0 = flags->slot;

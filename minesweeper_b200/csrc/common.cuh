@@ -81,6 +81,7 @@ struct ms_ctx {
     int device = 0;
     int precision = MS_PREC_F32;
     int fuse_interp = 1;           // ms_set_fusion
+    double *peers[MS_MAX_PEERS] = {nullptr}; int npeers = 0; int64_t peer_off = 0;   // ms_set_lnl_peers
     bool scratch_locked = false;   // ms_reserve(..., lock = 1): per-batch scratch may no longer grow
     int sm_count = 148;
     GridDev grid;

@@ -136,6 +136,9 @@ struct TcArgs {
     const double *pars; const int32_t *star_slot;
     double *mags; double *chi2; double *lnL; int ageweight;
     int slot0, nslots;                 // constant slot when star_slot is nullptr; loaded slots (bounds check)
+    // multi-GPU gather fused into the epilogue: lnL[p] is also stored at peers[r][peer_off + p] for every rank r of the
+    // box (peer memory mapped over NVLink / NVSwitch; ms_set_lnl_peers).  No collective kernel, no copy.
+    double *peers[MS_MAX_PEERS]; int npeers; int64_t peer_off;
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
     double xmin[8], xscale[8];
@@ -495,6 +498,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     if (slot < 0) l = ms_nan();
                 }
                 a.lnL[p] = l;
+                for (int rk = 0; rk < a.npeers; ++rk) a.peers[rk][a.peer_off + p] = l;      // posted writes to every rank
             } else if (ok && a.chi2) {
                 a.chi2[p] += slot < 0 ? ms_nan() : chi2;
             }
@@ -593,6 +597,8 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
     TcArgs ka;
     ka.pars = a.pars; ka.star_slot = a.star_slot; ka.mags = a.mags; ka.ageweight = a.ageweight;
     ka.slot0 = a.slot0; ka.nslots = ctx->nslots;
+    ka.npeers = a.lnL ? ctx->npeers : 0; ka.peer_off = ctx->peer_off;
+    for (int i = 0; i < MS_MAX_PEERS; ++i) ka.peers[i] = i < ka.npeers ? ctx->peers[i] : nullptr;
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
     ka.d_in = n.d_in; ka.nb_total = n.nb;

@@ -60,6 +60,47 @@ def sharded_lnlike(fn, theta, group=None):
     return gather_rows(lnl, n, group=group)
 
 
+class PeerGather(object):
+    """The path's one collective -- the gather of lnL -- without a collective kernel.
+
+    Every rank owns a gather buffer ``[world * rows_per_rank]`` f64 in symmetric memory (torch's
+    ``_symmetric_memory``: the same allocation mapped into every process of the box over NVLink / NVSwitch).  The
+    tensor-core photometry kernel is handed the peer-mapped addresses of all of them (``Engine.set_lnl_peers``) and its
+    epilogue stores each lnL[p] at ``rank * rows_per_rank + p`` of EVERY rank's buffer: the gathered vector
+    materialises on all GPUs while the tiles finish, no NCCL kernel competes with the persistent kernel for SMs and
+    no copy runs afterwards.  ``complete(i)`` orders the ranks (symmetric-memory barrier on the current stream: one
+    small CTA) so that buffer i is whole everywhere.  Two buffers by default so the barrier of step k can overlap
+    the kernel of step k + 1.  Traffic: (world - 1) * rows_per_rank * 8 B out and in per rank and step."""
+
+    def __init__(self, rows_per_rank, device, group=None, buffers=2):
+        import torch.distributed._symmetric_memory as symm
+        self.rank, self.size = world()
+        if self.size > 8:
+            raise ValueError('PeerGather supports up to 8 ranks (one box)')
+        self.n = int(rows_per_rank)
+        g = group if group is not None else dist.group.WORLD
+        self.bufs, self.hdls = [], []
+        for _ in range(buffers):
+            t = symm.empty(self.size * self.n, dtype=torch.float64, device=device)
+            self.hdls.append(symm.rendezvous(t, g))
+            self.bufs.append(t)
+
+    def arm(self, engine, i):
+        """Point the engine's likelihood kernel at buffer i of every rank."""
+        engine.set_lnl_peers([int(p) for p in self.hdls[i].buffer_ptrs], offset=self.rank * self.n)
+
+    def complete(self, i):
+        """All ranks have finished writing buffer i (enqueued on the current stream)."""
+        self.hdls[i].barrier(channel=i)
+
+    def gathered(self, i):
+        return self.bufs[i]
+
+    @property
+    def bytes_per_rank_per_step(self):
+        return (self.size - 1) * self.n * 8
+
+
 def star_blocks(n_stars, rank=None, size=None):
     """Catalog mode: the block of star indices pinned to this rank's device."""
     r, s = world()

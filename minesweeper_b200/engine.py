@@ -271,6 +271,12 @@ class Engine(object):
         interpolation kernel followed by the MLP kernel."""
         check(self.lib.ms_set_fusion(self._ctx, int(bool(on))))
 
+    def set_lnl_peers(self, ptrs=(), offset=0):
+        """Fused gather: the tensor-core photometry kernel also stores lnL[p] at ``ptrs[r] + 8 * (offset + p)`` for every
+        rank r (device pointers to peer-mapped buffers, see distributed.PeerGather); ``set_lnl_peers()`` clears."""
+        arr = (C.c_uint64 * max(len(ptrs), 1))(*[int(p) for p in ptrs])
+        check(self.lib.ms_set_lnl_peers(self._ctx, arr, len(ptrs), int(offset)))
+
     def set_spec_fast(self, on=True):
         """f32-class modes: fast broadening kernel (default) or the generic FFT kernel for every row."""
         check(self.lib.ms_set_spec_fast(self._ctx, int(on)))
