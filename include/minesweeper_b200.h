@@ -132,6 +132,15 @@ int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, const double 
                 int nb, const double *obs_wave, const double *obs_flux,
                 const double *obs_eflux, int n_obs);
 
+/* Wavelength-dependent line-spread function of a star (array-valued Inst_R: GenMod.genspec passes it through to the
+ * predictor, genmod.py:74-77, which smooths with smoothspec(..., smoothtype='lsf'), smoothing.py:125-128, 412-514).
+ * The reference's warped wavelength axis depends only on the net's grid and sigma(lambda), so it is prepared once on the
+ * host (minesweeper_b200/lsf.py): lam[nx] = wavelengths of the nx = 2^k uniform points of the warped coordinate,
+ * (idx, frac)[nx] = linear-interpolation map from the net's native pixels onto them, x_per_sigma = kernel width in the
+ * warped coordinate.  While set, batches against this slot ignore the scalar Inst_R.  nx = 0 clears. */
+int ms_set_lsf(ms_ctx *ctx, int star_slot, int nx, const double *lam, const int32_t *idx, const double *frac,
+               double x_per_sigma);
+
 /* Photometry of many stars at once (catalog mode): obs_mag / obs_err[nstars][nb] host arrays go to
  * slots first_slot .. first_slot + nstars - 1. */
 int ms_set_stars_phot(ms_ctx *ctx, int first_slot, int nstars, const double *obs_mag, const double *obs_err,

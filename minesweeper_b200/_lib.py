@@ -117,6 +117,7 @@ PROTOTYPES = {
     'ms_lnprob_batch_stars': (C.c_int, [C.c_void_p, C.POINTER(Flags), C.c_void_p, C.c_int64, C.c_int, c_ip, c_dp,
                                         C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ms_set_lsf': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_double]),
     'ms_set_stars_phot': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int]),
     'ms_ns_propose': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_uint64, C.c_void_p]),
     'ms_ns_accept': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),

@@ -305,7 +305,7 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(ctx->obs_mag); cudaFree(ctx->obs_err2); cudaFree(ctx->stars_dev); cudaFree(ctx->scr_fb);
     for (StarDev &s : ctx->stars) {
         cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2);
-        cudaFree(s.cheb_x);
+        cudaFree(s.cheb_x); cudaFree(s.lsf_lam); cudaFree(s.lsf_frac); cudaFree(s.lsf_idx);
     }
     cudaFree(ctx->scr_derived); cudaFree(ctx->scr_pars); cudaFree(ctx->scr_chi2); cudaFree(ctx->scr_chi2g);
     cudaFree(ctx->scr_flux); cudaFree(ctx->scr_hid); cudaFree(ctx->scr_theta); cudaFree(ctx->scr_out);
@@ -365,7 +365,8 @@ static int refresh_star_views(ms_ctx *ctx) {
     std::vector<StarView> v(ctx->stars.size());
     for (size_t i = 0; i < v.size(); ++i) {
         const StarDev &s = ctx->stars[i];
-        v[i] = StarView{s.n_obs, 0, s.obs_wave, s.obs_lnwave, s.obs_flux, s.obs_err2, s.cheb_x, s.wmin, s.wmax};
+        v[i] = StarView{s.n_obs, 0, s.obs_wave, s.obs_lnwave, s.obs_flux, s.obs_err2, s.cheb_x, s.wmin, s.wmax,
+                        s.lsf_nx, 0, s.lsf_lam, s.lsf_frac, s.lsf_idx, s.lsf_xps};
     }
     if ((int)v.size() > ctx->stars_dev_n) {
         cudaFree(ctx->stars_dev);
@@ -419,6 +420,7 @@ extern "C" int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, co
     if ((int)ctx->stars.size() <= star_slot) ctx->stars.resize(star_slot + 1);
     StarDev &s = ctx->stars[star_slot];
     cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2); cudaFree(s.cheb_x);
+    cudaFree(s.lsf_lam); cudaFree(s.lsf_frac); cudaFree(s.lsf_idx);
     s = StarDev();
     s.set = true;
     if (n_obs > 0) {
@@ -442,6 +444,34 @@ extern "C" int ms_set_star(ms_ctx *ctx, int star_slot, const double *obs_mag, co
         if ((rc = upload(&s.obs_err2, e2.data(), n_obs))) return rc;
         if ((rc = upload(&s.cheb_x, cx.data(), n_obs))) return rc;
         s.n_obs = n_obs; s.wmin = wmin; s.wmax = wmax;
+    }
+    return refresh_star_views(ctx);
+}
+
+// Wavelength-dependent LSF of a star slot (array Inst_R; smooth_lsf_fft, smoothing.py:412-514): the theta-independent
+// warped grid prepared on the host (minesweeper_b200/lsf.py).  nx = 0 clears.
+extern "C" int ms_set_lsf(ms_ctx *ctx, int star_slot, int nx, const double *lam, const int32_t *idx, const double *frac,
+                          double x_per_sigma) {
+    if (!ctx || star_slot < 0 || star_slot >= (int)ctx->stars.size() || !ctx->stars[star_slot].set) {
+        ms_set_error("ms_set_lsf: star slot %d is not set (call ms_set_star first)", star_slot);
+        return MS_ESTATE;
+    }
+    if (nx < 0 || (nx & (nx - 1)) != 0 || (nx > 0 && (!lam || !idx || !frac || !(x_per_sigma > 0.0)))) {
+        ms_set_error("ms_set_lsf: nx must be a power of two with its three arrays");
+        return MS_EINVAL;
+    }
+    MS_CUDA(cudaSetDevice(ctx->device));
+    StarDev &s = ctx->stars[star_slot];
+    cudaFree(s.lsf_lam); cudaFree(s.lsf_frac); cudaFree(s.lsf_idx);
+    s.lsf_lam = s.lsf_frac = nullptr; s.lsf_idx = nullptr; s.lsf_nx = 0; s.lsf_xps = 0;
+    if (nx > 0) {
+        for (int k = 0; k < nx; ++k)
+            if (idx[k] < 0 || idx[k] > ctx->spec.npix - 2) { ms_set_error("ms_set_lsf: idx[%d] out of range", k); return MS_EINVAL; }
+        int rc;
+        if ((rc = upload(&s.lsf_lam, lam, (size_t)nx))) return rc;
+        if ((rc = upload(&s.lsf_frac, frac, (size_t)nx))) return rc;
+        if ((rc = upload(&s.lsf_idx, (const int *)idx, (size_t)nx))) return rc;
+        s.lsf_nx = nx; s.lsf_xps = x_per_sigma;
     }
     return refresh_star_views(ctx);
 }

@@ -68,6 +68,10 @@ struct StarDev {
     double *obs_wave = nullptr, *obs_lnwave = nullptr, *obs_flux = nullptr, *obs_err2 = nullptr;
     double *cheb_x = nullptr;      // wavelength rescaled to [-1, 1] (fitutils.py:13-14)
     double wmin = 0, wmax = 0;
+    // LSF mode (ms_set_lsf): lam[nx] warped wavelengths, (idx, frac)[nx] resampling map from the native grid
+    int lsf_nx = 0;
+    double *lsf_lam = nullptr, *lsf_frac = nullptr; int *lsf_idx = nullptr;
+    double lsf_xps = 0;
 };
 
 // device-side view of one star slot's observed spectrum (table ctx->stars_dev, indexed by slot)
@@ -75,6 +79,10 @@ struct StarView {
     int n_obs, pad_;
     const double *obs_wave, *obs_lnwave, *obs_flux, *obs_err2, *cheb_x;
     double wmin, wmax;
+    // wavelength-dependent LSF (array Inst_R, ms_set_lsf): warped-grid map, nx = 0 when unset
+    int lsf_nx, pad2_;
+    const double *lsf_lam, *lsf_frac; const int *lsf_idx;
+    double lsf_xps;
 };
 
 struct ms_ctx {

@@ -29,6 +29,8 @@ struct SmoothArgs {
     double *chi2;                  // [B] or nullptr
     // row indirection (fallback launches of the generic kernel): rows[0 .. *nrows) or nullptr = all rows
     const int *rows, *nrows;
+    // LSF mode: the generic kernel stops after the rotational stage and writes the native-grid spectrum here ([B][npix] T)
+    void *native_out;
 };
 
 // Transfer function of the rotational profile, smoothing.py:541-548 (f32: 4-point Lagrange on a table).

@@ -427,6 +427,12 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
             __syncthreads();
         }
 
+        if (a.native_out) {                                   // LSF mode: the instrumental stage runs in spec_lsf_kernel
+            T *orow = static_cast<T *>(a.native_out) + (size_t)p * npix;
+            for (int i = threadIdx.x; i < npix; i += blockDim.x) orow[i] = fr[i];
+            __syncthreads();
+            continue;
+        }
         // ---- Doppler shift + instrumental broadening + resampling to the observed pixels ----
         const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
         const double lnscale = log(scale);
@@ -526,6 +532,95 @@ spec_smooth_kernel(SmoothArgs a, int nB) {
     }
 }
 
+// ---- wavelength-dependent line-spread function (array Inst_R): smooth_lsf_fft, smoothing.py:412-514 --------------
+// The reference warps the wavelength axis by the cumulative distribution of d(lambda) / sigma(lambda) so that the
+// kernel has constant width, resamples the spectrum on nx = 2^k uniform points of the warped coordinate, smooths by
+// FFT with a Gaussian of `x_per_sigma` and interpolates onto the observed wavelengths.  Everything up to the resampling
+// map depends only on the net's grid and the star's sigma array (a Doppler factor s rescales the warped wavelengths
+// lam -> s lam and the kernel width x_per_sigma -> x_per_sigma / s, nothing else), so the host prepares the map once
+// (minesweeper_b200/lsf.py -> ms_set_lsf) and this kernel does, per point: gather-resample, Gaussian smoothing, search
+// + interpolation at the observed pixels, blaze, chi-square.  nx = 2^ceil(log2(2 / x_per_sigma)) puts the kernel width
+// at 2 .. 4 grid pixels, where the reference's circular FFT convolution equals the direct sum with Gaussian taps
+// (Poisson summation, error exp(-pi^2 sigma^2 / 2) times the spectrum's Nyquist content); taps are cut at 5.5 sigma in
+// f32 and 8.5 sigma in f64.
+template <typename T>
+__global__ void __launch_bounds__(256)
+spec_lsf_kernel(SmoothArgs a, int nB) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *sx = reinterpret_cast<T *>(smem_raw);                  // spectrum on the warped grid
+    __shared__ double gt[64];
+    __shared__ double red[8];
+    for (int p = blockIdx.x; p < nB; p += gridDim.x) {
+        const double *r = a.pars + (size_t)p * MS_NPARS;
+        const int slot = a.star_slot ? a.star_slot[p] : a.slot0;
+        const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
+        const StarView sv = a.stars[slot_ok ? slot : 0];
+        const int nobs = slot_ok ? sv.n_obs : 0, nx = sv.lsf_nx;
+        if (r[PV_TEFF] == ms_inf() || nobs <= 0 || nx <= 0) {
+            if (a.flux_out && slot_ok)
+                for (int j = threadIdx.x; j < nobs; j += blockDim.x) a.flux_out[(size_t)p * nobs + j] = ms_nan();
+            if (a.chi2 && r[PV_TEFF] != ms_inf() && threadIdx.x == 0 && (!slot_ok || nx <= 0)) a.chi2[p] = ms_nan();
+            continue;
+        }
+        const double vrad = r[PV_VRAD];
+        const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
+        const T *frow = static_cast<const T *>(a.flux_native) + (size_t)p * a.npix;
+        for (int k = threadIdx.x; k < nx; k += blockDim.x) {
+            const int i = sv.lsf_idx[k];
+            const T f = (T)sv.lsf_frac[k];
+            const T v0 = frow[i], v1 = frow[i + 1];
+            sx[k] = v0 + (v1 - v0) * f;
+        }
+        const double spx = sv.lsf_xps / scale * (double)nx;  // kernel width in grid pixels
+        const int ntap = min(63, (int)ceil((sizeof(T) == 4 ? 5.5 : 8.5) * spx));
+        if (threadIdx.x <= ntap) {
+            const double t = (double)threadIdx.x / spx;
+            gt[threadIdx.x] = exp(-0.5 * t * t) / (spx * 2.5066282746310002);
+        }
+        __syncthreads();
+        double csum = 0.0;
+        const int mask = nx - 1;
+        const double *lam = sv.lsf_lam;
+        for (int j = threadIdx.x; j < nobs; j += blockDim.x) {
+            const double x = sv.obs_wave[j] / scale;          // position on the unshifted warped wavelengths
+            int lo = 0, hi = nx - 1;                          // largest i with lam[i] <= x (np.interp semantics)
+            double m;
+            auto conv = [&](int i) {
+                double acc = 0.0;
+                for (int t = -ntap; t <= ntap; ++t) acc += gt[t < 0 ? -t : t] * (double)sx[(i - t) & mask];
+                return acc;
+            };
+            if (!(x == x)) m = ms_nan();
+            else if (x <= lam[0]) m = conv(0);
+            else if (x >= lam[nx - 1]) m = conv(nx - 1);
+            else {
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (lam[mid] <= x) lo = mid; else hi = mid; }
+                const double l0 = lam[lo], l1 = lam[lo + 1];
+                const double c0 = conv(lo), c1 = conv(lo + 1);
+                m = c0 + (c1 - c0) * ((x - l0) / (l1 - l0));
+            }
+            if (a.modpoly) m *= cheb_eval(sv.cheb_x[j], r + PV_PC0, a.n_pc);
+            if (a.flux_out) a.flux_out[(size_t)p * nobs + j] = m;
+            if (a.chi2) {
+                const double d = m - sv.obs_flux[j];
+                const double t = (d * d) / sv.obs_err2[j];
+                if (t == t) csum += t;
+            }
+        }
+        if (a.chi2) {
+            for (int o = 16; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = csum;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double tot = 0.0;
+                for (int w = 0; w < 8; ++w) tot += red[w];
+                a.chi2[p] += tot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 template <typename T>
@@ -595,6 +690,19 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
     }
     auto kern = spec_smooth_kernel<T>;
     if (generic_fits) MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // LSF mode (array Inst_R registered with ms_set_lsf for the star): all-or-nothing per batch
+    bool lsf = false;
+    int lsf_nx_max = 0;
+    if (!a.star_slots) lsf = ctx->stars[a.star_slot].lsf_nx > 0, lsf_nx_max = ctx->stars[a.star_slot].lsf_nx;
+    else {
+        int n_lsf = 0, n_spec = 0;
+        for (const StarDev &sd : ctx->stars) {
+            if (sd.n_obs > 0) { ++n_spec; if (sd.lsf_nx > 0) { ++n_lsf; if (sd.lsf_nx > lsf_nx_max) lsf_nx_max = sd.lsf_nx; } }
+        }
+        if (n_lsf && n_lsf != n_spec) { ms_set_error("per-row star slots: either every star has an LSF array or none"); return MS_EINVAL; }
+        lsf = n_lsf > 0;
+    }
+    if (lsf && (size_t)lsf_nx_max * sizeof(T) > 200 * 1024) { ms_set_error("LSF resampling length %d too large", lsf_nx_max); return MS_EINVAL; }
     int *fb_count = ctx->scr_fb, *fb_rows = ctx->scr_fb + 4;
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
@@ -614,9 +722,26 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         sa.modpoly = a.modpoly; sa.n_pc = a.n_pc;
         sa.flux_out = a.flux ? a.flux + b0 * ctx->stars[a.star_slot].n_obs : nullptr;
         sa.chi2 = a.chi2 ? a.chi2 + b0 : nullptr;
-        sa.rows = nullptr; sa.nrows = nullptr;
+        sa.rows = nullptr; sa.nrows = nullptr; sa.native_out = nullptr;
         KernelTimer timer_(ctx, MS_K_SPEC_SMOOTH, st);
-        if (fast) {
+        if (lsf) {
+            // array Inst_R: rotational stage by the generic kernel, written back onto the native grid in place,
+            // then the LSF kernel (warped-grid resampling, Gaussian smoothing, observed pixels, chi-square)
+            if (!generic_fits) { ms_set_error("LSF mode needs the generic broadening kernel, which does not fit"); return MS_EINVAL; }
+            int64_t grid = (int64_t)ctx->sm_count;
+            if (grid > nb) grid = nb;
+            SmoothArgs rot = sa;
+            rot.native_out = ctx->scr_flux; rot.flux_out = nullptr; rot.chi2 = nullptr;
+            kern<<<(unsigned)grid, SmoothCfg<T>::THREADS, smem, st>>>(rot, (int)nb);
+            ctx->launches++;
+            MS_CUDA(cudaGetLastError());
+            const size_t lsmem = (size_t)lsf_nx_max * sizeof(T);
+            auto lk = spec_lsf_kernel<T>;
+            MS_CUDA(cudaFuncSetAttribute(lk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+            int64_t lgrid = (int64_t)ctx->sm_count * (lsmem > 100 * 1024 ? 1 : 2);
+            if (lgrid > nb) lgrid = nb;
+            lk<<<(unsigned)lgrid, 256, lsmem, st>>>(sa, (int)nb);
+        } else if (fast) {
             // fast kernel; rows it declines (unusual broadening widths) go through the generic FFT kernel
             MS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
             if ((rc = launch_spec_fast(ctx, sa, (int)nb, fb_rows, fb_count, st))) return rc;

@@ -94,6 +94,7 @@ class Engine(object):
                              int(bool(specnet['logt_input'])))
             keep += list(w.values()) + [xmin, xmax, wave]
             self.spec_shape = (d_in, h, npix)
+            self.spec_wave = wave.copy()
         self._ctx = C.c_void_p()
         check(self.lib.ms_create(C.byref(self._ctx), self.device_index, _lib.PRECISIONS[precision],
                                  C.byref(gd) if gd else None, C.byref(pd) if pd else None,
@@ -142,6 +143,16 @@ class Engine(object):
         self.n_obs[int(slot)] = n_obs
         if nb:
             self.nslots_phot = max(self.nslots_phot, int(slot) + 1)
+
+    def set_lsf(self, slot, sigma=None):
+        """Wavelength-dependent LSF of a star (array-valued Inst_R, genmod.py:74-77): ``sigma[npix]`` on the spectral
+        net's wavelength grid, in wavelength units; None clears.  See minesweeper_b200/lsf.py."""
+        if sigma is None:
+            check(self.lib.ms_set_lsf(self._ctx, int(slot), 0, None, None, None, 0.0))
+            return
+        from . import lsf
+        nx, lam, idx, frac, xps = lsf.prepare(self.spec_wave, sigma)
+        check(self.lib.ms_set_lsf(self._ctx, int(slot), nx, _dp(lam), idx.ctypes.data_as(_lib.c_ip), _dp(frac), xps))
 
     def set_stars_phot(self, obs_mag, obs_err, first_slot=0):
         """Catalog mode: obs_mag / obs_err[nstars, nb] (NaN = unobserved) into consecutive slots."""

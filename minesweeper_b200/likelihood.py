@@ -77,6 +77,14 @@ class likelihood(object):
             obs_flux=fitargs['obs_flux_fit'] if self.spec_bool else None,
             obs_eflux=fitargs['obs_eflux_fit'] if self.spec_bool else None)
 
+        # array-valued Inst_R (fixed): the wavelength-dependent LSF mode of genspec (genmod.py:74-77)
+        self.lsf_sigma = None
+        inst = self.fixedpars.get('Inst_R', None) if isinstance(self.fixedpars, dict) else None
+        if self.spec_bool and inst is not None and np.ndim(inst) > 0:
+            self.lsf_sigma = np.asarray(inst, dtype=np.float64)
+            self.engine.set_lsf(self.slot, self.lsf_sigma)
+            self.fixedpars = dict(self.fixedpars)
+            self.fixedpars['Inst_R'] = np.nan              # the scalar slot of the parameter block is unused in LSF mode
         self.GM = GenMod(engine=self.engine, slot=self.slot)
         if self.spec_bool:
             self.GM._initspecnn(nnpath=fitargs.get('specANNpath'), NNtype=fitargs.get('NNtype'))

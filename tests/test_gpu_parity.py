@@ -810,3 +810,75 @@ def test_spectrum_fit_with_per_row_star_slots():
     assert np.abs(la[fin] - lb[fin]).min() > 1.0
     B_own = likelihood(fb, fitpars, rb, precision='tc', verbose=False)
     np.testing.assert_array_equal(B_own.lnlike_batch(th)[0].cpu().numpy(), lb)
+
+
+@pytest.mark.gpu
+def test_lsf_array_smoothing_vs_reference_goldens(g_smooth):
+    """array-valued Inst_R = wavelength-dependent LSF (smooth_lsf_fft,
+    smoothing.py:412-514, reached through genmod.py:74-77).  A net whose output is a constant spectrum isolates the
+    broadening chain; compared with the reference's own smoothspec(..., smoothtype='lsf') outputs
+    (tests/golden/smoothing.npz: lsf_out) and with the pinned port, also behind rotation and a Doppler shift."""
+    from oracle import smoothing_port
+    w, f, ow = g_smooth['wave'], g_smooth['flux'], g_smooth['outwave']
+    npix = len(w)
+    net = dict(w0=np.zeros((8, 4), np.float32), b0=np.zeros(8, np.float32),
+               w1=np.zeros((8, 8), np.float32), b1=np.zeros(8, np.float32),
+               w2=np.zeros((npix, 8), np.float32), b2=f.astype(np.float32),
+               xmin=np.zeros(4), xmax=np.ones(4), wavelength=w, resolution=float(g_smooth['r_inres']),
+               leak=0.01, logt_input=False)
+    f32 = net['b2'].astype(np.float64)
+    for prec, tol in (('f64', 2e-9), ('f32', 1e-5), ('tc', 1e-5)):
+        eng = _engine(specnet=net, precision=prec)
+        eng.set_star(0, obs_wave=ow, obs_flux=np.ones_like(ow), obs_eflux=np.ones_like(ow))
+        for k, (a, b) in enumerate(g_smooth['lsf_ab']):
+            sigma = a + b * (w - w[0])
+            eng.set_lsf(0, sigma)
+            rows = np.array([[5000., 4., 0., 0., 0.0, 0.0, np.nan, 12345.0],          # scalar Inst_R is ignored
+                             [5000., 4., 0., 0., 7.3, 4.2, np.nan, np.nan]])          # rotation + Doppler shift first
+            flux = eng.spec_model(rows).cpu().numpy()
+            ref = smoothing_port.smooth_lsf(w, f32, ow, sigma)
+            np.testing.assert_allclose(flux[0], ref, rtol=tol, atol=tol)
+            np.testing.assert_allclose(flux[0], g_smooth['lsf_out'][k], rtol=2e-6, atol=2e-6)
+            rot = smoothing_port.smooth_vsini(w, f32, 4.2)
+            ref2 = smoothing_port.smooth_lsf(w * (1.0 + 7.3 / 299792.458), rot, ow, sigma)
+            np.testing.assert_allclose(flux[1], ref2, rtol=tol, atol=tol)
+        eng.set_lsf(0, None)                                     # cleared: back to the scalar-R path
+        back = eng.spec_model(np.array([[5000., 4., 0., 0., 0.0, 0.0, np.nan, 35000.0]])).cpu().numpy()
+        np.testing.assert_allclose(back[0], smoothing_port.smooth_R(w, f32, 35000.0 * 2.355, ow,
+                                                                    inres=float(g_smooth['r_inres'])), rtol=tol, atol=tol)
+
+
+@pytest.mark.gpu
+def test_lnlike_with_lsf_array_inst_r_vs_per_point_oracle():
+    """likelihood(...) with fixedpars['Inst_R'] = array runs the LSF mode end to end (spectrum + photometry lnL)."""
+    from minesweeper_b200.likelihood import likelihood
+    from oracle import smoothing_port
+    from oracle.like_port import LikelihoodPort, blaze
+    fitargs, fitpars, rb, obs = _spec_fit(npix=4096, n_obs=400)
+    wave = fitargs['specANNpath']['wavelength']
+    sigma = 0.06 + 3e-5 * (wave - wave[0])
+    fa = dict(fitargs, fixedpars={'Inst_R': sigma})
+    L = likelihood(fa, fitpars, rb, precision='f64', verbose=False)
+    th = _spec_theta(60, 12)
+    lnl = L.lnlike_batch(th)[0].cpu().numpy()
+    # oracle: the port with a scalar R cannot express the LSF; assemble it from the pinned pieces
+    ref = LikelihoodPort(dict(fitargs, fixedpars={'Inst_R': 35000.0}), fitpars, rb)
+    PP = ref.PP
+    for i in range(0, 60, 5):
+        base = ref.lnlikefn(list(th[i]))                        # fills parsdict; gives the photometric part via difference
+        if not np.isfinite(base):
+            assert lnl[i] == base
+            continue
+        pd = ref.parsdict
+        nat = PP.predictspec(pd['Teff'], pd['log(g)'], pd['[Fe/H]'], pd['[a/Fe]'])
+        if pd['Vrot'] != 0.0:
+            nat = smoothing_port.smooth_vsini(PP.wavelength, nat, pd['Vrot'])
+        mod = smoothing_port.smooth_lsf(PP.wavelength * (1.0 + pd['Vrad'] / 299792.458), nat, obs['obs_wave'], sigma)
+        mod = mod * blaze([pd[k] for k in L.fitpars_i if 'pc' in k], obs['obs_wave'])
+        chi_spec = np.nansum((mod - obs['obs_flux']) ** 2 / obs['obs_eflux'] ** 2)
+        _, mod_r = ref.genspec([pd.get(k, np.nan) for k in ('Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic',
+                                                            'Inst_R')] + [pd[k] for k in L.fitpars_i if 'pc' in k],
+                               outwave=obs['obs_wave'], modpoly=True)
+        chi_r = np.nansum((mod_r - obs['obs_flux']) ** 2 / obs['obs_eflux'] ** 2)
+        want = base + 0.5 * chi_r - 0.5 * chi_spec
+        assert abs(lnl[i] - want) <= 1e-6 + 1e-9 * abs(want), (i, lnl[i], want)
