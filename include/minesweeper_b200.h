@@ -185,7 +185,10 @@ enum { MS_PRIOR_UNIFORM = 0,     /* p = lo, hi                        pv_uniform
        MS_PRIOR_GAUSSIAN,        /* p = loc, scale                    pv_gaussian                */
        MS_PRIOR_TGAUSSIAN,       /* p = lo, hi, loc, scale            pv_tgaussian, blaze coeffs */
        MS_PRIOR_EXP,             /* p = loc, scale                    pv_exp                     */
-       MS_PRIOR_LOGUNIFORM };    /* p = a, b                          pv_loguniform              */
+       MS_PRIOR_LOGUNIFORM,      /* p = a, b                          pv_loguniform              */
+       MS_PRIOR_BETA,            /* p = a, b, loc, scale              pv_beta (scipy.stats.beta.ppf, prior.py:198-203) */
+       MS_PRIOR_TABLE };         /* p = scale: scale * weighted quantile of the table of ms_set_prior_table
+                                    (Galactic distance prior: 1000 AP.gal_ppf(u), prior.py:333-336)           */
 typedef struct { int32_t kind; int32_t pad_; double p[4]; } ms_prior_col;
 
 /* value a prior term applies to: an MS_P_* id (sampled / fixed / isochrone-predicted label) or */
@@ -196,6 +199,26 @@ enum { MS_TERM_UNIFORM = 0,      /* p = lo, hi: -inf outside */
        MS_TERM_TGAUSSIAN_BOUNDS  /* p = lo, hi (spec / phot families apply the bounds only)  */ };
 typedef struct { int32_t value_id; int32_t kind; double p[4]; } ms_prior_term;
 #define MS_MAX_PRIOR_TERMS 32
+
+/* Tabulated inverse CDF for MS_PRIOR_TABLE columns: x[n] ascending and cdf[n] (cdf[0] = 0, non-decreasing), host
+ * arrays, copied; the transform is the linear interpolation np.interp(u, cdf, x) of Payne's weighted quantile
+ * (advancedpriors.py:665-670).  One table per ctx. */
+int ms_set_prior_table(ms_ctx *ctx, const double *x, const double *cdf, int n);
+
+/* Physically motivated additive priors of advancedpriors.py, evaluated per point inside the ln-prior kernel:
+ *   gal     AdvancedPriors.gal_lnprior(Dist / 1000) with coords = [] (thin + thick disk + halo number density along the
+ *           sight line (l, b) given at construction; advancedpriors.py:410-663, prior.py:413-446)
+ *   galage  + age_lnprior on 10^(log(Age) - 9) with the component membership probabilities (advancedpriors.py:776-833)
+ *   vrot    vrot_lnprior (Kraft break / giant / dwarf sigmoid; advancedpriors.py:691-733, prior.py:453-466)
+ *   alpha   alpha_lnprior (advancedpriors.py:672-688, prior.py:494-501)
+ * age_*: min, max, mean, sigma (sigma <= 0: uniform between min and max). */
+typedef struct {
+    int32_t gal, galage, vrot, alpha;
+    double Xp, Yp, Zp, sol_X, sol_Z;
+    double age_thin[4], age_thick[4], age_halo[4];
+    double vrot_dwarf[3], vrot_giant[3];             /* a, c, n */
+    double minalpha;
+} ms_adv_prior;
 
 /* u[B][ndim] in the unit cube -> theta[B][ndim] (device pointers); cols[ndim] host. */
 int ms_prior_transform(ms_ctx *ctx, const double *u, int64_t B, int ndim, const ms_prior_col *cols,
@@ -213,6 +236,12 @@ int ms_lnprob_batch_stars(ms_ctx *ctx, const ms_flags *flags, const double *thet
                           const int32_t *colmap, const double *fixed, const double *derived,
                           const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
                           const int32_t *star_slot, const double *star_plx, void *stream);
+
+/* As ms_lnprob_batch_stars, plus the advanced priors (adv may be NULL). */
+int ms_lnprob_batch_adv(ms_ctx *ctx, const ms_flags *flags, const double *theta, int64_t B, int ndim,
+                        const int32_t *colmap, const double *fixed, const double *derived,
+                        const ms_prior_term *terms, int nterms, int imf, const double *lnL, double *out,
+                        const int32_t *star_slot, const double *star_plx, const ms_adv_prior *adv, void *stream);
 
 /* ---- nested-sampling bookkeeping ---------------------------
  * Replaces the sequential part of dynesty's static sampler as driven by fitstar._runsampler

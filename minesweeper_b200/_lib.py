@@ -75,7 +75,14 @@ class PriorTerm(C.Structure):
     _fields_ = [('value_id', C.c_int32), ('kind', C.c_int32), ('p', C.c_double * 4)]
 
 
-PRIOR_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'exp': 3, 'loguniform': 4}
+class AdvPrior(C.Structure):
+    _fields_ = [('gal', C.c_int32), ('galage', C.c_int32), ('vrot', C.c_int32), ('alpha', C.c_int32),
+                ('Xp', C.c_double), ('Yp', C.c_double), ('Zp', C.c_double), ('sol_X', C.c_double), ('sol_Z', C.c_double),
+                ('age_thin', C.c_double * 4), ('age_thick', C.c_double * 4), ('age_halo', C.c_double * 4),
+                ('vrot_dwarf', C.c_double * 3), ('vrot_giant', C.c_double * 3), ('minalpha', C.c_double)]
+
+
+PRIOR_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'exp': 3, 'loguniform': 4, 'beta': 5, 'table': 6}
 TERM_KINDS = {'uniform': 0, 'gaussian': 1, 'tgaussian': 2, 'tgaussian_bounds': 3}
 MS_V_LOGAGE, MS_V_AGE, MS_V_PARALLAX = MS_NPARAM, MS_NPARAM + 1, MS_NPARAM + 2
 MS_MAX_PRIOR_TERMS = 32
@@ -118,6 +125,10 @@ PROTOTYPES = {
                                         C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     'ms_set_lsf': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_ip, c_dp, C.c_double]),
+    'ms_set_prior_table': (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int]),
+    'ms_lnprob_batch_adv': (C.c_int, [C.c_void_p, C.POINTER(Flags), C.c_void_p, C.c_int64, C.c_int, c_ip, c_dp,
+                                      C.c_void_p, C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.POINTER(AdvPrior), C.c_void_p]),
     'ms_set_stars_phot': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int]),
     'ms_ns_propose': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_uint64, C.c_void_p]),
     'ms_ns_accept': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),

@@ -303,6 +303,7 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(S.a1_fracd); cudaFree(S.a2_fracd); cudaFree(S.twiddle32); cudaFree(S.twiddle64);
     cudaFree(S.xms); cudaFree(S.rot_tab); cudaFree(S.twlev32); spec_tc_release(ctx);
     cudaFree(ctx->obs_mag); cudaFree(ctx->obs_err2); cudaFree(ctx->stars_dev); cudaFree(ctx->scr_fb);
+    cudaFree(ctx->ptab_x); cudaFree(ctx->ptab_cdf);
     for (StarDev &s : ctx->stars) {
         cudaFree(s.obs_wave); cudaFree(s.obs_lnwave); cudaFree(s.obs_flux); cudaFree(s.obs_err2);
         cudaFree(s.cheb_x); cudaFree(s.lsf_lam); cudaFree(s.lsf_frac); cudaFree(s.lsf_idx);

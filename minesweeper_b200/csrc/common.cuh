@@ -112,6 +112,7 @@ struct ms_ctx {
     double *scr_theta = nullptr;   size_t scr_theta_n = 0;     // for the host-buffer entry point
     double *scr_out = nullptr;     size_t scr_out_n = 0;
     int32_t *colmap_dev = nullptr; double *fixed_dev = nullptr;
+    double *ptab_x = nullptr, *ptab_cdf = nullptr; int ptab_n = 0;      // ms_set_prior_table
     cudaStream_t own_stream = nullptr;           // compute stream of the host-buffer entry point
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_pool;            // chunk pipeline events

@@ -240,9 +240,72 @@ def gen_prior():
     print('prior.npz: %d points, %d finite lnl, %d finite lnprob' % (n, np.isfinite(lnl).sum(), np.isfinite(lnprob).sum()))
 
 
+def gen_prior_adv():
+    """The advanced priors (prior.py:413-501 -> advancedpriors.py:410-833): Galactic density + age (GALAGE, which also
+    replaces the Dist transform by AP.gal_ppf), rotation (VROT), alpha (ALPHA), a pv_beta transform, and the two keys the
+    reference accepts but never applies (VTOT, AngDia); spectrum + photometry fit so that Vrot is a parameter."""
+    import json
+    mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10, frac_missing=0.04, frac_trunc=0.15)
+    refshim.register_h5('golden://mist', synth.mist_rows(mist))
+    phot = synth.make_phot_net(h=32, seed=11)
+    specnet = synth.make_spec_net(npix=2048, h=16, seed=12, nlines=150)
+    ow = np.linspace(5146.0, 5170.0, 64)
+    obs = synth.make_obs_spectrum(specnet, n_obs=64, wave_lo=5146.0, wave_hi=5170.0)
+    priordict = {'EEP': {'pv_uniform': [202, 261]}, 'initial_Mass': {'pv_uniform': [0.5, 1.6]},
+                 'initial_[Fe/H]': {'pv_uniform': [-2.0, 0.3]}, 'initial_[a/Fe]': {'pv_uniform': [-0.2, 0.6]},
+                 'Dist': {'pv_uniform': [50.0, 8000.0]}, 'Av': {'pv_beta': [2.0, 5.0, 0.0, 0.4]},
+                 'Vrad': {'pv_uniform': [-5.0, 5.0]}, 'Vrot': {'pv_uniform': [0.0, 20.0]}, 'Inst_R': {'fixed': 35000.0},
+                 'GALAGE': {'lb_coords': [35.0, 52.0],
+                            'pars': {'thin': {'min': 0.5, 'max': 14.0}, 'thick': {'min': 6.0, 'max': 14.0, 'mean': 10.0, 'sigma': 2.0},
+                                     'halo': {'min': 8.0, 'max': 14.0, 'mean': 12.0, 'sigma': 2.0}}},
+                 'VROT': {'dwarf': {'a': -10.0, 'c': 10.0, 'n': 0.4}, 'giant': {'a': -10.0, 'c': 7.0, 'n': 1.0}},
+                 'ALPHA': {'min': 0.1}, 'VTOT': {'pmra': 3.0, 'pmdec': -4.0}, 'AngDia': {'gaussian': [0.7, 0.05]},
+                 'IMF': {'IMF_type': 'Kroupa'}}
+    inputdict = dict(phot=synth.demo_obs_phot(), photANNpath=phot, MISTpath='golden://mist', specANNpath=specnet,
+                     NNtype='YST1', isochrone_prior=True, ageweight=True, priordict=priordict,
+                     spec=dict(obs_wave=obs['obs_wave'], obs_flux=obs['obs_flux'], obs_eflux=obs['obs_eflux'],
+                               modpoly=False, convertair=False))
+    fs = refshim.build_fit(inputdict)
+    L, P = fs.likeobj, fs.priorobj
+    rng = np.random.default_rng(654)
+    n = 400
+    u = rng.random((n, L.ndim))
+    u[0, :] = 1e-9; u[1, :] = 1 - 1e-9
+    theta = np.array([P.priortrans(list(r)) for r in u], dtype=np.float64)
+    lnl = np.empty(n); lnp = np.full(n, np.nan)
+    keys, rows = None, []
+    for i, th in enumerate(theta):
+        lnl[i] = L.lnlikefn(list(th))
+        pd = dict(L.parsdict)
+        if np.isfinite(lnl[i]):
+            lnp[i] = P.lnpriorfn(dict(pd))
+            if keys is None:
+                keys = list(pd.keys())
+        rows.append(pd)
+    pars = np.array([[r.get(k, np.nan) if np.ndim(r.get(k, np.nan)) == 0 else np.nan for k in keys] for r in rows], dtype=np.float64)
+    out = dict(u=u, theta=theta, lnl=lnl, lnprior=lnp, parsdict_keys=np.array(keys), parsdict=pars,
+               priordict=np.array(json.dumps(priordict)), fitpars_i=np.array(L.fitpars_i), fitpars_all=np.array(fs.fitpars),
+               fitpars_bool=np.array([fs.fitpars_bool[k] for k in fs.fitpars]),
+               runbools=np.array([fs.spec_bool, fs.phot_bool, fs.modpoly_bool, fs.photscale_bool, fs.flux_bool]),
+               obs_phot_bands=np.array(list(fs.fitargs['obs_phot'].keys())),
+               obs_phot=np.array([fs.fitargs['obs_phot'][b] for b in fs.fitargs['obs_phot'].keys()]),
+               fixed_keys=np.array(list(fs.fitargs['fixedpars'].keys()), dtype='<U16'),
+               fixed_vals=np.array([fs.fitargs['fixedpars'][k] for k in fs.fitargs['fixedpars']], dtype=np.float64),
+               obs_wave_fit=fs.fitargs['obs_wave_fit'], obs_flux_fit=fs.fitargs['obs_flux_fit'],
+               obs_eflux_fit=fs.fitargs['obs_eflux_fit'])
+    out.update(pack('mist_', mist)); out.update(pack('phot_', phot)); out.update(pack('spec_', specnet))
+    np.savez_compressed(os.path.join(HERE, 'prior_adv.npz'), **out)
+    print('prior_adv.npz: %d points, %d finite lnl, %d finite lnprior, fitpars %s' % (
+        n, np.isfinite(lnl).sum(), np.isfinite(lnp).sum(), L.fitpars_i))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'prior_adv':
+        gen_prior_adv()
+        sys.exit(0)
     gen_mist()
     gen_smoothing()
     gen_like(False, 'like_phot.npz', 400)
     gen_like(True, 'like_spec.npz', 120)
     gen_prior()
+    gen_prior_adv()

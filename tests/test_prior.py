@@ -86,6 +86,74 @@ def test_priordict_translation_rules():
     assert (_lib.MS_V_PARALLAX, _lib.TERM_KINDS['gaussian']) in kinds
     assert (_lib.param_id('Vrad'), _lib.TERM_KINDS['tgaussian_bounds']) in kinds       # spec family: bounds only
     assert p.imf_bool
+    # advanced priors: GAL turns the Dist column into the tabulated distance quantile; VTOT / AngDia are accepted and
+    # inert (dead code in the reference's lnpriorfn); pv_texp is refused (NameError in the reference)
+    pd2 = dict(pd, GAL={'lb_coords': [30.0, 45.0]}, VTOT={'pmra': 1.0, 'pmdec': 2.0}, AngDia={'gaussian': [1.0, 0.1]},
+               ALPHA={'min': 0.0}, Av={'pv_beta': [2.0, 5.0, 0.0, 0.3]}, Dist={'pv_uniform': [10.0, 3000.0]})
+    p2 = P.prior(dict(fixedpars={'Inst_R': 35000.0}, ageweight=True, mistdif=True), pd2, fitpars,
+                 [True, True, True, False, False], engine=FakeEngine())
+    cols2 = {n: p2._cols[i] for i, n in enumerate(p2.fitpars_i)}
+    assert cols2['Dist'].kind == _lib.PRIOR_KINDS['table'] and cols2['Dist'].p[0] == 1000.0
+    assert cols2['Av'].kind == _lib.PRIOR_KINDS['beta'] and list(cols2['Av'].p) == [2.0, 5.0, 0.0, 0.3]
+    assert p2._adv.gal == 1 and p2._adv.galage == 0 and p2._adv.alpha == 1 and p2._adv.vrot == 0
+    assert abs(p2._adv.Zp - np.sin(np.deg2rad(45.0))) < 1e-15
     with pytest.raises(NotImplementedError):
-        P.prior(dict(fixedpars={}), {'GAL': {'lb_coords': [0, 0]}}, fitpars, [False, True, False, False, False],
-                engine=FakeEngine())
+        P.prior(dict(fixedpars={'Inst_R': 35000.0}), dict(pd, Dist={'pv_texp': [1, 100, 0, 10]}), fitpars,
+                [True, True, True, False, False], engine=FakeEngine())
+
+
+@pytest.fixture(scope='module')
+def g_prior_adv():
+    return load_golden('prior_adv.npz')
+
+
+def _setup_adv(g):
+    fitargs, fitpars, runbools, priordict = _setup(g)
+    fitargs['fixedpars'] = {str(k): float(v) for k, v in zip(g['fixed_keys'], g['fixed_vals'])}
+    fitargs.update(specANNpath=sub(g, 'spec_'), NNtype='YST1', obs_wave_fit=g['obs_wave_fit'],
+                   obs_flux_fit=g['obs_flux_fit'], obs_eflux_fit=g['obs_eflux_fit'])
+    return fitargs, fitpars, runbools, priordict
+
+
+def test_galactic_distance_table_matches_reference_gal_ppf(g_prior_adv):
+    """CPU: the host-built quantile table (minesweeper_b200/advancedpriors.py) reproduces the reference's
+    ``1000 * AP.gal_ppf(u)`` distance transform (prior.py:333-336, advancedpriors.py:43-63, 665-670)."""
+    from minesweeper_b200 import advancedpriors as AP
+    g = g_prior_adv
+    pd = json.loads(str(g['priordict']))
+    l, b = pd['GALAGE']['lb_coords']
+    x, cdf = AP.distance_table(l, b, pd['Dist']['pv_uniform'][0] / 1000.0, pd['Dist']['pv_uniform'][1] / 1000.0)
+    i = [str(s) for s in g['fitpars_i']].index('Dist')
+    np.testing.assert_allclose(1000.0 * np.interp(g['u'][:, i], cdf, x), g['theta'][:, i], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_advanced_priors_golden(g_prior_adv):
+    """GAL / GALAGE / VROT / ALPHA additive priors, the Galactic distance transform and pv_beta on the GPU against
+    the reference's own prior class (tests/golden/prior_adv.npz); VTOT / AngDia are in the priordict and, as in the
+    reference, change nothing."""
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    g = g_prior_adv
+    fitargs, fitpars, runbools, priordict = _setup_adv(g)
+    L = likelihood(fitargs, fitpars, runbools, precision='f64', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    assert P.fitpars_i == [str(s) for s in g['fitpars_i']]
+    theta = P.priortrans_batch(g['u']).cpu().numpy()
+    ib = P.fitpars_i.index('Av')                                                  # the pv_beta column: scipy's own ppf is
+    np.testing.assert_allclose(theta[:, ib], g['theta'][:, ib], rtol=1e-9, atol=1e-12)   # good to ~1e-10 in the far tails
+    rest = [i for i in range(P.ndim) if i != ib]
+    np.testing.assert_allclose(theta[:, rest], g['theta'][:, rest], rtol=1e-10, atol=1e-12)   # incl. the gal_ppf column
+    lnl, der, _ = L.lnlike_batch(g['theta'])
+    lnp = P.lnprob_batch(g['theta'], None, der).cpu().numpy()
+    ok = np.isfinite(g['lnl'])
+    ref = g['lnprior'][ok]
+    assert np.array_equal(np.isneginf(lnp[ok]), np.isneginf(ref)) and np.isneginf(ref).sum() > 20
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(lnp[ok][fin], ref[fin], rtol=1e-10, atol=1e-7)
+    # scalar API on a parsdict as lnprobfn passes it
+    keys = [str(k) for k in g['parsdict_keys']]
+    for i in np.flatnonzero(ok)[:5]:
+        pdict = {k: float(v) for k, v in zip(keys, g['parsdict'][i])}
+        v = P.lnpriorfn(pdict)
+        assert (v == g['lnprior'][i]) or abs(v - g['lnprior'][i]) <= 1e-7 + 1e-10 * abs(g['lnprior'][i])
