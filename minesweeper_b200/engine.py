@@ -10,12 +10,19 @@ from . import _lib
 from ._lib import Flags, GridDesc, PhotNetDesc, SpecNetDesc, check
 
 
-def load_container(obj):
-    """A model container is a dict of arrays or a path to an ``.npz``."""
+def load_container(obj, kind=None, bands=None):
+    """A model container is a dict of arrays or a path to an ``.npz``; an HDF5 path (what an unmodified caller of
+    the reference passes: fastMISTmod.py:65-66, genmod.py:15-44) is converted on the fly where h5py is importable
+    (minesweeper_b200.ingest; ``kind`` in 'mist' | 'phot' | 'spec')."""
     if obj is None:
         return None
     if isinstance(obj, dict):
         return obj
+    import os
+    name = os.fspath(obj)
+    if kind is not None and (name.endswith(('.h5', '.hdf5')) or (kind == 'phot' and os.path.isdir(name))):
+        from . import ingest
+        return ingest.load_model_file(name, kind, bands=bands)
     with np.load(obj, allow_pickle=False) as z:
         return {k: z[k] for k in z.files}
 

@@ -69,3 +69,112 @@ def mist_dense_from_h5(path, ageweight=True, save=None):
     if save:
         np.savez(save, **dense)
     return dense
+
+
+# ---- Payne network weight files (genmod.py:15-44 hands their paths to the un-vendored Payne package) --------------
+# Layouts as recalled in SURVEY.md Appendix B (PARITY UNPINNED, like the ANN arithmetic itself); every shape is read
+# from the file, nothing is assumed about widths.  Inputs are "HDF5-like" mappings (an open h5py.File / Group, or nested
+# dicts of arrays in tests); `open_h5` turns a path into one where h5py is importable.
+def open_h5(path):
+    try:
+        import h5py
+    except ImportError as e:
+        raise ImportError('reading %r needs h5py, which this package does not depend on: run tools/h5_to_npz.py on a '
+                          'machine that has it and pass the .npz' % (path,)) from e
+    return h5py.File(path, 'r')                                                      # pragma: no cover
+
+
+def _flatten(group, prefix=''):
+    """{'a/b/c': array} for every dataset under an HDF5-like mapping."""
+    out = {}
+    for k in group.keys():
+        v = group[k]
+        name = prefix + _name(k)
+        if hasattr(v, 'keys') and not isinstance(v, np.ndarray):
+            out.update(_flatten(v, name + '/'))
+        else:
+            out[name] = np.asarray(v)
+    return out
+
+
+def _find(flat, *needles):
+    hits = [k for k in flat if all(n in k for n in needles)]
+    if len(hits) != 1:
+        raise KeyError('expected exactly one dataset matching %s, found %s among %s' % (needles, hits, sorted(flat)))
+    return flat[hits[0]]
+
+
+def payne_phot_net(files, bands=None):
+    """Per-filter photometric nets -> the stacked container of ``synth.make_phot_net`` / ms_phot_net_desc.
+
+    ``files``: ``{band: HDF5-like mapping}`` of the ``nnMIST_<band>.h5`` files (reference data/nnMIST/README.md;
+    FastPayneSEDPredict(usebands, nnpath), genmod.py:39-44), each holding a 3-layer perceptron
+    ``lin1 / lin2 / lin3`` (``weight`` [out, in], ``bias``) and the input box ``xmin`` / ``xmax``."""
+    bands = list(files.keys()) if bands is None else [b for b in bands if b in files]
+    if not bands:
+        raise ValueError('no photometric net files for the requested bands')
+    per = []
+    for b in bands:
+        flat = _flatten(files[b])
+        per.append(dict(w1=_find(flat, 'lin1', 'weight'), b1=_find(flat, 'lin1', 'bias'),
+                        w2=_find(flat, 'lin2', 'weight'), b2=_find(flat, 'lin2', 'bias'),
+                        w3=_find(flat, 'lin3', 'weight'), b3=_find(flat, 'lin3', 'bias'),
+                        xmin=_find(flat, 'xmin'), xmax=_find(flat, 'xmax')))
+    h, d_in = per[0]['w1'].shape
+    for b, p in zip(bands, per):
+        if p['w1'].shape != (h, d_in) or p['w2'].shape != (h, h) or p['w3'].shape != (1, h):
+            raise ValueError('net of band %s has a different architecture (%s)' % (b, p['w1'].shape))
+        if not (np.allclose(p['xmin'], per[0]['xmin']) and np.allclose(p['xmax'], per[0]['xmax'])):
+            raise ValueError('net of band %s was trained on a different input box' % b)
+    f32 = np.float32
+    return dict(bands=np.array(bands), w1=np.stack([p['w1'] for p in per]).astype(f32),
+                b1=np.stack([p['b1'] for p in per]).astype(f32), w2=np.stack([p['w2'] for p in per]).astype(f32),
+                b2=np.stack([p['b2'] for p in per]).astype(f32), w3=np.stack([p['w3'] for p in per]).astype(f32),
+                b3=np.stack([p['b3'].reshape(1) for p in per]).astype(f32),
+                xmin=np.asarray(per[0]['xmin'], dtype=np.float64).ravel()[:d_in],
+                xmax=np.asarray(per[0]['xmax'], dtype=np.float64).ravel()[:d_in], activation=np.array('sigmoid'))
+
+
+def payne_spec_net(h5like, leak=0.01, logt_input=False):
+    """Spectral net file (``w_array_0/1/2``, ``b_array_0/1/2``, ``x_min``, ``x_max``, ``wavelength``, ``resolution``;
+    PayneSpecPredict(nnpath), genmod.py:24-34) -> the container of ``synth.make_spec_net`` / ms_spec_net_desc."""
+    flat = _flatten(h5like)
+    w = [_find(flat, 'w_array_%d' % i) for i in range(3)]
+    b = [_find(flat, 'b_array_%d' % i) for i in range(3)]
+    d_in = w[0].shape[1]
+    if w[1].shape != (w[0].shape[0],) * 2 or w[2].shape[1] != w[0].shape[0]:
+        raise ValueError('unexpected spectral net shapes %s' % ([x.shape for x in w],))
+    wave = np.asarray(_find(flat, 'wavelength'), dtype=np.float64).ravel()
+    if len(wave) != w[2].shape[0]:
+        raise ValueError('wavelength grid (%d) does not match the output layer (%d)' % (len(wave), w[2].shape[0]))
+    f32 = np.float32
+    return dict(w0=w[0].astype(f32), b0=b[0].astype(f32).ravel(), w1=w[1].astype(f32), b1=b[1].astype(f32).ravel(),
+                w2=w[2].astype(f32), b2=b[2].astype(f32).ravel(),
+                xmin=np.asarray(_find(flat, 'x_min'), dtype=np.float64).ravel()[:d_in],
+                xmax=np.asarray(_find(flat, 'x_max'), dtype=np.float64).ravel()[:d_in], wavelength=wave,
+                resolution=np.float64(np.asarray(_find(flat, 'resolution')).ravel()[0]), leak=np.float64(leak),
+                logt_input=np.bool_(logt_input))
+
+
+def load_model_file(path, kind, bands=None, **kw):
+    """``fitargs['MISTpath' | 'photANNpath' | 'specANNpath']`` given as an HDF5 path, the way an unmodified caller of
+    the reference passes them (fastMISTmod.py:65-66, genmod.py:15-44): read with h5py where it is importable.
+    kind: 'mist' | 'phot' | 'spec'.  For 'phot', ``path`` is the directory (or prefix) holding ``nnMIST_<band>.h5``."""
+    import os
+    if kind == 'mist':
+        return mist_dense_from_h5(path, **kw)
+    if kind == 'spec':
+        with open_h5(path) as f:                                                     # pragma: no cover
+            return payne_spec_net(f, **kw)
+    if kind == 'phot':                                                               # pragma: no cover
+        files = {}
+        for b in bands or []:
+            p = os.path.join(path, 'nnMIST_%s.h5' % b)
+            if os.path.exists(p):
+                files[b] = open_h5(p)
+        try:
+            return payne_phot_net(files, bands)
+        finally:
+            for f in files.values():
+                f.close()
+    raise ValueError('unknown model kind %r' % kind)

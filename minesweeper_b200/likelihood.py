@@ -64,9 +64,9 @@ class likelihood(object):
         self.engine = kwargs.get('engine', None)
         if self.engine is None:
             self.engine = Engine(
-                mist=load_container(fitargs['MISTpath']) if self.iso_bool else None,
-                photnet=load_container(fitargs['photANNpath']) if self.phot_bool else None,
-                specnet=load_container(fitargs['specANNpath']) if self.spec_bool else None,
+                mist=load_container(fitargs['MISTpath'], 'mist') if self.iso_bool else None,
+                photnet=load_container(fitargs['photANNpath'], 'phot', bands=bands) if self.phot_bool else None,
+                specnet=load_container(fitargs['specANNpath'], 'spec') if self.spec_bool else None,
                 bands=bands, precision=kwargs.get('precision', 'f32'),
                 device=kwargs.get('device', None))
         self.slot = kwargs.get('slot', 0)

@@ -219,3 +219,31 @@ def test_samples_file_header_is_the_references_parsdict_order(which, g_like_phot
     want = list(R.parsdict.keys())
     fitpars_i = [p for p in fitpars[0] if fitpars[1][p]]
     assert parsdict_keys(fitpars_i, fitargs['fixedpars'], iso=True, ageweight=True) == want
+
+
+def test_payne_weight_file_ingestion_roundtrip():
+    """minesweeper_b200.ingest: HDF5-like network files (layout of SURVEY.md Appendix B) -> containers that evaluate
+    to the same numbers as the nets they were written from (through the oracle's CPU restatement)."""
+    from minesweeper_b200 import ingest
+    from oracle.payne_port import FastPayneSEDPredict, PayneSpecPredict
+    phot = synth.make_phot_net(h=24, seed=5)
+    files = {}
+    for i, b in enumerate(phot['bands']):
+        files[str(b)] = {'model': {'lin1.weight': phot['w1'][i], 'lin1.bias': phot['b1'][i], 'lin2.weight': phot['w2'][i],
+                                   'lin2.bias': phot['b2'][i], 'lin3.weight': phot['w3'][i], 'lin3.bias': phot['b3'][i]},
+                         'xmin': phot['xmin'], 'xmax': phot['xmax']}
+    pick = ['WISE_W1', '2MASS_J', 'GaiaEDR3_G']
+    c = ingest.payne_phot_net(files, bands=pick)
+    assert [str(b) for b in c['bands']] == pick and c['w2'].shape == (3, 24, 24)
+    x = [5600.0, 4.4, -0.3, 0.1, 0.05, 3.1]
+    np.testing.assert_array_equal(FastPayneSEDPredict(nnpath=c).bolcorr(x),
+                                  FastPayneSEDPredict(usebands=pick, nnpath=phot).bolcorr(x))
+    spec = synth.make_spec_net(npix=512, h=16, seed=6, nlines=40)
+    f = {'w_array_0': spec['w0'], 'w_array_1': spec['w1'], 'w_array_2': spec['w2'], 'b_array_0': spec['b0'],
+         'b_array_1': spec['b1'], 'b_array_2': spec['b2'], 'x_min': spec['xmin'], 'x_max': spec['xmax'],
+         'wavelength': spec['wavelength'], 'resolution': np.array([spec['resolution']])}
+    cs = ingest.payne_spec_net(f)
+    np.testing.assert_array_equal(PayneSpecPredict(nnpath=cs).predictspec(5600.0, 4.4, -0.3, 0.1),
+                                  PayneSpecPredict(nnpath=spec).predictspec(5600.0, 4.4, -0.3, 0.1))
+    with pytest.raises(ImportError):                       # h5py is absent here: an .h5 path fails loudly, with the recipe
+        ingest.load_model_file('/nonexistent/MIST.h5', 'mist')
