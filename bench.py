@@ -247,8 +247,10 @@ def main():
                                                 seed=rank)
         arm = CpuArm(sfa, sfp, srb, sth[:8192])
         r1 = arm.calibrate(1.0)
-        n = int(max(r1 * arm.cores * 0.8 * args.cpu_seconds * 0.6, 4 * arm.cores))
-        arm.step(max(n // 10, arm.cores))
+        # the spectrum path is memory-bound on the host (24 MB of output-layer weights per evaluation): the workers do
+        # not scale like the single-core probe, so the sample is sized from a short parallel step
+        n0, t0_ = arm.step(4 * arm.cores)
+        n = int(max(n0 / t0_ * args.cpu_seconds * 0.6, 4 * arm.cores))
         ne, te = arm.step(n)
         rows = np.arange(SPEC_PARITY_ROWS)
         lref = arm.eval_rows(rows)
