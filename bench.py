@@ -500,6 +500,36 @@ def main():
         except Exception as e:
             specblk = dict(error=repr(e))
 
+    # ---- other hidden widths of the photometric nets ("default H_p = 128; also report 64 and
+    # 256"): same workload, same timing loop; 64 runs on the tcgen05 kernel, 256 does not fit its TMEM / shared-memory
+    # plan and runs on the f32 CUDA-core kernel
+    hidden_variants = {}
+    if args.hidden == 128 and not args.small_grid and args.precision == 'tc':
+        for hh, hprec in ((64, 'tc'), (256, 'f32')):
+            try:
+                fa_h = dict(fitargs, photANNpath=synth.make_phot_net(h=hh, seed=1))
+                Lh = likelihood(fa_h, fitpars, runbools, precision=hprec, device=local, verbose=False)
+                outh = torch.empty(B, dtype=torch.float64, device=dev)
+                nst = 5 if hh == 64 else 2
+                for _ in range(2):
+                    Lh.engine.lnlike_batch(theta, Lh._colmap, Lh._fixed, Lh._flags, want_derived=False, out=outh)
+                evh = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nst)]
+                for e0, e1 in evh:
+                    flush.zero_()
+                    e0.record()
+                    Lh.engine.lnlike_batch(theta, Lh._colmap, Lh._fixed, Lh._flags, want_derived=False, out=outh)
+                    e1.record()
+                torch.cuda.synchronize()
+                msh = sum(e0.elapsed_time(e1) for e0, e1 in evh) / nst
+                flop_h = len(Lh.engine.bands) * 2.0 * (6 * hh + hh * hh + hh)
+                hidden_variants[str(hh)] = dict(value=B / (msh * 1e-3), unit=UNIT, ms_per_step=msh, precision=hprec,
+                                                flop_per_eval=flop_h, achieved_tflops=flop_h * B / (msh * 1e-3) / 1e12,
+                                                kernel='phot_mlp_tc (tcgen05, fused)' if hprec == 'tc' else 'phot_mlp_kernel<float> (CUDA cores)')
+                Lh.engine.close()
+                del Lh, outh
+            except Exception as e:
+                hidden_variants[str(hh)] = dict(error=repr(e))
+
     # ---- the two kernels on their own (the timed step runs them fused in the tensor-core modes)
     eng.set_fusion(False)
     for _ in range(2):
@@ -555,6 +585,7 @@ def main():
             kernel_ms_two_kernel_sequence={k: v[0] / 5 for k, v in prof2.items() if v[1]},
             parity_check=parity,
             with_derived=derived_variant,
+            hidden_widths=hidden_variants,
             catalog=catalog,
             spec_phot=specblk,
             cpu_baseline=cpu)
