@@ -460,7 +460,7 @@ def main():
                             accuracy=acc)
 
             catalog = run_catalog(args.catalog_stars, GATE_WALKS)
-            catalog['sampler'] = ('lock-step static nested sampling, rwalk, 4 queued walkers per star, bookkeeping in CUDA '
+            catalog['sampler'] = ('lock-step static nested sampling, rwalk, 4 queued walkers per star (up to 64 for the stragglers), bookkeeping in CUDA '
                                   'kernels, CUDA-graph replay')
             catalog['note'] = 'configs[4]: stars per GPU fixed (weak scaling); walks = shortest walk passing accuracy.gate'
             catalog['demo_settings'] = run_catalog(max(args.catalog_stars // 5, 64), 5)

@@ -421,7 +421,7 @@ class QueuedNestedSampler(object):
     """
 
     def __init__(self, likeobj, priorobj, nstars=1, nlive=150, walks=5, queue=32, dlogz=0.01, maxiter=100000,
-                 seed=0, star_plx=None, store_samples=False, dead_cap=20000):
+                 seed=0, star_plx=None, store_samples=False, dead_cap=20000, max_queue=64):
         if not likeobj.iso_bool:
             raise NotImplementedError('the queued sampler tracks the derived MIST block (isochrone fits)')
         self.L, self.P = likeobj, priorobj
@@ -432,18 +432,19 @@ class QueuedNestedSampler(object):
         self.dlogz, self.maxiter, self.seed = float(dlogz), int(maxiter), int(seed)
         self.star_plx = None if star_plx is None else torch.as_tensor(star_plx, dtype=torch.float64).to(self.dev).contiguous()
         self.store, self.dead_cap = bool(store_samples), int(dead_cap)
+        self.max_queue = max(int(max_queue), self.Q)
         self.eng.check_star_slots(self.S, self.star_plx)
 
-    def run(self, check_every=4, verbose=False, min_compact=512):
+    def run(self, check_every=4, verbose=False, min_compact=512, compact_frac=0.5):
         # the rounds are captured into CUDA graphs that bake the ctx's scratch pointers in: size the scratch for the
         # largest batch of the run and pin it for its duration (another caller growing it would free it under us)
         self.eng.reserve(self.S * max(self.K, self.Q), lock=True)
         try:
-            return self._run(check_every, verbose, min_compact)
+            return self._run(check_every, verbose, min_compact, compact_frac)
         finally:
             self.eng.reserve(0, lock=False)
 
-    def _run(self, check_every=4, verbose=False, min_compact=512):
+    def _run(self, check_every=4, verbose=False, min_compact=512, compact_frac=0.5):
         import ctypes as C
         if self.store and min_compact < self.S:
             raise ValueError('store_samples needs min_compact >= nstars (the dead-point buffer is not compacted)')
@@ -505,7 +506,7 @@ class QueuedNestedSampler(object):
             out['mean'][o] = mean; out['std'][o] = torch.sqrt(var)
 
         rounds, captures = 0, 0
-        bootstrap = True
+        bootstrap, reseed = True, False
         with torch.cuda.device(dev):
             while True:
                 Sc = len(orig)
@@ -536,6 +537,11 @@ class QueuedNestedSampler(object):
                     consume()
                     t['scale'].fill_(1.0)
                     bootstrap = False
+                elif reseed:                              # new queue after a compaction: restart points only (an empty
+                    keep_scale, keep_calls = t['scale'].clone(), t['ncall'].clone()      # queue consumes nothing)
+                    consume()
+                    t['scale'].copy_(keep_scale); t['ncall'].copy_(keep_calls)
+                reseed = False
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
@@ -554,7 +560,7 @@ class QueuedNestedSampler(object):
                     nrun = int((t['done'] == 0).sum().item())
                     if verbose:
                         print('round %d: %d / %d stars running (working set %d)' % (rounds, nrun, S, Sc))
-                    if nrun == 0 or (Sc > min_compact and nrun * 2 <= Sc) or rounds >= self.maxiter + 16:
+                    if nrun == 0 or (Sc > min_compact and nrun <= compact_frac * Sc) or rounds >= self.maxiter + 16:
                         break
                 del graph
                 if rounds >= self.maxiter + 16:
@@ -573,13 +579,19 @@ class QueuedNestedSampler(object):
                 for kname in ('live_u', 'live_lp', 'live_row'):          # [S*K, ...] blocks of K rows per star
                     v = t[kname]
                     t[kname] = v.reshape((Sc, K) + tuple(v.shape[1:]))[keep].reshape((nk * K,) + tuple(v.shape[1:])).contiguous()
+                # the walkers restart from live points every round, so the queue can be re-dimensioned at a compaction:
+                # as the working set shrinks to the stragglers, every star gets more queued walkers (fewer sequential
+                # rounds for the tail, batches that still fill the GPU); the walker budget of the first round is kept
+                q_new = int(min(self.max_queue, max(Q, (self.S * self.Q) // max(nk, 1))))
                 for kname in walker_keys:                                 # [S*Q, ...] blocks of Q rows per star
                     v = t[kname]
-                    t[kname] = v.reshape((Sc, Q) + tuple(v.shape[1:]))[keep].reshape((nk * Q,) + tuple(v.shape[1:])).contiguous()
+                    t[kname] = torch.zeros((nk * q_new,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev)
                 for kname in per_star_keys:                               # [S, ...]
                     if kname in t and not kname.startswith('live'):
                         t[kname] = t[kname][keep].contiguous()
                 orig = orig[keep]
+                Q = q_new
+                reseed = True
             torch.cuda.synchronize(dev)
         res = dict(logz=out['logz'].cpu().numpy(), logzerr=torch.sqrt(out['H'].clamp_min(0.0) / K).cpu().numpy(),
                    information=out['H'].cpu().numpy(), niter=out['niter'].cpu().numpy(), ncall=out['ncall'].cpu().numpy(),

@@ -172,6 +172,8 @@ def main():
     ap.add_argument('--maxiter', type=int, default=20000)
     ap.add_argument('--small-grid', action='store_true')
     ap.add_argument('--eager', action='store_true', help='use the eager sampler loop instead of the CUDA-graph one')
+    ap.add_argument('--compact-frac', type=float, default=0.5)
+    ap.add_argument('--check-every', type=int, default=64)
     ap.add_argument('--bruteforce', type=int, default=0, help='check this many stars against brute-force quadrature')
     ap.add_argument('--queued', type=int, default=4,
                     help='walkers per star of the kernel-bookkeeping sampler; 0 = torch-tensor sampler')
@@ -209,7 +211,7 @@ def main():
     l0 = L.engine.launch_count()
     t0 = time.perf_counter()
     if args.queued:
-        res = ns.run(check_every=64)
+        res = ns.run(check_every=args.check_every, compact_frac=args.compact_frac)
     else:
         res = ns.run() if args.eager else ns.run_graphed()
     torch.cuda.synchronize()
