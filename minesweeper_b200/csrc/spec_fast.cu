@@ -335,6 +335,148 @@ __device__ __noinline__ void rotational_filter(float2 *z, const float *fr, int n
     while (lNs < lM) { fft_pass<RM, true>(z, M, lNs, twlev, own); lNs += LRM; }
 }
 
+// ---- in-place variant (RM = 0): decimation-in-frequency forward, decimation-in-time inverse ------------------
+// A Stockham pass has to hold all of a thread's outputs across a CTA barrier (16 complex numbers at 512 threads) and the
+// 64-register budget of two CTAs per SM then spills ~32 registers per pass to local memory (ncu r02: 12 M local requests
+// per 1536 spectra, L1 hit rate 23 %).  A convolution does not care about the order of the spectrum, so the forward
+// transform here is the Gentleman-Sande in-place form (natural order in, digit-reversed out), the transfer function is
+// applied at the permuted positions and the inverse is the mirrored Cooley-Tukey form (digit-reversed in, natural out):
+// every butterfly writes the slots it read, one butterfly is live per thread, one barrier per pass.
+// Stage list for M = 2^lM: [2^lL leftover] 8 ... 8, then a final radix 2 that is fused -- together with the first inverse
+// radix 2 -- into the split / transfer / merge pass (ip_quad_pass).  X[k] ends at the position whose digits are those of
+// k in reversed stage order.
+struct IpPlan {
+    int lM, lL, n8;               // log2 M; log2 of the leftover radix (0, 1, 2); number of radix-8 stages
+    __device__ __forceinline__ void set(int lM_) { lM = lM_; lL = (lM_ - 1) % 3; n8 = (lM_ - 1) / 3; }
+    __device__ __forceinline__ int freq_at(int i) const {           // frequency index stored at position i
+        int rem = lM, shift = 0, k = 0;
+        if (lL) { rem -= lL; k = (i >> rem) & ((1 << lL) - 1); shift = lL; }
+        for (int s = 0; s < n8; ++s) { rem -= 3; k |= ((i >> rem) & 7) << shift; shift += 3; }
+        return k | ((i & 1) << shift);
+    }
+    __device__ __forceinline__ int pos_of(int k) const {            // position of frequency index k
+        int rem = lM, shift = 0, i = 0;
+        if (lL) { rem -= lL; i = (k & ((1 << lL) - 1)) << rem; shift = lL; }
+        for (int s = 0; s < n8; ++s) { rem -= 3; i |= ((k >> shift) & 7) << rem; shift += 3; }
+        return i | ((k >> shift) & 1);
+    }
+};
+
+// One in-place stage over blocks of length L = 2^lL_, radix R = 2^LR, stride S = L / R.  Forward: DFT over the R inputs,
+// then output p times W_L^(j p).  Inverse: input p times conj(W_L^(j p)), then the inverse DFT.
+template <int LR, bool INV, typename LOADER>
+__device__ __forceinline__ void ip_stage(float2 *z, int lM, int lL_, const float2 *__restrict__ twlev, const LOADER &ld) {
+    constexpr int R = 1 << LR;
+    const int lS = lL_ - LR, S = 1 << lS;
+    const int nbf = 1 << (lM - LR), lnblk = lM - lL_;
+    const float2 *tw = twlev + (1 << (lL_ - 1));                    // exp(-2 pi i j / L), j < L / 2
+#pragma unroll 1
+    for (int t = threadIdx.x; t < nbf; t += FT) {
+        int blk, j;
+        if (lS >= 4) { blk = t >> lS; j = t & (S - 1); }            // consecutive threads: consecutive j
+        else { blk = t & ((1 << lnblk) - 1); j = t >> lnblk; }      // short strides: consecutive blocks (padded stride L + L/16)
+        const int base = (blk << lL_) + j;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = ld(base + (r << lS));
+        if (!INV) Dft<R, false>::run(v);
+        if (lS > 0) {
+            float2 w1 = tw[j];
+            if (INV) w1.y = -w1.y;
+            v[1] = cmul(v[1], w1);
+            if (R >= 4) {
+                const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
+                v[2] = cmul(v[2], w2); v[3] = cmul(v[3], w3);
+                if (R >= 8) {
+                    const float2 w4 = cmul(w2, w2);
+                    v[4] = cmul(v[4], w4); v[5] = cmul(v[5], cmul(w4, w1));
+                    v[6] = cmul(v[6], cmul(w3, w3)); v[7] = cmul(v[7], cmul(w4, w3));
+                }
+            }
+        }
+        if (INV) Dft<R, true>::run(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[padi(base + (r << lS))] = v[r];
+    }
+    __syncthreads();
+}
+
+// Final forward radix 2 (adjacent positions, no twiddle), real-spectrum split, transfer function, merge and first
+// inverse radix 2, in place.  Positions (2a, 2a+1) hold the radix-2 inputs of frequencies (k, k + M/2) with
+// k = freq_at(2a) < M/2; a quadruple {k, M/2-k, M/2+k, M-k} is two such position pairs, owned by the thread of k < M/4.
+__device__ __forceinline__ void ip_quad_pass(float2 *z, const IpPlan &pl, const RotTransfer &tf,
+                                             const float2 *__restrict__ twlev) {
+    const int M = 1 << pl.lM, H = M >> 1, Q = M >> 2;
+    const float2 *twN = twlev + M;                 // exp(-2 pi i k / (2M)), k < M
+    const int lrp = pl.n8 ? 3 : pl.lL;             // log2 radix of the last stage before the fused radix 2
+    const int lh = lrp - 1;
+#pragma unroll 1
+    for (int w = threadIdx.x; w < Q; w += FT) {
+        const int a = ((w >> lh) << lrp) + (w & ((1 << lh) - 1));
+        const int k = pl.freq_at(2 * a);
+        if (k == 0) continue;
+        const int ap = pl.pos_of(H - k);
+        const float2 x0 = z[padi(2 * a)], x1 = z[padi(2 * a + 1)], y0 = z[padi(ap)], y1 = z[padi(ap + 1)];
+        float2 Za = cadd(x0, x1), Zc = csub(x0, x1);                   // Z[k], Z[k + H]
+        float2 Zb = cadd(y0, y1), Zd = csub(y0, y1);                   // Z[H - k], Z[M - k]
+        const float2 u = twN[k];
+        real_pair(Za, Zd, u, tf(k), tf(M - k));
+        const float2 ub = {-u.y, -u.x};                                // exp(-2 pi i (H - k) / (2M)) = -i conj(u)
+        real_pair(Zb, Zc, ub, tf(H - k), tf(H + k));
+        z[padi(2 * a)] = cadd(Za, Zc); z[padi(2 * a + 1)] = csub(Za, Zc);
+        z[padi(ap)] = cadd(Zb, Zd); z[padi(ap + 1)] = csub(Zb, Zd);
+    }
+    if (threadIdx.x == 0) {
+        {   // k = 0 (pairs with itself) and k = H (with itself): positions 0, 1
+            const float2 x0 = z[0], x1 = z[padi(1)];
+            float2 Z0 = cadd(x0, x1), ZH = csub(x0, x1);
+            const float y0 = tf(0) * (Z0.x + Z0.y), ym = tf(M) * (Z0.x - Z0.y);
+            Z0 = {0.5f * (y0 + ym), 0.5f * (y0 - ym)};
+            float2 dup = ZH;
+            const float th = tf(H);
+            real_pair(ZH, dup, twN[H], th, th);
+            z[0] = cadd(Z0, ZH); z[padi(1)] = csub(Z0, ZH);
+        }
+        if (Q > 0) {   // k = M/4: the pair (Q, 3Q)
+            const int pq = pl.pos_of(Q);
+            const float2 x0 = z[padi(pq)], x1 = z[padi(pq + 1)];
+            float2 Za = cadd(x0, x1), Zc = csub(x0, x1);
+            real_pair(Za, Zc, twN[Q], tf(Q), tf(M - Q));
+            z[padi(pq)] = cadd(Za, Zc); z[padi(pq + 1)] = csub(Za, Zc);
+        }
+    }
+    __syncthreads();
+}
+
+// same contract as rotational_filter<RM>: z[m] = y[2m] + i y[2m+1] in natural order
+__device__ __noinline__ void rotational_filter_ip(float2 *z, const float *fr, int npix, int n1, double dlnw, double vrot,
+                                                  const float *rot_tab, const float2 *__restrict__ twlev) {
+    const int M = n1 >> 1;
+    IpPlan pl;
+    pl.set(31 - __clz(M));
+    LoadResampled src;
+    src.fr = fr; src.ap.set((double)(npix - 1) / (double)(n1 - 1));
+    const LoadZ own{z};
+    int l = pl.lM;
+    bool first = true;
+    if (pl.lL == 1) { ip_stage<1, false>(z, pl.lM, l, twlev, src); l -= 1; first = false; }
+    else if (pl.lL == 2) { ip_stage<2, false>(z, pl.lM, l, twlev, src); l -= 2; first = false; }
+    for (int s = 0; s < pl.n8; ++s) {
+        if (first) ip_stage<3, false>(z, pl.lM, l, twlev, src);
+        else ip_stage<3, false>(z, pl.lM, l, twlev, own);
+        first = false; l -= 3;
+    }
+    const double step1 = (double)(npix - 1) * dlnw / (double)(n1 - 1);
+    RotTransfer tf;
+    tf.tab = rot_tab; tf.inv = 1.f / (float)M;
+    tf.coef = 2.0 * M_PI * sqrt(vrot * vrot) / ((double)n1 * MS_CKMS * step1);
+    ip_quad_pass(z, pl, tf, twlev);
+    l = 1;
+    for (int s = 0; s < pl.n8; ++s) { l += 3; ip_stage<3, true>(z, pl.lM, l, twlev, own); }
+    if (pl.lL == 1) ip_stage<1, true>(z, pl.lM, l + 1, twlev, own);
+    else if (pl.lL == 2) ip_stage<2, true>(z, pl.lM, l + 2, twlev, own);
+}
+
 __device__ __forceinline__ float conv_at(const float2 *z, int k) {          // real sample k of the filtered sequence
     const float2 c = z[padi(k >> 1)];
     return (k & 1) ? c.y : c.x;
@@ -507,7 +649,8 @@ spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restric
 
         // ---- rotational broadening on the full native grid (outwave = None), back onto the native pixels
         if (ps.rot) {
-            rotational_filter<RM>(z, fr, npix, n1, a.dlnw, ps.vrot, a.rot_tab, twlev);
+            if constexpr (RM == 0) rotational_filter_ip(z, fr, npix, n1, a.dlnw, ps.vrot, a.rot_tab, twlev);
+            else rotational_filter<RM>(z, fr, npix, n1, a.dlnw, ps.vrot, a.rot_tab, twlev);
             // smoothing.py:262: interpolation of the filtered n1 grid at the native wavelengths
             AffinePos ap;
             ap.set((double)(n1 - 1) / (double)(npix - 1));
@@ -677,27 +820,31 @@ bool spec_fast_usable(const ms_ctx *ctx) {
 
 // Rows the kernel declines are appended to fb_rows / *fb_count (device; the caller zeroes the counter).
 // ctx->spec_fast selects the variant: 1 = radix 16, one CTA per SM, bulk-copy prefetch of the next spectrum;
-// 2 = radix 8, two CTAs per SM (when two fit).
+// 2 = radix 8 Stockham, two CTAs per SM (when two fit); 3 = in-place radix 8 (DIF / DIT), two CTAs per SM.
 int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, int *fb_rows, int *fb_count, cudaStream_t st) {
     const bool aligned = (sa.npix & 3) == 0;
     const size_t smem_pf = fast_smem_bytes(sa.npix, sa.n1, true), smem_1 = fast_smem_bytes(sa.npix, sa.n1, false);
-    const bool two = (ctx->spec_fast == 2 || FT == 256) && 2 * (smem_1 + 1024 + 4096) <= 227 * 1024;
-    const bool pf = !two && aligned && smem_pf <= 226 * 1024;
+    const bool fits2 = 2 * (smem_1 + 1024 + 4096) <= 227 * 1024;
+    const bool inplace = ctx->spec_fast >= 3;
+    const bool two = (inplace || ctx->spec_fast == 2 || FT == 256) && fits2;
+    const bool pf = !inplace && !two && aligned && smem_pf <= 226 * 1024;
     const size_t smem = pf ? smem_pf : smem_1;
     auto k16 = spec_fast_kernel<16, false>;
     auto k16p = spec_fast_kernel<16, true>;
     auto k8 = spec_fast_kernel<8, false>;
-    static size_t cfg16 = 0, cfg16p = 0, cfg8 = 0;
-    if (two && FT == 256 && ctx->spec_fast != 2) { if (cfg16 < smem) { MS_CUDA(cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg16 = smem; } }
-    else if (two) { if (cfg8 < smem) { MS_CUDA(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg8 = smem; } }
-    else if (pf) { if (cfg16p < smem) { MS_CUDA(cudaFuncSetAttribute(k16p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg16p = smem; } }
-    else { if (cfg16 < smem) { MS_CUDA(cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg16 = smem; } }
+    auto kip = spec_fast_kernel<0, false>;
+    void (*kern)(SmoothArgs, int, int *, int *);
+    size_t *cfg;
+    static size_t cfg16 = 0, cfg16p = 0, cfg8 = 0, cfgip = 0;
+    if (inplace) { kern = kip; cfg = &cfgip; }
+    else if (two && FT == 256 && ctx->spec_fast != 2) { kern = k16; cfg = &cfg16; }
+    else if (two) { kern = k8; cfg = &cfg8; }
+    else if (pf) { kern = k16p; cfg = &cfg16p; }
+    else { kern = k16; cfg = &cfg16; }
+    if (*cfg < smem) { MS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); *cfg = smem; }
     int grid = ctx->sm_count * (two ? 2 : 1);
     if (grid > nB) grid = nB;
-    if (two && FT == 256 && ctx->spec_fast != 2) k16<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
-    else if (two) k8<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
-    else if (pf) k16p<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
-    else k16<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    kern<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

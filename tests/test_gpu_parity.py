@@ -746,7 +746,7 @@ def _spec_theta(n, seed, with_inst=False):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('variant', [1, 2])
+@pytest.mark.parametrize('variant', [1, 2, 3])
 @pytest.mark.parametrize('npix', [4096, 10240, 1000])
 def test_fast_broadening_kernel_equals_generic_fft_kernel(npix, variant):
     """f32-class modes: the fast kernel (radix-16 FFT for the rotational stage, direct Gaussian sum for the
