@@ -283,11 +283,10 @@ int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
 int ms_set_fusion(ms_ctx *ctx, int enable);
 
 /* f32-class modes: the broadening chain of genspec (smoothing.py:202-264, 517-598) normally runs in the fast
- * kernel (csrc/spec_fast.cu: radix-16 FFT for the rotational stage, direct Gaussian sum for the instrumental
- * stage) with the generic FFT kernel (csrc/spec_smooth.cu) taking the rows it declines.  ms_set_spec_fast(ctx, 0)
- * sends every row through the generic kernel (used by the tests to compare the two); 1 = radix-16 transform, one
- * CTA per SM, next spectrum prefetched by a bulk async copy; 2 (default, measured faster: 18.0 vs 19.9 ms per 65 536
- * spectra) = radix-8 transform, two CTAs per SM (falls back to 1 when two do not fit in shared memory). */
+ * kernel (csrc/spec_fast.cu: in-place radix-8 FFT for the rotational stage, direct Gaussian sum for the
+ * instrumental stage, two CTAs per SM) with the generic FFT kernel (csrc/spec_smooth.cu) taking the rows it declines.
+ * ms_set_spec_fast(ctx, 0) sends every row through the generic kernel (used by the tests to compare the two); any other
+ * value (default 1) enables the fast kernel. */
 int ms_set_spec_fast(ms_ctx *ctx, int enable);
 
 /* Multi-GPU gather fused into the likelihood kernel (the path's one collective is the gather of

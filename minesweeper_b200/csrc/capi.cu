@@ -323,7 +323,7 @@ extern "C" int64_t ms_launch_count(const ms_ctx *ctx) { return ctx ? ctx->launch
 
 extern "C" int ms_set_spec_fast(ms_ctx *ctx, int enable) {
     if (!ctx) { ms_set_error("bad arguments"); return MS_EINVAL; }
-    ctx->spec_fast = enable < 0 ? 0 : (enable > 3 ? 3 : enable);
+    ctx->spec_fast = enable ? 1 : 0;
     return MS_OK;
 }
 

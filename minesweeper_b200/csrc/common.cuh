@@ -100,7 +100,7 @@ struct ms_ctx {
     double *obs_mag = nullptr, *obs_err2 = nullptr;
     std::vector<StarDev> stars;
     StarView *stars_dev = nullptr; int stars_dev_n = 0;      // device copy of the spectrum views, refreshed by ms_set_star
-    int spec_fast = 2;             // f32-class modes: fast broadening kernel variant (ms_set_spec_fast); 0 = generic kernel only
+    int spec_fast = 1;             // f32-class modes: fast broadening kernel (ms_set_spec_fast); 0 = generic kernel only
     int *scr_fb = nullptr; size_t scr_fb_bytes = 0;          // fallback row list of the fast broadening kernel
     // scratch (grown on demand, stream-ordered use on one stream at a time)
     double *scr_derived = nullptr; size_t scr_derived_n = 0;

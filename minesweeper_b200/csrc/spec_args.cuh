@@ -110,3 +110,4 @@ __device__ __forceinline__ void mask_window(const double *__restrict__ wave, int
 int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, int *fallback_rows, int *fallback_count,
                      cudaStream_t st);
 bool spec_fast_usable(const ms_ctx *ctx);
+bool spec_fast_two_per_sm(const ms_ctx *ctx);

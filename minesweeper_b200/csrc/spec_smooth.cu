@@ -635,6 +635,10 @@ static int64_t spec_chunk(const ms_ctx *ctx) {
     if (ctx->precision == MS_PREC_F64) return 1024;
     const int64_t by_l2 = (int64_t)(60u << 20) / ((int64_t)ctx->spec.npix * 4);      // <= 60 MB of flux in flight
     int64_t c = (by_l2 / 128) * 128;
+    // the fast broadening kernel runs two CTAs per SM, one spectrum per CTA at a time: a chunk that is a whole number
+    // of waves has no partly filled last wave (1536 spectra on 296 CTAs would run 6 rounds for 5.2 rounds of work)
+    const int64_t wave = (spec_fast_two_per_sm(ctx) ? 2 : 1) * (int64_t)ctx->sm_count;
+    if (ctx->spec_fast && spec_fast_usable(ctx) && wave > 0 && by_l2 >= wave) c = (by_l2 / wave) * wave;
     if (c > 8192) c = 8192;
     if (c < 128) c = 128;
     return c;

@@ -46,7 +46,7 @@ def make_spec_workload(mist, phot, batch, nobs=1536, npix=10240, seed=0):
 
 
 def run_spec_bench(mist, phot, batch=65536, nobs=1536, npix=10240, precision='tc', steps=3, device=None,
-                   cpu_points=0, seed=0, spec_fast=2, parity_ref=None):
+                   cpu_points=0, seed=0, spec_fast=1, parity_ref=None):
     """Times spectrum + photometry lnL over `batch` points resident on the GPU; returns a dict.  parity_ref:
     (rows, lnl_ref, tol) from the CPU leg -- the first rows of this batch evaluated by the per-point reference."""
     import torch
@@ -110,7 +110,7 @@ def main():
     ap.add_argument('--npix', type=int, default=10240)
     ap.add_argument('--precision', default='f32')
     ap.add_argument('--steps', type=int, default=3)
-    ap.add_argument('--spec-fast', type=int, default=2, help='0 generic FFT kernel, 1 radix-16 / 1 CTA per SM, 2 radix-8 / 2 CTAs')
+    ap.add_argument('--spec-fast', type=int, default=1, help='0 generic FFT kernel for every row, 1 fast broadening kernel')
     ap.add_argument('--cpu-points', type=int, default=0, help='also time the per-point oracle on N points')
     args = ap.parse_args()
     from minesweeper_b200 import synth
