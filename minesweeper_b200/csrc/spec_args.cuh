@@ -106,8 +106,16 @@ __device__ __forceinline__ void mask_window(const double *__restrict__ wave, int
     i_e = ce - 1;
 }
 
+// per-point decisions of the fast broadening kernel (spec_fast.cu), one record per point of a chunk
+struct __align__(16) PointSetup {
+    int mode;             // 0: Gaussian FIR on the n2 grid; 1: plain interpolation; 2: all NaN; 3: fallback; 4: skip row
+    int i_s, i_e, n2, ntap, nobs, rot, slot_ok, teff_inf, pad_[3];
+    double d2, inv_d2, ratio2, spx, lnscale, lnw_s, inst, vrot;
+};
+static_assert(sizeof(PointSetup) == 112, "PointSetup is copied in 16-byte pieces");
+
 // kernel launchers
-int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, int *fallback_rows, int *fallback_count,
+int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, void *setup, int *fallback_rows, int *fallback_count,
                      cudaStream_t st);
 bool spec_fast_usable(const ms_ctx *ctx);
 bool spec_fast_two_per_sm(const ms_ctx *ctx);

@@ -312,15 +312,69 @@ __device__ __forceinline__ float conv_at(const float2 *z, int k) {          // r
     return (k & 1) ? c.y : c.x;
 }
 
-// per-point decisions, made once by thread 0 and broadcast through shared memory
-struct PointSetup {
-    int mode;             // 0: Gaussian FIR on the n2 grid; 1: plain interpolation; 2: all NaN; 3: fallback; 4: skip row
-    int i_s, i_e, n2, ntap, nobs, rot;
-    double d2, ratio2, spx, lnscale, lnw_s, inst, vrot;
-};
+// Per-point decisions (window, grid of the instrumental stage, kernel width, which path), one thread per point, ahead
+// of the broadening kernel: its CTAs fetch the 96-byte record of their NEXT point with an async copy while they work on
+// the current one, instead of one thread computing it (three f64 logarithms behind two dependent global loads) with
+// 511 threads waiting.  Rows the fast kernel declines are appended to the fallback list here.
+__global__ void spec_setup_kernel(SmoothArgs a, int nB, PointSetup *__restrict__ out, int *__restrict__ fb_rows,
+                                  int *__restrict__ fb_count) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nB) return;
+    const int npix = a.npix;
+    const double *r = a.pars + (size_t)p * MS_NPARS;
+    const int slot = a.star_slot ? a.star_slot[p] : a.slot0;
+    const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
+    const StarView sv = a.stars[slot_ok ? slot : 0];
+    PointSetup q;
+    q.nobs = slot_ok ? sv.n_obs : 0;
+    q.i_s = 0; q.i_e = npix - 1; q.n2 = 0; q.ntap = 0; q.d2 = 0.0; q.ratio2 = 0.0; q.spx = 0.0;
+    const double vrad = r[PV_VRAD];
+    q.vrot = r[PV_VROT]; q.rot = q.vrot != 0.0;
+    q.inst = 2.355 * r[PV_INSTR];                                    // genmod.py:74-75
+    const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
+    q.lnscale = log(scale);
+    if (r[PV_TEFF] == ms_inf() || q.nobs <= 0) q.mode = 4;
+    else if (q.inst != 0.0) {
+        if (!(q.inst == q.inst) || !(scale == scale)) q.mode = 2;
+        else {
+            mask_window(a.wave, npix, a.lnw0, a.dlnw, scale, sv.wmin * (1.0 - 20.0 / q.inst),
+                        sv.wmax * (1.0 + 20.0 / q.inst), q.i_s, q.i_e);
+            const int nmask = q.i_e - q.i_s + 1;
+            const double so = MS_CKMS / q.inst, si = MS_CKMS / a.resolution;
+            const double sigma = sqrt(so * so - si * si);            // NaN when sharper than the net
+            if (nmask < 4) q.mode = 2;
+            else if (sigma <= 0.0) q.mode = 1;
+            else if (!(sigma == sigma)) q.mode = 3;                  // NaN kernel: let the generic kernel propagate it
+            else {
+                int n2 = 1; while (n2 < nmask) n2 <<= 1;
+                q.n2 = n2;
+                q.ratio2 = (double)(q.i_e - q.i_s) / (double)(n2 - 1);
+                q.d2 = q.ratio2 * a.dlnw;
+                q.spx = sigma / (MS_CKMS * q.d2);                    // kernel width in pixels of the n2 grid
+                q.ntap = (int)ceil(5.5 * q.spx);
+                q.mode = (q.spx >= 2.0 && q.ntap <= MAXTAP && 2 * q.ntap + 12 < n2) ? 0 : 3;
+            }
+        }
+    } else {
+        q.mode = 1;
+    }
+    q.lnw_s = a.lnw0 + (double)q.i_s * a.dlnw;
+    q.inv_d2 = q.d2 != 0.0 ? 1.0 / q.d2 : 0.0;
+    q.slot_ok = slot_ok; q.teff_inf = r[PV_TEFF] == ms_inf();
+    if (q.mode == 3) fb_rows[atomicAdd(fb_count, 1)] = p;
+    out[p] = q;
+}
+
+__device__ __forceinline__ void fetch_setup(PointSetup *dst, const PointSetup *src) {       // 6 lanes x 16 bytes
+    if (threadIdx.x < sizeof(PointSetup) / 16) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<unsigned char *>(dst) + 16 * threadIdx.x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(reinterpret_cast<const unsigned char *>(src) + 16 * threadIdx.x) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(FT, 2)
-spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restrict__ fb_count) {
+spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int npix = a.npix, n1 = a.n1, M = n1 >> 1;
     float2 *z = reinterpret_cast<float2 *>(smem_raw);                        // padded complex buffer
@@ -330,65 +384,32 @@ spec_fast_kernel(SmoothArgs a, int nB, int *__restrict__ fb_rows, int *__restric
     __shared__ __align__(16) float wtab[4 * WSTRIDE];                        // FIR weights for the 4 window alignments
     __shared__ float gtap[MAXTAP + 2];
     __shared__ double red[FT / 32];
-    __shared__ PointSetup ps;
+    __shared__ __align__(16) PointSetup ps2[2];
     const float2 *twlev = static_cast<const float2 *>(a.twlev);
 
-    for (int p = blockIdx.x; p < nB; p += gridDim.x) {
+    if ((int)blockIdx.x < nB) fetch_setup(&ps2[0], setup + blockIdx.x);
+    int it = 0;
+    for (int p = blockIdx.x; p < nB; p += gridDim.x, ++it) {
         const double *r = a.pars + (size_t)p * MS_NPARS;
-        const int slot = a.star_slot ? a.star_slot[p] : a.slot0;
-        const bool slot_ok = (unsigned)slot < (unsigned)a.nstars;
-        const StarView sv = a.stars[slot_ok ? slot : 0];
-        if (threadIdx.x == 0) {
-            PointSetup q;
-            q.nobs = slot_ok ? sv.n_obs : 0;
-            q.i_s = 0; q.i_e = npix - 1; q.n2 = 0; q.ntap = 0; q.d2 = 0.0; q.ratio2 = 0.0; q.spx = 0.0;
-            const double vrad = r[PV_VRAD];
-            q.vrot = r[PV_VROT]; q.rot = q.vrot != 0.0;
-            q.inst = 2.355 * r[PV_INSTR];                                    // genmod.py:74-75
-            const double scale = (vrad != 0.0) ? 1.0 + vrad / MS_C_KMS : 1.0;
-            q.lnscale = log(scale);
-            if (r[PV_TEFF] == ms_inf() || q.nobs <= 0) q.mode = 4;
-            else if (q.inst != 0.0) {
-                if (!(q.inst == q.inst) || !(scale == scale)) q.mode = 2;
-                else {
-                    mask_window(a.wave, npix, a.lnw0, a.dlnw, scale, sv.wmin * (1.0 - 20.0 / q.inst),
-                                sv.wmax * (1.0 + 20.0 / q.inst), q.i_s, q.i_e);
-                    const int nmask = q.i_e - q.i_s + 1;
-                    const double so = MS_CKMS / q.inst, si = MS_CKMS / a.resolution;
-                    const double sigma = sqrt(so * so - si * si);            // NaN when sharper than the net
-                    if (nmask < 4) q.mode = 2;
-                    else if (sigma <= 0.0) q.mode = 1;
-                    else if (!(sigma == sigma)) q.mode = 3;                  // NaN kernel: let the generic kernel propagate it
-                    else {
-                        int n2 = 1; while (n2 < nmask) n2 <<= 1;
-                        q.n2 = n2;
-                        q.ratio2 = (double)(q.i_e - q.i_s) / (double)(n2 - 1);
-                        q.d2 = q.ratio2 * a.dlnw;
-                        q.spx = sigma / (MS_CKMS * q.d2);                    // kernel width in pixels of the n2 grid
-                        q.ntap = (int)ceil(5.5 * q.spx);
-                        q.mode = (q.spx >= 2.0 && q.ntap <= MAXTAP && 2 * q.ntap + 12 < n2) ? 0 : 3;
-                    }
-                }
-            } else {
-                q.mode = 1;
-            }
-            q.lnw_s = a.lnw0 + (double)q.i_s * a.dlnw;
-            if (q.mode == 3) fb_rows[atomicAdd(fb_count, 1)] = p;
-            ps = q;
-        }
+        asm volatile("cp.async.wait_all;" ::: "memory");                      // this point's record (issued one point ago)
         __syncthreads();
+        const PointSetup &ps = ps2[it & 1];
+        if (p + (int)gridDim.x < nB) fetch_setup(&ps2[(it & 1) ^ 1], setup + p + gridDim.x);
+        const bool slot_ok = ps.slot_ok != 0;
+        const int slot = a.star_slot ? a.star_slot[p] : a.slot0;
+        const StarView sv = a.stars[slot_ok ? slot : 0];
         const int mode = ps.mode, nobs = ps.nobs;
         if (mode >= 3) {                                                      // uniform: skipped or handed to the generic kernel
             if (mode == 4) {
                 if (a.flux_out && slot_ok)
                     for (int j = threadIdx.x; j < nobs; j += FT) a.flux_out[(size_t)p * nobs + j] = ms_nan();
-                if (a.chi2 && !slot_ok && threadIdx.x == 0 && r[PV_TEFF] != ms_inf()) a.chi2[p] = ms_nan();
+                if (a.chi2 && !slot_ok && threadIdx.x == 0 && !ps.teff_inf) a.chi2[p] = ms_nan();
             }
             __syncthreads();
             continue;
         }
         const int i_s = ps.i_s, i_e = ps.i_e, n2 = ps.n2, ntap = ps.ntap;
-        const double d2 = ps.d2, inst = ps.inst, inv_d2 = 1.0 / ps.d2;
+        const double d2 = ps.d2, inst = ps.inst, inv_d2 = ps.inv_d2;
         // ---- native spectrum -> shared memory
         {
             const float *frow = static_cast<const float *>(a.flux_native) + (size_t)p * npix;
@@ -573,14 +594,19 @@ bool spec_fast_two_per_sm(const ms_ctx *ctx) {
     return 2 * (fast_smem_bytes(ctx->spec.npix, ctx->spec.n1) + 1024 + 4096) <= 227 * 1024;
 }
 
-// Rows the kernel declines are appended to fb_rows / *fb_count (device; the caller zeroes the counter).
-int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, int *fb_rows, int *fb_count, cudaStream_t st) {
+// Rows the kernel declines are appended to fb_rows / *fb_count (device; the caller zeroes the counter).  setup: scratch
+// for nB PointSetup records.
+int launch_spec_fast(ms_ctx *ctx, const SmoothArgs &sa, int nB, void *setup, int *fb_rows, int *fb_count, cudaStream_t st) {
     const size_t smem = fast_smem_bytes(sa.npix, sa.n1);
     static size_t cfg = 0;
     if (cfg < smem) { MS_CUDA(cudaFuncSetAttribute(spec_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); cfg = smem; }
     int grid = ctx->sm_count * (spec_fast_two_per_sm(ctx) ? 2 : 1);
     if (grid > nB) grid = nB;
-    spec_fast_kernel<<<grid, FT, smem, st>>>(sa, nB, fb_rows, fb_count);
+    PointSetup *su = static_cast<PointSetup *>(setup);
+    spec_setup_kernel<<<(nB + 127) / 128, 128, 0, st>>>(sa, nB, su, fb_rows, fb_count);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    spec_fast_kernel<<<grid, FT, smem, st>>>(sa, nB, su);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

@@ -651,7 +651,8 @@ int spec_reserve(ms_ctx *ctx, int64_t max_batch) {
     if (max_batch < chunk) chunk = max_batch;
     const size_t flux_bytes = (size_t)chunk * n.npix * esz;
     const size_t hid_bytes = (size_t)chunk * (n.d_in + 2 * n.h) * esz;
-    const size_t fb_bytes = ((size_t)chunk + 4) * sizeof(int);
+    // fallback counter (16 B), PointSetup records and fallback rows of a full chunk
+    const size_t fb_bytes = 16 + (size_t)spec_chunk(ctx) * (sizeof(PointSetup) + sizeof(int));
     auto grow = [&](void **p, size_t *have, size_t need) -> int {
         if (*have >= need) return MS_OK;
         if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
@@ -707,7 +708,9 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         lsf = n_lsf > 0;
     }
     if (lsf && (size_t)lsf_nx_max * sizeof(T) > 200 * 1024) { ms_set_error("LSF resampling length %d too large", lsf_nx_max); return MS_EINVAL; }
-    int *fb_count = ctx->scr_fb, *fb_rows = ctx->scr_fb + 4;
+    int *fb_count = ctx->scr_fb;
+    PointSetup *fb_setup = reinterpret_cast<PointSetup *>(ctx->scr_fb + 4);
+    int *fb_rows = reinterpret_cast<int *>(fb_setup + chunk);
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
         int rc = spec_mlp_chunk_t<T>(ctx, a.pars + b0 * MS_NPARS, nb, (T *)ctx->scr_hid,
@@ -748,7 +751,7 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         } else if (fast) {
             // fast kernel; rows it declines (unusual broadening widths) go through the generic FFT kernel
             MS_CUDA(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
-            if ((rc = launch_spec_fast(ctx, sa, (int)nb, fb_rows, fb_count, st))) return rc;
+            if ((rc = launch_spec_fast(ctx, sa, (int)nb, fb_setup, fb_rows, fb_count, st))) return rc;
             if (!generic_fits) continue;
             sa.rows = fb_rows; sa.nrows = fb_count;
             const int64_t grid = nb < ctx->sm_count ? nb : ctx->sm_count;
