@@ -131,11 +131,13 @@ __device__ __forceinline__ void real_pair(float2 &A, float2 &B, const float2 u, 
 }
 
 struct RotTransfer {
-    double coef; const float *tab; float inv;
+    // u = coef k in f32: relative error 6e-8 of u, i.e. < 2e-5 at the end of the table where the transfer function
+    // (~ u^-3/2) and its slope are below 3e-4 -- far inside the fp32 budget of the spectrum itself
+    float coef; const float *tab; float inv;
     __device__ __forceinline__ float operator()(int k) const {
-        const double u = coef * (double)k;
+        const float u = coef * (float)k;
         if (!(u == u)) return __int_as_float(0x7fc00000);
-        return inv * rot_transfer_f((float)u, tab);
+        return inv * rot_transfer_f(u, tab);
     }
 };
 
@@ -274,7 +276,7 @@ __device__ __noinline__ void rotational_filter_ip(float2 *z, const float *fr, in
     const double step1 = (double)(npix - 1) * dlnw / (double)(n1 - 1);
     RotTransfer tf;
     tf.tab = rot_tab; tf.inv = 1.f / (float)M;
-    tf.coef = 2.0 * M_PI * sqrt(vrot * vrot) / ((double)n1 * MS_CKMS * step1);
+    tf.coef = (float)(2.0 * M_PI * sqrt(vrot * vrot) / ((double)n1 * MS_CKMS * step1));
     if (pl.lM == 13) {
         // n1 = 16384 (nets of 8193 .. 16384 pixels): the same stage list with every length a literal, so strides, masks
         // and the digit reversal fold into immediates
@@ -379,7 +381,7 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
     const int npix = a.npix, n1 = a.n1, M = n1 >> 1;
     float2 *z = reinterpret_cast<float2 *>(smem_raw);                        // padded complex buffer
     float *s2 = reinterpret_cast<float *>(smem_raw);                         // later: the n2-point instrumental grid
-    const size_t fr_off = (size_t)padi(M) * sizeof(float2) + 16;
+    const size_t fr_off = (((size_t)padi(M) * sizeof(float2) + 15) & ~(size_t)15) + 16;
     float *fr = reinterpret_cast<float *>(smem_raw + fr_off);                // native / rotated spectrum
     __shared__ __align__(16) float wtab[4 * WSTRIDE];                        // FIR weights for the 4 window alignments
     __shared__ float gtap[MAXTAP + 2];
@@ -389,6 +391,7 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
 
     if ((int)blockIdx.x < nB) fetch_setup(&ps2[0], setup + blockIdx.x);
     int it = 0;
+    bool fr_ready = false;                 // this point's native spectrum was fetched during the previous point's last phase
     for (int p = blockIdx.x; p < nB; p += gridDim.x, ++it) {
         const double *r = a.pars + (size_t)p * MS_NPARS;
         asm volatile("cp.async.wait_all;" ::: "memory");                      // this point's record (issued one point ago)
@@ -405,22 +408,28 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
                     for (int j = threadIdx.x; j < nobs; j += FT) a.flux_out[(size_t)p * nobs + j] = ms_nan();
                 if (a.chi2 && !slot_ok && threadIdx.x == 0 && !ps.teff_inf) a.chi2[p] = ms_nan();
             }
+            fr_ready = false;
             __syncthreads();
             continue;
         }
         const int i_s = ps.i_s, i_e = ps.i_e, n2 = ps.n2, ntap = ps.ntap;
         const double d2 = ps.d2, inst = ps.inst, inv_d2 = ps.inv_d2;
-        // ---- native spectrum -> shared memory
+        // ---- native spectrum -> shared memory (unless the previous point's last phase already fetched it)
         {
             const float *frow = static_cast<const float *>(a.flux_native) + (size_t)p * npix;
-            if ((npix & 3) == 0) {
-                const float4 *src4 = reinterpret_cast<const float4 *>(frow);
-                float4 *dst4 = reinterpret_cast<float4 *>(fr);
-                for (int i = threadIdx.x; i < (npix >> 2); i += FT) dst4[i] = __ldcs(src4 + i);
+            if (fr_ready) {
+                if (threadIdx.x == FT - 1) fr[npix] = fr[npix - 1];
             } else {
-                for (int i = threadIdx.x; i < npix; i += FT) fr[i] = __ldcs(frow + i);
+                if ((npix & 3) == 0) {
+                    const float4 *src4 = reinterpret_cast<const float4 *>(frow);
+                    float4 *dst4 = reinterpret_cast<float4 *>(fr);
+                    for (int i = threadIdx.x; i < (npix >> 2); i += FT) dst4[i] = __ldcs(src4 + i);
+                } else {
+                    for (int i = threadIdx.x; i < npix; i += FT) fr[i] = __ldcs(frow + i);
+                }
+                if (threadIdx.x == FT - 1) fr[npix] = __ldcs(frow + npix - 1);   // one-sample pad: interpolation at the last pixel
             }
-            if (threadIdx.x == FT - 1) fr[npix] = __ldcs(frow + npix - 1);   // one-sample pad: interpolation at the last pixel
+            fr_ready = false;
         }
         if (mode == 0 && threadIdx.x <= ntap) {                               // Gaussian taps, t = 0 .. ntap
             const double t = (double)threadIdx.x / ps.spx;
@@ -471,6 +480,16 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
             }
         }
         __syncthreads();
+        // the native spectrum is dead from here on in this mode: fetch the next point's row into its place while the
+        // Gaussian sums run (async copies, waited for at the top of the next iteration)
+        if (mode == 0 && (npix & 3) == 0 && p + (int)gridDim.x < nB) {
+            const float *nrow = static_cast<const float *>(a.flux_native) + (size_t)(p + gridDim.x) * npix;
+            const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(fr);
+            for (int i = threadIdx.x; i < (npix >> 2); i += FT)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * (uint32_t)i), "l"(nrow + 4 * i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            fr_ready = true;
+        }
         double csum = 0.0;
         const double lnw_s = ps.lnw_s;
         const int mask2 = n2 - 1;
@@ -578,7 +597,7 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
 size_t fast_smem_bytes(int npix, int n1) {
     const int M = n1 >> 1;
     const size_t fr_bytes = ((size_t)(npix + 1) * sizeof(float) + 15) & ~(size_t)15;
-    return (size_t)(M + (M >> 4)) * sizeof(float2) + 16 + fr_bytes + 16;
+    return (((size_t)(M + (M >> 4)) * sizeof(float2) + 15) & ~(size_t)15) + 16 + fr_bytes + 16;
 }
 
 }  // namespace
