@@ -18,7 +18,8 @@
 // tile i+1.  Warp 0 = producer, warp 1 = MMA issuer, warps 2-5 = epilogue (TMEM -> registers
 // -> + bias -> global).  Tiles are ordered m-fastest so concurrently running CTAs share the
 // same weight tile through L2.  L2 -> shared operand traffic (64 KB per 64-wide K chunk) is what
-// bounds the output-layer GEMM, not the tensor pipe.
+// bounds the output-layer GEMM, not the tensor pipe: measured 21 B/clk inbound per SM (5.2 TB/s on the chip) whether
+// 48 or 148 CTAs run, against the 85 B/clk a tensor-bound 128 x 128 split-precision tile would need.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -133,31 +134,35 @@ spec_gemm_tc_kernel(GemmArgs a) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int g = 0, it = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(bar(BAR_ACC_EMPTY + buf), ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        // MMA issuer: the whole warp runs the loop converged and one elected lane issues.  Every operand is
+        // warp-uniform, so descriptors live in uniform registers and the MMAs of a K chunk are back-to-back
+        // instructions (a divergent `if (lane == 0)` makes the compiler wrap each one in an elect / branch loop,
+        // ~130 clk per MMA: measured on the photometric kernel, and the reason this GEMM sat at 23 % tensor use).
+        int g = 0, it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(bar(BAR_ACC_EMPTY + buf), ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem + buf * BN;
+            for (int kc = 0; kc < nkc; ++kc, ++g) {
+                const int st = g % STAGES;
+                mbar_wait(bar(BAR_FULL + st), (g / STAGES) & 1);
                 tc_fence_after();
-                const uint32_t d = tmem + buf * BN;
-                for (int kc = 0; kc < nkc; ++kc, ++g) {
-                    const int st = g % STAGES;
-                    mbar_wait(bar(BAR_FULL + st), (g / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t sa = sbase + st * STAGE_BYTES;
+                const uint32_t sa = sbase + st * STAGE_BYTES;
+                const uint64_t ah0 = make_desc(sa, 2048, 128), al0 = make_desc(sa + OPER_BYTES, 2048, 128);
+                const uint64_t bh0 = make_desc(sa + 2 * OPER_BYTES, 2048, 128), bl0 = make_desc(sa + 3 * OPER_BYTES, 2048, 128);
+                if (elect_one()) {
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) {
-                        const uint64_t ah = make_desc(sa + ks * 4096, 2048, 128);
-                        const uint64_t al = make_desc(sa + OPER_BYTES + ks * 4096, 2048, 128);
-                        const uint64_t bh = make_desc(sa + 2 * OPER_BYTES + ks * 4096, 2048, 128);
-                        const uint64_t bl = make_desc(sa + 3 * OPER_BYTES + ks * 4096, 2048, 128);
-                        mma_ss(d, ah, bh, (kc | ks) != 0, IDESC);
-                        mma_ss(d, al, bh, 1, IDESC);
-                        mma_ss(d, ah, bl, 1, IDESC);
+                        const uint64_t o = (uint64_t)(ks * (4096 / 16));          // start-address field advances by 4096 B
+                        mma_ss(d, ah0 + o, bh0 + o, (kc | ks) != 0, IDESC);
+                        mma_ss(d, al0 + o, bh0 + o, 1, IDESC);
+                        mma_ss(d, ah0 + o, bl0 + o, 1, IDESC);
                     }
                     tc_commit(bar(BAR_EMPTY + st));                            // stage reusable once these MMAs retire
+                    if (kc == nkc - 1) tc_commit(bar(BAR_ACC_FULL + buf));
                 }
-                tc_commit(bar(BAR_ACC_FULL + buf));
+                __syncwarp();
             }
         }
     } else {
