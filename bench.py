@@ -418,11 +418,13 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = B * world * args.steps / float(te.item())
-    # the host entry point evaluates chunk by chunk; a short last chunk takes the two-kernel form, which agrees with
-    # the one-kernel form to rounding (log10 Teff from the table vs log10(10**x))
+    # the host entry point evaluates chunk by chunk; a short last chunk takes the two-kernel form (f64 corner sums), the
+    # one-kernel form sums the corners in f32: they agree to the fp32-class magnitude tolerance (1e-5 mag in every band)
     dev_l = lnl.cpu().numpy()
-    assert np.array_equal(np.isfinite(out_h), np.isfinite(dev_l)) and \
-        np.allclose(out_h[np.isfinite(dev_l)], dev_l[np.isfinite(dev_l)], rtol=1e-12, atol=1e-9), \
+    fin_ = np.isfinite(dev_l)
+    sig_min = min(float(v[1]) for v in fitargs['obs_phot'].values())
+    tol_hd = 1e-5 * np.sqrt(2.0 * np.abs(dev_l[fin_]) * len(fitargs['obs_phot'])) / sig_min + 1e-6
+    assert np.array_equal(np.isfinite(out_h), fin_) and np.all(np.abs(out_h[fin_] - dev_l[fin_]) <= tol_hd), \
         'host and device entry points disagree'
 
     # ---- in-run parity: the output of the timed (fused) kernel itself against the oracle sample

@@ -138,4 +138,67 @@ __device__ __forceinline__ bool interp_point(const double *const g[4], const int
     return inside;
 }
 
+// fp32-class form for the prologue of the tensor-core photometry kernel (f32 table): the brackets are found exactly as
+// above (f64 comparisons: bit-exact cells), but the weights and the 16-corner sums are f32 -- the sums feed f32 network
+// inputs and a distance modulus with an fp32-class tolerance, and the kernel is bound by instruction issue, where every
+// f64 instruction costs two slots.  Same corner order, same renormalisation; results agree with interp_point to ~2e-7.
+// The two columns that enter the distance modulus with a factor of 5 and 10 (log R, log Teff) are ALSO summed in f64
+// with the same f32 weights (accd[0], accd[1], wsumd): a rounded weight only moves the ratio by its error times the
+// spread of the corner values, so these two come out at ~1e-9 instead of one f32 ulp of 3.7 (2.4e-6 mag after x 10).
+template <int ROWS = 2>
+__device__ __forceinline__ bool interp_point_f32(const double *const g[4], const int n[4], const float *__restrict__ table,
+                                                 const double x[4], int idx[4], float acc[MS_NCOL], float &wsum,
+                                                 double accd[2], double &wsumd) {
+    constexpr int CP = MS_CP32;
+    const int ne = n[0], nm = n[1], nf = n[2];
+    float wl[4], wu[4];
+    bool inside = true;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        int i = bracket_of(g[d], n[d], x[d]);
+        idx[d] = i;
+        inside = inside && (i >= 0) && (i <= n[d] - 2);
+        int ic = inside ? i : 0;
+        const double g0 = g[d][ic];
+        const float frac = __fdividef((float)(x[d] - g0), (float)(g[d][ic + (n[d] > 1 ? 1 : 0)] - g0));
+        wl[d] = 1.f - frac;
+        wu[d] = frac > 0.f ? frac : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < MS_NCOL; ++c) acc[c] = 0.f;
+    wsum = 0.f;
+    accd[0] = accd[1] = 0.0; wsumd = 0.0;
+    if (inside) {
+        const int64_t sE = CP, sM = (int64_t)ne * CP, sF = (int64_t)nm * sM, sA = (int64_t)nf * sF;
+        const float *base = table + idx[3] * sA + idx[2] * sF + idx[1] * sM + idx[0] * sE;
+#pragma unroll
+        for (int k0 = 0; k0 < 16; k0 += ROWS) {
+            Row<float>::Raw raw[ROWS];
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                const int k = k0 + j;
+                raw[j] = Row<float>::fetch(base + ((k >> 2) & 1) * sA + (k >> 3) * sF + ((k >> 1) & 1) * sM + (k & 1) * sE);
+            }
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                const int k = k0 + j;
+                const int cf = k >> 3, ca = (k >> 2) & 1, cm = (k >> 1) & 1, ce = k & 1;
+                float w = (ce ? wu[0] : wl[0]) * (cm ? wu[1] : wl[1]);
+                w = w * ((cf ? wu[2] : wl[2]) * (ca ? wu[3] : wl[3]));
+                const Row<float>::Raw &r = raw[j];
+                if (w > 0.f && r.a.x == r.a.x) {       // weight present, vertex present
+                    wsum += w;
+                    const double wd = (double)w;
+                    wsumd += wd;
+                    accd[0] = fma(wd, (double)r.a.z, accd[0]); accd[1] = fma(wd, (double)r.b.x, accd[1]);
+                    acc[0] = fmaf(w, r.a.x, acc[0]); acc[1] = fmaf(w, r.a.y, acc[1]); acc[2] = fmaf(w, r.a.z, acc[2]);
+                    acc[3] = fmaf(w, r.a.w, acc[3]); acc[4] = fmaf(w, r.b.x, acc[4]); acc[5] = fmaf(w, r.b.y, acc[5]);
+                    acc[6] = fmaf(w, r.b.z, acc[6]); acc[7] = fmaf(w, r.b.w, acc[7]); acc[8] = fmaf(w, r.c.x, acc[8]);
+                }
+            }
+        }
+    }
+    return inside;
+}
+
 }  // namespace mist

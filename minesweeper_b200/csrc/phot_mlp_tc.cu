@@ -120,6 +120,15 @@ struct TcArgs {
     double *derived;                   // [B][MS_NDERIVED] or nullptr
 };
 
+#ifdef MS_PHOT_STAMPS
+// tuning builds only (MS_BUILD_VARIANT): clock64 stamps of CTA 0, one fixed slot per (pair, event), read back once
+__device__ long long g_stamps[8192];
+__device__ long long g_cta[148 * 8];
+#define STAMP(pair, ev) do { if (blockIdx.x == 0 && (pair) < 1000) g_stamps[(pair) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define STAMP(pair, ev) do { } while (0)
+#endif
+
 // one instantiation of the kernel family per supported hidden width
 struct TcVariant {
     int h, band_bytes, const_bytes, sm_fixed, max_nb;
@@ -246,3 +255,10 @@ int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, do
     if (!phot_tc_can_fuse(ctx)) { ms_set_error("fused interpolation + photometry does not fit this model"); return MS_ESTATE; }
     return launch_tc(ctx, a, B, st, &tv, derived, mistdif);
 }
+
+#ifdef MS_PHOT_STAMPS
+extern "C" int ms_debug_read_cta(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_cta, sizeof(long long) * 148 * 8); }
+extern "C" int ms_debug_read_stamps(long long *out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_stamps, sizeof(long long) * (size_t)(n < 8192 ? n : 8192));
+}
+#endif

@@ -44,6 +44,13 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem_base;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MS_PHOT_STAMPS
+    if (threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_cta[blockIdx.x * 8 + 0] = clock64(); g_cta[blockIdx.x * 8 + 2] = (long long)gt; g_cta[blockIdx.x * 8 + 4] = sm;
+    }
+#endif
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar0 = sbase + SM_BAR;
     auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -158,7 +165,9 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         const int tid = threadIdx.x - 19 * 32;
         for (int it = 0; it < my_pairs; ++it) {
             const int xbuf = it & 1;
+            if (tid == 0) STAMP(it, 0);
             mbar_wait(bar(BAR_XEMPTY + xbuf), ((it >> 1) & 1) ^ 1);
+            if (tid == 0) STAMP(it, 1);
             const int pr = blockIdx.x + it * gridDim.x;
 #pragma unroll 1
             for (int T = 0; T < 2; ++T) {
@@ -180,27 +189,33 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         x[2] = theta_get(a.tv, p, MS_P_INIT_FEH);
                         x[3] = theta_get(a.tv, p, MS_P_INIT_AFE);
                         int idx[4];
-                        double acc[MS_NCOL], wsum;
-                        const bool inside = mist::interp_point<float, FAST ? 1 : 2>(g, n, a.table, x, idx, acc, wsum);   // rows per round trip: measured
-                        const bool okp = inside && (wsum > 0.0);
-                        const double inv = okp ? 1.0 / wsum : 0.0;
+                        float acc[MS_NCOL], wsum;
+                        double accd[2], wsumd;
+                        const bool inside = mist::interp_point_f32<FAST ? 1 : 2>(g, n, a.table, x, idx, acc, wsum, accd, wsumd);   // rows per round trip: measured
+                        const bool okp = inside && (wsum > 0.f);
+                        const float inv = okp ? __fdividef(1.f, wsum) : 0.f;
                         const double inf = ms_inf();
                         // Teff = 10**log(Teff) (likelihood.py:121) is only needed as a network input here;
                         // genphot's log10(Teff) (genmod.py:111) is the interpolated value itself
-                        logt = acc[4] * inv;
-                        teff = okp ? exp10(logt) : inf;
-                        logg = okp ? acc[7] * inv : inf;
-                        feh = okp ? (a.mistdif ? acc[5] * inv : x[2]) : inf;     // :127-132
-                        afe = okp ? (a.mistdif ? acc[6] * inv : x[3]) : inf;
-                        logr = okp ? acc[2] * inv : inf;
-                        ps.agewgt = okp ? acc[8] * inv : inf;
+                        const double invd = okp ? 1.0 / wsumd : 0.0;
+                        logt = accd[1] * invd;
+                        // 10**logt from the f64 sum: f32 exponential of the rounded value times the first-order term of
+                        // the remainder (an f32 logt alone would cost 9e-7 of Teff: ln 10 times one ulp of 3.7)
+                        const float lt_hi = (float)logt, lt_lo = (float)(logt - (double)lt_hi);
+                        teff = okp ? (double)(exp10f(lt_hi) * fmaf(2.302585093f, lt_lo, 1.f)) : inf;
+                        logg = okp ? (double)(acc[7] * inv) : inf;
+                        feh = okp ? (a.mistdif ? (double)(acc[5] * inv) : x[2]) : inf;     // :127-132
+                        afe = okp ? (a.mistdif ? (double)(acc[6] * inv) : x[3]) : inf;
+                        logr = okp ? accd[0] * invd : inf;
+                        ps.agewgt = okp ? (double)(acc[8] * inv) : inf;
                         dist = theta_get(a.tv, p, MS_P_DIST);
                         av = theta_get(a.tv, p, MS_P_AV);
                         if (a.derived) {
                             double *o = a.derived + p * MS_NDERIVED;
                             o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
 #pragma unroll
-                            for (int c = 0; c < MS_NCOL; ++c) o[4 + c] = okp ? acc[c] * inv : inf;
+                            for (int c = 0; c < MS_NCOL; ++c)
+                                o[4 + c] = okp ? (c == 2 ? logr : (c == 4 ? logt : (double)(acc[c] * inv))) : inf;
                         }
                     } else {
                         const double *q = a.pars + p * MS_NPARS;
@@ -243,6 +258,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             }
             fence_proxy_async();
             __syncwarp();
+            if (tid == 0) STAMP(it, 2);
             if (lane == 0) mbar_arrive(bar(BAR_XFULL + xbuf));
         }
     } else {
@@ -264,8 +280,10 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             bool ok = false;
             double mag0 = 0.0, agewgt = 1.0;
             int slot = 0;
+            if (threadIdx.x == 0) STAMP(it, 3);
             if (half == 0) {                           // point state from the prologue warpgroup
                 mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+                if (threadIdx.x == 0) STAMP(it, 4);
                 const PointState ps = reinterpret_cast<const PointState *>(smem + SM_PT)[((it & 1) * 2 + T) * TILE + r];
                 ok = ps.ok != 0; mag0 = ps.mag0; agewgt = ps.agewgt; slot = ps.slot;
                 __syncwarp();
@@ -371,6 +389,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     a.mags[p * a.nb_total + a.b0 + b] = ms_nan();
                 }
             }
+            if (threadIdx.x == 0) STAMP(it, 5);
             if (half == 1) continue;
             if (live && a.lnL) {
                 double l = -ms_inf();
@@ -388,6 +407,12 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     }
     tc_fence_before();
     __syncthreads();
+#ifdef MS_PHOT_STAMPS
+    if (threadIdx.x == 0) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_cta[blockIdx.x * 8 + 1] = clock64(); g_cta[blockIdx.x * 8 + 3] = (long long)gt;
+    }
+#endif
     if (warp == 16) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(4 * H) : "memory");
     }

@@ -436,10 +436,10 @@ def test_empty_and_degenerate_batches(g_like_phot):
 @pytest.mark.parametrize('prec', ['tc', 'tc16'])
 @pytest.mark.parametrize('n', [148 * 256 * 4, 148 * 256 * 5 + 19])
 def test_fused_interp_phot_matches_two_kernel_sequence(prec, n):
-    """Tensor-core modes: the one-kernel form (MIST interpolation inside the MLP kernel's prologue) and the
-    interpolation kernel followed by the MLP kernel share the interpolation code: the derived block is
-    bit-identical and lnL agrees to rounding, including out-of-grid rows and an unobserved band; the launch
-    count drops."""
+    """Tensor-core modes: the one-kernel form (MIST interpolation inside the MLP kernel's prologue: same cells --
+    f64 bracket comparisons -- but f32 weights and corner sums, csrc/mist_interp.cuh:interp_point_f32) against the
+    interpolation kernel followed by the MLP kernel: derived block to 1e-6, lnL to the fp32-class bound, including
+    out-of-grid rows and an unobserved band; the launch count drops."""
     from minesweeper_b200 import synth
     from minesweeper_b200.likelihood import likelihood
     mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
@@ -467,10 +467,14 @@ def test_fused_interp_phot_matches_two_kernel_sequence(prec, n):
     lf, lu, df, du = (t.cpu().numpy() for t in (lf, lu, df, du))
     assert np.array_equal(np.isneginf(lf), np.isneginf(lu))
     fin = np.isfinite(lf)
-    # same interpolation code, so the derived block is identical; the one-kernel form takes log10(Teff) straight
-    # from the interpolated column instead of log10(10**x): lnL agrees to rounding
-    assert np.array_equal(df, du)
-    np.testing.assert_allclose(lf[fin], lu[fin], rtol=1e-12, atol=1e-9)
+    # same cells, f32 sums in the one-kernel form: the derived block agrees to 2e-6 (values of order 0.1 .. 1e4) and
+    # lnL to what the fp32-class magnitude tolerance (1e-5 mag; measured 3e-6: network inputs one f32 ulp apart) of
+    # every band can do at these residuals (sigma = 0.02 .. 0.05 mag)
+    assert np.array_equal(np.isposinf(df), np.isposinf(du))
+    ok_ = np.isfinite(du).all(1)
+    np.testing.assert_allclose(df[ok_], du[ok_], rtol=2e-6, atol=2e-6)
+    tol = 1e-5 * np.sqrt(2.0 * np.abs(lu[fin]) * 10) / 0.02 + 1e-6
+    assert np.all(np.abs(lf[fin] - lu[fin]) <= tol), ((np.abs(lf[fin] - lu[fin]) / tol).max(), np.abs(lf[fin] - lu[fin]).max())
     assert np.isneginf(lf).sum() > 0 or n < 50
 
 
@@ -509,7 +513,8 @@ def test_fused_interp_phot_with_star_slots():
     lu = L.lnlike_batch(th, want_derived=False, star_slot=slot)[0].cpu().numpy()
     fin = np.isfinite(lu)
     assert np.array_equal(fin, np.isfinite(lf)) and fin.sum() > n // 2
-    np.testing.assert_allclose(lf[fin], lu[fin], rtol=1e-12, atol=1e-9)
+    tol = 1e-5 * np.sqrt(2.0 * np.abs(lu[fin]) * nb) / 0.05 + 1e-6          # f32 corner sums in the one-kernel form
+    assert np.all(np.abs(lf[fin] - lu[fin]) <= tol), ((np.abs(lf[fin] - lu[fin]) / tol).max(), np.abs(lf[fin] - lu[fin]).max())
     s = 3
     pick = np.flatnonzero(slot.cpu().numpy() == s)[:2000]
     L.engine.set_star(0, (mags[s], errs[s]))
@@ -600,7 +605,8 @@ def test_headline_config_fused_vs_oracle_full_grid():
     L.engine.set_fusion(False)
     l2, d2, br = L.lnlike_batch(th, want_brackets=True)
     assert np.array_equal(br.cpu().numpy(), ref['brackets'])
-    np.testing.assert_array_equal(d2.cpu().numpy(), der)
+    d2 = d2.cpu().numpy()
+    np.testing.assert_allclose(d2[ok], der[ok], rtol=2e-6, atol=2e-6)             # f64 sums (two kernels) vs f32 sums (fused)
     # magnitudes of the tensor-core MLP at the interpolated parameters
     mags = L.engine.phot_sed(ref['photpars'][ok][:65536]).cpu().numpy()
     np.testing.assert_allclose(mags, ref['mags'][ok][:65536], rtol=1e-5, atol=1e-5)
