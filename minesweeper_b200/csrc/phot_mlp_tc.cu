@@ -108,6 +108,7 @@ struct TcArgs {
     double *peers[MS_MAX_PEERS]; int npeers; int64_t peer_off;
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
+    int *sched;                        // [2]: next pair beyond the first wave, CTAs that have left (both 0 between launches)
     double xmin[8], xscale[8];
     int nb, d_in;                      // bands of this launch (a group when the net has more than MAX_NB)
     int nb_total, b0;                  // row length of obs / mags and the first band of the group
@@ -167,8 +168,9 @@ int phot_tc_prepare(ms_ctx *ctx) {
     std::vector<unsigned char> img;
     int rc = V->pack(ctx, img);
     if (rc) return rc;
-    MS_CUDA(cudaMalloc(&P.tc_pack, img.size()));
+    MS_CUDA(cudaMalloc(&P.tc_pack, img.size() + 64));            // + the pair scheduler's two counters
     MS_CUDA(cudaMemcpy(P.tc_pack, img.data(), img.size(), cudaMemcpyHostToDevice));
+    MS_CUDA(cudaMemset(static_cast<unsigned char *>(P.tc_pack) + img.size(), 0, 64));
     P.tc_pack_bytes = img.size();
     MS_CUDA(cudaFuncSetAttribute(V->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     MS_CUDA(cudaFuncSetAttribute(V->kern_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -193,6 +195,7 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
     ka.d_in = n.d_in; ka.nb_total = n.nb;
+    ka.sched = reinterpret_cast<int *>(static_cast<unsigned char *>(n.tc_pack) + n.tc_pack_bytes);
     ka.fused = tv != nullptr;
     int smem_extra = 0;
     if (tv) {

@@ -43,6 +43,11 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint32_t s_tmem_base;
+    // Pairs are handed out dynamically (a.sched[0] = next pair beyond the first wave): SMs differ by a few per cent in
+    // speed and 4096 pairs are not a multiple of 148, so a static round-robin leaves the slowest CTA 5 % behind the
+    // median.  The prologue warpgroup, one pair ahead, draws the index and publishes it here before it arrives on the
+    // pair's XFULL barrier; every other role reads it after its own XFULL wait.  An index >= npairs ends the CTA.
+    __shared__ int s_pair[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef MS_PHOT_STAMPS
     if (threadIdx.x == 0) {
@@ -84,19 +89,21 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = s_tmem_base;
-    int my_pairs = 0;
-    for (int pr = blockIdx.x; pr < npairs; pr += gridDim.x) ++my_pairs;
 
     if (warp == 18) {
         // ===== weight producer =====
         if (lane == 0) {
-            const int total = my_pairs * nb;
-            for (int g = 0; g < total; ++g) {
-                const int buf = g & 1;
-                mbar_wait(bar(BAR_WEMPTY + buf), ((g >> 1) & 1) ^ 1);
-                mbar_expect_tx(bar(BAR_WFULL + buf), RING_BYTES);
-                bulk_g2s(sbase + SM_W + buf * RING_BYTES, a.wimg + (size_t)(g % nb) * BAND_BYTES, RING_BYTES,
-                         bar(BAR_WFULL + buf));
+            int g = 0;
+            for (int it = 0;; ++it) {
+                mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+                if (*(volatile int *)&s_pair[it & 3] >= npairs) break;
+                for (int b = 0; b < nb; ++b, ++g) {
+                    const int buf = g & 1;
+                    mbar_wait(bar(BAR_WEMPTY + buf), ((g >> 1) & 1) ^ 1);
+                    mbar_expect_tx(bar(BAR_WFULL + buf), RING_BYTES);
+                    bulk_g2s(sbase + SM_W + buf * RING_BYTES, a.wimg + (size_t)b * BAND_BYTES, RING_BYTES,
+                             bar(BAR_WFULL + buf));
+                }
             }
         }
     } else if (warp == 16 || warp == 17) {
@@ -120,11 +127,12 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 w2h[i] = make_desc(wb + OFF_W2H, WLBO, 128); w2l[i] = make_desc(wb + OFF_W2L, WLBO, 128);
             }
             int g = 0;
-            for (int it = 0; it < my_pairs; ++it) {
+            for (int it = 0;; ++it) {
+                mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+                if (*(volatile int *)&s_pair[it & 3] >= npairs) break;
                 for (int b = 0; b < nb; ++b, ++g) {
                     const int buf = g & 1;
                     mbar_wait(bar(BAR_WFULL + buf), (g >> 1) & 1);
-                    if (b == 0) mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
                     const uint64_t xh = xh0 + (uint64_t)((it & 1) * (4 * X_BYTES / 16));
                     const uint64_t xl = xl0 + (uint64_t)((it & 1) * (4 * X_BYTES / 16));
                     tc_fence_after();
@@ -163,12 +171,18 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         // (GenMod.genphot, genmod.py:97-142), one pair ahead of the epilogue so the f64 logarithms and the
         // strided loads of the parameter block never sit on the critical path.
         const int tid = threadIdx.x - 19 * 32;
-        for (int it = 0; it < my_pairs; ++it) {
+        for (int it = 0;; ++it) {
             const int xbuf = it & 1;
             if (tid == 0) STAMP(it, 0);
+            if (tid == 0) s_pair[it & 3] = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.sched, 1);
             mbar_wait(bar(BAR_XEMPTY + xbuf), ((it >> 1) & 1) ^ 1);
+            asm volatile("bar.sync 3, 128;" ::: "memory");              // the four prologue warps: index visible
             if (tid == 0) STAMP(it, 1);
-            const int pr = blockIdx.x + it * gridDim.x;
+            const int pr = s_pair[it & 3];
+            if (pr >= npairs) {                                           // publish the end marker and stop
+                if (lane == 0) mbar_arrive(bar(BAR_XFULL + xbuf));
+                break;
+            }
 #pragma unroll 1
             for (int T = 0; T < 2; ++T) {
                 const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + tid;
@@ -272,9 +286,11 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         int g = 0;
         // skew: tile 1 starts when tile 0 has finished its first layer-1 epilogue, so that one tile's waits for
         // the tensor pipe fall into the other tile's activation phases instead of coinciding with its own
-        if (T == 1 && my_pairs > 0) mbar_wait(bar(BAR_A1 + NCH - 1), 0);
-        for (int it = 0; it < my_pairs; ++it) {
-            const int pr = blockIdx.x + it * gridDim.x;
+        if (T == 1) mbar_wait(bar(BAR_A1 + NCH - 1), 0);
+        for (int it = 0;; ++it) {
+            mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+            const int pr = *(volatile int *)&s_pair[it & 3];
+            if (pr >= npairs) break;
             const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + r;
             const bool live = half == 0 && p < B;
             bool ok = false;
@@ -282,7 +298,6 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             int slot = 0;
             if (threadIdx.x == 0) STAMP(it, 3);
             if (half == 0) {                           // point state from the prologue warpgroup
-                mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
                 if (threadIdx.x == 0) STAMP(it, 4);
                 const PointState ps = reinterpret_cast<const PointState *>(smem + SM_PT)[((it & 1) * 2 + T) * TILE + r];
                 ok = ps.ok != 0; mag0 = ps.mag0; agewgt = ps.agewgt; slot = ps.slot;
@@ -407,6 +422,8 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     }
     tc_fence_before();
     __syncthreads();
+    // the last CTA to leave re-arms the pair counter for the next launch (every CTA has drawn its end marker by then)
+    if (threadIdx.x == 0 && atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1) { a.sched[0] = 0; a.sched[1] = 0; __threadfence(); }
 #ifdef MS_PHOT_STAMPS
     if (threadIdx.x == 0) {
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
