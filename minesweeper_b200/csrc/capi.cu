@@ -312,6 +312,8 @@ extern "C" void ms_destroy(ms_ctx *ctx) {
     cudaFree(ctx->scr_flux); cudaFree(ctx->scr_hid); cudaFree(ctx->scr_theta); cudaFree(ctx->scr_out);
     for (auto &r : ctx->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    cudaFree(ctx->rows_ready_dev);
+    if (ctx->rows_ready_host) cudaFreeHost(ctx->rows_ready_host);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
@@ -633,6 +635,86 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
     if ((rc = ensure_scratch(ctx, &ctx->scr_theta, &ctx->scr_theta_n, (size_t)B * ndim, ctx->own_stream))) return rc;
     if ((rc = ensure_scratch(ctx, &ctx->scr_out, &ctx->scr_out_n, (size_t)B * (1 + MS_NDERIVED), ctx->own_stream))) return rc;
     double *lnl_d = ctx->scr_out, *der_d = derived_host ? ctx->scr_out + B : nullptr;
+    // Streaming form (photometry-only isochrone batches on the tensor-core path, no derived block): ONE launch of the
+    // fused kernel starts as soon as the first rows have landed; theta keeps arriving in chunks on the copy stream, each
+    // followed by a 4-byte copy that advances a device counter the kernel's prologue waits on before it touches a pair's
+    // rows, and lnL is stored straight into the caller's buffer when that is pinned, device-mapped host memory
+    // (PCIe posted writes of 256 B per warp).  No per-chunk launches (each costs a non-overlapped first prologue and a
+    // tail), no device->host copy behind the last kernel.
+    {
+        ThetaView tv0;
+        identity_view(tv0, nullptr, ndim);
+        if (fixed) for (int i = 0; i < MS_NPARAM; ++i) tv0.fixed[i] = fixed[i];
+        for (int c = 0; c < ndim; ++c) tv0.col[colmap[c]] = c;
+        const bool iso = tv0.col[MS_P_EEP] >= 0 || tv0.fixed[MS_P_EEP] == tv0.fixed[MS_P_EEP];
+        const int64_t wave = (int64_t)ctx->sm_count * 256;
+        if (iso && flags->phot && !flags->spec && !derived_host && ctx->fuse_interp && ctx->precision >= MS_PREC_TC &&
+            B >= 4 * wave && B < (int64_t)1 << 31 && phot_tc_can_fuse(ctx) && !ctx->npeers) {
+            const int kChunks = 8;
+            if (!ctx->rows_ready_dev) {
+                MS_CUDA(cudaMalloc((void **)&ctx->rows_ready_dev, sizeof(int)));
+                MS_CUDA(cudaHostAlloc((void **)&ctx->rows_ready_host, (kChunks + 2) * sizeof(int), cudaHostAllocDefault));
+            }
+            while (ctx->ev_pool.size() < 2) {
+                cudaEvent_t e;
+                MS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->ev_pool.push_back(e);
+            }
+            auto fail = [&](int code) {
+                cudaStreamSynchronize(ctx->h2d_stream); cudaStreamSynchronize(ctx->own_stream);
+                return code;
+            };
+            // lnL straight into the caller's buffer when the device can address it
+            double *lnl_target = lnl_d;
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, lnL_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                lnl_target = static_cast<double *>(at.devicePointer);
+            else
+                cudaGetLastError();
+            // upload plan: one wave first (the kernel starts after 1.8 MB), then equal chunks
+            std::vector<int64_t> cuts{0, wave};
+            const int64_t step = ((B - wave + kChunks - 2) / (kChunks - 1) + 255) / 256 * 256;
+            while (cuts.back() < B) cuts.push_back(cuts.back() + step < B ? cuts.back() + step : B);
+            if (flags->slot >= ctx->nslots || flags->slot >= (int)ctx->stars.size() || !ctx->stars[flags->slot].set) {
+                ms_set_error("star slot %d has no photometry loaded (ms_set_star)", flags->slot);
+                return MS_ESTATE;
+            }
+            cudaError_t e = cudaMemsetAsync(ctx->rows_ready_dev, 0, sizeof(int), ctx->h2d_stream);
+            auto upload = [&](size_t k) {
+                const int64_t b0 = cuts[k], nb = cuts[k + 1] - b0;
+                ctx->rows_ready_host[k] = (int)cuts[k + 1];
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(ctx->scr_theta + b0 * ndim, theta_host + b0 * ndim, (size_t)nb * ndim * sizeof(double),
+                                        cudaMemcpyHostToDevice, ctx->h2d_stream);
+                if (e == cudaSuccess)
+                    e = cudaMemcpyAsync(ctx->rows_ready_dev, ctx->rows_ready_host + k, sizeof(int), cudaMemcpyHostToDevice,
+                                        ctx->h2d_stream);
+            };
+            // first chunk, then the launch, then the rest of the uploads: the kernel is in flight while the host is
+            // still queueing copies
+            upload(0);
+            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pool[0], ctx->h2d_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->own_stream, ctx->ev_pool[0], 0);
+            if (e != cudaSuccess) { ms_set_error("host entry (streaming): %s", cudaGetErrorString(e)); return fail(MS_ECUDA); }
+            ThetaView tv = tv0;
+            tv.theta = ctx->scr_theta;
+            PhotArgs pa{nullptr, nullptr, nullptr, nullptr};
+            pa.lnL = lnl_target; pa.ageweight = flags->ageweight; pa.slot0 = flags->slot;
+            pa.rows_ready = ctx->rows_ready_dev;
+            rc = launch_phot_tc_fused(ctx, tv, pa, nullptr, flags->mistdif, B, ctx->own_stream);
+            // the uploads are queued even if the launch failed part-way: a launched kernel must not wait forever
+            for (size_t k = 1; k + 1 < cuts.size(); ++k) upload(k);
+            if (rc) return fail(rc);
+            if (e != cudaSuccess) { ms_set_error("host entry (streaming): %s", cudaGetErrorString(e)); return fail(MS_ECUDA); }
+            if (lnl_target == lnl_d) {
+                e = cudaMemcpyAsync(lnL_host, lnl_d, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->own_stream);
+                if (e != cudaSuccess) { ms_set_error("host entry (streaming): %s", cudaGetErrorString(e)); return fail(MS_ECUDA); }
+            }
+            MS_CUDA(cudaStreamSynchronize(ctx->own_stream));
+            MS_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+            return MS_OK;
+        }
+    }
     // Chunked three-stream pipeline: the host->device copy of chunk k+1 and the device->host
     // copy of chunk k-1 overlap the kernels of chunk k (pinned host buffers make the copies
     // truly asynchronous; pageable ones still work, serialised by the driver).

@@ -116,6 +116,8 @@ struct ms_ctx {
     cudaStream_t own_stream = nullptr;           // compute stream of the host-buffer entry point
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     std::vector<cudaEvent_t> ev_pool;            // chunk pipeline events
+    int *rows_ready_dev = nullptr;               // streaming host entry: rows of theta uploaded so far (device int)
+    int *rows_ready_host = nullptr;              // pinned staging of the values copied into it, one per upload chunk
     int64_t launches = 0;
     // live timing (ms_profile_*)
     bool prof_on = false;
@@ -183,6 +185,9 @@ struct PhotArgs {
     double *lnL = nullptr;
     int ageweight = 0;
     int slot0 = 0;                 // star slot of every row when star_slot is nullptr (ms_flags.slot)
+    // streaming host entry (fused tensor-core form only): theta rows [0, *rows_ready) have landed on the device; the
+    // kernel waits for a pair's rows before touching them.  nullptr: every row is there.
+    const int *rows_ready = nullptr;
 };
 int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
 int phot_tc_prepare(ms_ctx *ctx);          // pack weights for the tensor-core kernel

@@ -108,6 +108,7 @@ struct TcArgs {
     double *peers[MS_MAX_PEERS]; int npeers; int64_t peer_off;
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
+    const int *rows_ready;             // streaming host entry: rows of theta on the device so far (nullptr: all)
     int *sched;                        // [2]: next pair beyond the first wave, CTAs that have left (both 0 between launches)
     double xmin[8], xscale[8];
     int nb, d_in;                      // bands of this launch (a group when the net has more than MAX_NB)
@@ -195,6 +196,7 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
     ka.obs_mag = ctx->obs_mag; ka.obs_err2 = ctx->obs_err2;
     for (int i = 0; i < 8; ++i) { ka.xmin[i] = n.xmin[i]; ka.xscale[i] = n.xscale[i]; }
     ka.d_in = n.d_in; ka.nb_total = n.nb;
+    ka.rows_ready = tv ? a.rows_ready : nullptr;
     ka.sched = reinterpret_cast<int *>(static_cast<unsigned char *>(n.tc_pack) + n.tc_pack_bytes);
     ka.fused = tv != nullptr;
     int smem_extra = 0;

@@ -174,7 +174,18 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         for (int it = 0;; ++it) {
             const int xbuf = it & 1;
             if (tid == 0) STAMP(it, 0);
-            if (tid == 0) s_pair[it & 3] = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.sched, 1);
+            if (tid == 0) {
+                const int mine = it == 0 ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(a.sched, 1);
+                s_pair[it & 3] = mine;
+                if (a.rows_ready && mine < npairs) {
+                    // streaming host entry: this pair's rows of theta are still on their way over PCIe (copy engine
+                    // writes, then the counter: both through L2; the rows are first touched after this load)
+                    int64_t need = ((int64_t)mine + 1) * (2 * TILE);
+                    if (need > B) need = B;
+                    while ((int64_t)*reinterpret_cast<const volatile int *>(a.rows_ready) < need) __nanosleep(256);
+                    __threadfence();
+                }
+            }
             mbar_wait(bar(BAR_XEMPTY + xbuf), ((it >> 1) & 1) ^ 1);
             asm volatile("bar.sync 3, 128;" ::: "memory");              // the four prologue warps: index visible
             if (tid == 0) STAMP(it, 1);
