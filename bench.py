@@ -503,16 +503,16 @@ def main():
             specblk = dict(error=repr(e))
 
     # ---- other hidden widths of the photometric nets ("default H_p = 128; also report 64 and
-    # 256"): same workload, same timing loop; 64 runs on the tcgen05 kernel, 256 does not fit its TMEM / shared-memory
-    # plan and runs on the f32 CUDA-core kernel
+    # 256"): same workload, same timing loop, same fused tcgen05 kernel family (256: one tile per CTA, layer-2 weights
+    # streamed in K slices)
     hidden_variants = {}
     if args.hidden == 128 and not args.small_grid and args.precision == 'tc':
-        for hh, hprec in ((64, 'tc'), (256, 'f32')):
+        for hh, hprec in ((64, 'tc'), (256, 'tc')):
             try:
                 fa_h = dict(fitargs, photANNpath=synth.make_phot_net(h=hh, seed=1))
                 Lh = likelihood(fa_h, fitpars, runbools, precision=hprec, device=local, verbose=False)
                 outh = torch.empty(B, dtype=torch.float64, device=dev)
-                nst = 5 if hh == 64 else 2
+                nst = 5
                 for _ in range(2):
                     Lh.engine.lnlike_batch(theta, Lh._colmap, Lh._fixed, Lh._flags, want_derived=False, out=outh)
                 evh = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nst)]

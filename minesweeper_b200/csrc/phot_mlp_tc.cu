@@ -133,7 +133,7 @@ __device__ long long g_cta[148 * 8];
 
 // one instantiation of the kernel family per supported hidden width
 struct TcVariant {
-    int h, band_bytes, const_bytes, sm_fixed, max_nb;
+    int h, band_bytes, const_bytes, sm_fixed, max_nb, pair_rows;     // pair_rows: points a CTA takes at a time
     int (*pack)(ms_ctx *, std::vector<unsigned char> &);
     void (*kern)(TcArgs, int64_t, int);
     void (*kern_fast)(TcArgs, int64_t, int);
@@ -149,10 +149,16 @@ namespace h64 {
 #include "phot_mlp_tc_body.cuh"
 #undef PH_H
 }  // namespace h64
+namespace h256 {
+#define PH_H 256
+#include "phot_mlp_tc_body.cuh"
+#undef PH_H
+}  // namespace h256
 
 const TcVariant *variant_for(int h) {
     if (h == 128) return &h128::variant;
     if (h == 64) return &h64::variant;
+    if (h == 256) return &h256::variant;
     return nullptr;
 }
 
@@ -162,7 +168,7 @@ int phot_tc_prepare(ms_ctx *ctx) {
     PhotNetDev &P = ctx->phot;
     const TcVariant *V = variant_for(P.h);
     if (!V || P.d_in > 6) {
-        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 64 or 128 and <= 6 inputs "
+        ms_set_error("MS_PREC_TC supports photometric nets with hidden width 64, 128 or 256 and <= 6 inputs "
                      "(got h=%d, d_in=%d); use MS_PREC_F32", P.h, P.d_in);
         return MS_EINVAL;
     }
@@ -221,7 +227,7 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
             MS_CUDA(cudaMemsetAsync(carry, 0, (size_t)B * sizeof(double), st));
         }
     }
-    const int64_t npairs = (B + 2 * TILE - 1) / (2 * TILE);
+    const int64_t npairs = (B + V->pair_rows - 1) / V->pair_rows;
     const int grid = (int)(npairs < ctx->sm_count ? npairs : ctx->sm_count);
     KernelTimer timer_(ctx, MS_K_PHOT, st);
     for (int gi = 0; gi < ngroups; ++gi) {

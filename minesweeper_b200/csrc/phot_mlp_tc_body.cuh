@@ -1,6 +1,10 @@
 // H-dependent part of phot_mlp_tc.cu: included once per supported hidden width with PH_H defined, inside a
-// namespace of its own.  TMEM: 2 tiles x (H columns D1/A1 + H columns D2) = 4 H columns.
+// namespace of its own.  TMEM: NT tiles x (H columns D1/A1 + H columns D2): two tiles for H <= 128, ONE for H = 256
+// (512 columns), whose layer-2 weights (256 KB per band as hi + lo) do not fit shared memory either and are streamed
+// through the ring in K slices of 32 instead of as one image per band.
 constexpr int H = PH_H;              // hidden width of this instantiation
+constexpr int NT = H <= 128 ? 2 : 1; // tiles (of 128 points) a CTA works on at a time
+constexpr bool STREAM = H > 128;     // layer-2 weights arrive in K slices
 // Per-band weight image in global memory (and in each shared-memory ring slot).
 // Operand images use the K-major no-swizzle core-matrix layout: [k/8][row][k%8] fp16,
 // i.e. 8 rows x 16 B core matrices, SBO = 128 B between 8-row groups, LBO = 2048 B
@@ -15,15 +19,20 @@ constexpr int OFF_CB2 = OFF_W2L + W2_BYTES;            // float[128]: -log2e * b
 constexpr int OFF_W3 = OFF_CB2 + 4 * H;                // float[H]
 constexpr int OFF_B3 = OFF_W3 + 4 * H;                 // float[4] (b3 in [0])
 constexpr int BAND_BYTES = OFF_B3 + 128;               // 74,880 B per band in global memory (multiple of 128)
-constexpr int RING_BYTES = OFF_CB2;                    // operand images only: what a ring slot holds
+constexpr int KSL = 32;                                // STREAM: K of one slice (two k-steps)
+constexpr int NSL = H / KSL;                           //         slices per band
+constexpr int SLICE_BYTES = (KSL / 8) * H * 16;        //         one slice of W2 hi (or lo): contiguous in the image
+constexpr int RING_SLOTS = STREAM ? 3 : 2;
+constexpr int RING_BYTES = STREAM ? 2 * SLICE_BYTES : OFF_CB2;   // what a ring slot holds (operand images only)
 constexpr int CONST_BYTES = BAND_BYTES - OFF_CB2;      // cb2, w3, b3: resident in shared memory for all bands
 
-constexpr int SM_W = 0;                                // 2 ring slots
-constexpr int SM_X = SM_W + 2 * RING_BYTES;            // [2 pair buffers][2 tiles][hi, lo] X tile images
+constexpr int SM_W = 0;                                // ring slots
+constexpr int SM_W1 = SM_W + RING_SLOTS * RING_BYTES;  // STREAM: [2][W1 hi, W1 lo] of the current / next band
+constexpr int SM_X = SM_W1 + (STREAM ? 2 * 2 * W1_BYTES : 0);   // [2 pair buffers][2 tiles][hi, lo] X tile images
 constexpr int SM_PT = SM_X + 8 * X_BYTES;              // [2 pair buffers][256 points] PointState
 constexpr int SM_PART = SM_PT + 2 * 256 * 24;          // float[2 band parities][2 tiles][128]: B's partial dot products
 constexpr int SM_BAR = SM_PART + 2048;                 // mbarriers
-constexpr int SM_CONST = SM_BAR + 256;                 // [nb][CONST_BYTES] epilogue constants
+constexpr int SM_CONST = SM_BAR + 512;                 // [nb][CONST_BYTES] epilogue constants
 constexpr int SM_FIXED = SM_CONST;
 constexpr int MAX_NB = (SMEM_LIMIT - SM_FIXED) / CONST_BYTES;
 
@@ -32,8 +41,10 @@ constexpr uint32_t IDESC = make_idesc_f16(128, H);
 constexpr int NCH = H / 16;            // 16-column chunks of an accumulator = layer-2 k-steps
 constexpr int WLBO = H * 16;           // bytes between 8-element K chunks of a weight image (H rows of 16 B)
 
-enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR_A1 = 10 /* [tile][8 chunks] */,
-       BAR_XEMPTY = 26, BAR_N = 28 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = 2, BAR_XFULL = 4, BAR_D1 = 6, BAR_D2 = 8, BAR_A1 = 10 /* [tile][8 chunks] or [16 chunks] */,
+       BAR_XEMPTY = 26, BAR_SFULL = 28 /* STREAM: [3] */, BAR_SEMPTY = 31, BAR_W1FULL = 34 /* [2] */, BAR_W1EMPTY = 36,
+       BAR_N = 38 };
+static_assert(BAR_N * 8 <= 512, "mbarrier area");
 
 // FAST = MS_PREC_TC16: sigmoid(z) = 1/2 + tanh(z/2)/2 with the affine part folded into the next
 // layer's packed weights, tanh.approx.f32 (one MUFU per activation), activations handed to layer 2 as
@@ -63,17 +74,20 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar(BAR_WFULL + i), 1);
-            mbar_init(bar(BAR_WEMPTY + i), 2);
+            mbar_init(bar(BAR_WEMPTY + i), NT);
             mbar_init(bar(BAR_XFULL + i), 4);                   // [pair buffer]: the 4 prologue warps
-            mbar_init(bar(BAR_XEMPTY + i), 2 + 8);              // both issuers (last layer 1 done) + the 8 A warps
+            mbar_init(bar(BAR_XEMPTY + i), NT * (1 + 4));       // per tile: its issuer (last layer 1 done) + its 4 A warps
+            mbar_init(bar(BAR_W1FULL + i), 1);
+            mbar_init(bar(BAR_W1EMPTY + i), 1);
             mbar_init(bar(BAR_D1 + i), 1);
             mbar_init(bar(BAR_D2 + i), 1);
             for (int j = 0; j < 8; ++j) mbar_init(bar(BAR_A1 + 8 * i + j), 4);
         }
+        for (int i = 0; i < 3; ++i) { mbar_init(bar(BAR_SFULL + i), 1); mbar_init(bar(BAR_SEMPTY + i), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 16) {                                  // TMEM: all 512 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(4 * H) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(2 * NT * H) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int nb = a.nb;
@@ -93,16 +107,36 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     if (warp == 18) {
         // ===== weight producer =====
         if (lane == 0) {
-            int g = 0;
+            int g = 0, gs = 0;
             for (int it = 0;; ++it) {
                 mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
                 if (*(volatile int *)&s_pair[it & 3] >= npairs) break;
-                for (int b = 0; b < nb; ++b, ++g) {
-                    const int buf = g & 1;
-                    mbar_wait(bar(BAR_WEMPTY + buf), ((g >> 1) & 1) ^ 1);
-                    mbar_expect_tx(bar(BAR_WFULL + buf), RING_BYTES);
-                    bulk_g2s(sbase + SM_W + buf * RING_BYTES, a.wimg + (size_t)b * BAND_BYTES, RING_BYTES,
-                             bar(BAR_WFULL + buf));
+                if constexpr (!STREAM) {
+                    for (int b = 0; b < nb; ++b, ++g) {
+                        const int buf = g & 1;
+                        mbar_wait(bar(BAR_WEMPTY + buf), ((g >> 1) & 1) ^ 1);
+                        mbar_expect_tx(bar(BAR_WFULL + buf), RING_BYTES);
+                        bulk_g2s(sbase + SM_W + buf * RING_BYTES, a.wimg + (size_t)b * BAND_BYTES, RING_BYTES,
+                                 bar(BAR_WFULL + buf));
+                    }
+                } else {
+                    // per band: the layer-1 image (hi + lo, contiguous) into its own double buffer, then the NSL K slices
+                    // of the layer-2 image (hi and lo halves are NSL * SLICE_BYTES apart) through the ring
+                    for (int b = 0; b < nb; ++b, ++g) {
+                        const unsigned char *img = a.wimg + (size_t)b * BAND_BYTES;
+                        const int b1 = g & 1;
+                        mbar_wait(bar(BAR_W1EMPTY + b1), ((g >> 1) & 1) ^ 1);
+                        mbar_expect_tx(bar(BAR_W1FULL + b1), 2 * W1_BYTES);
+                        bulk_g2s(sbase + SM_W1 + b1 * 2 * W1_BYTES, img + OFF_W1H, 2 * W1_BYTES, bar(BAR_W1FULL + b1));
+                        for (int sl = 0; sl < NSL; ++sl, ++gs) {
+                            const int slot = gs % RING_SLOTS;
+                            mbar_wait(bar(BAR_SEMPTY + slot), ((gs / RING_SLOTS) & 1) ^ 1);
+                            mbar_expect_tx(bar(BAR_SFULL + slot), 2 * SLICE_BYTES);
+                            const uint32_t dst = sbase + SM_W + slot * RING_BYTES;
+                            bulk_g2s(dst, img + OFF_W2H + (size_t)sl * SLICE_BYTES, SLICE_BYTES, bar(BAR_SFULL + slot));
+                            bulk_g2s(dst + SLICE_BYTES, img + OFF_W2L + (size_t)sl * SLICE_BYTES, SLICE_BYTES, bar(BAR_SFULL + slot));
+                        }
+                    }
                 }
             }
         }
@@ -113,7 +147,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         // built once; a k-step advances the start-address field.
         // The whole warp runs the loop converged and one elected lane issues: every operand is
         // warp-uniform, so the descriptors live in uniform registers and an MMA is a single instruction.
-        {
+        if constexpr (!STREAM) {
             const int T = __shfl_sync(0xffffffffu, warp, 0) - 16;
             const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
             const uint32_t xb = sbase + SM_X + T * 2 * X_BYTES;          // pair buffer 1 is 4 * X_BYTES further
@@ -165,6 +199,59 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                     }
                 }
             }
+        } else if (warp == 16) {
+            // one tile: layer 1 from the band's own W1 buffer, layer 2 k-step by k-step as the A1 chunks land and the
+            // K slices of W2 arrive (a slice = two k-steps; its ring slot is released by the commit behind the second)
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint32_t xb = sbase + SM_X;
+            const uint64_t xh0 = make_desc(xb, 2048, 128), xl0 = make_desc(xb + X_BYTES, 2048, 128);
+            const uint32_t d1 = tm, d2 = tm + H;
+            int g = 0, gs = 0;
+            for (int it = 0;; ++it) {
+                mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
+                if (*(volatile int *)&s_pair[it & 3] >= npairs) break;
+                const uint64_t xh = xh0 + (uint64_t)((it & 1) * (4 * X_BYTES / 16));
+                const uint64_t xl = xl0 + (uint64_t)((it & 1) * (4 * X_BYTES / 16));
+                for (int b = 0; b < nb; ++b, ++g) {
+                    const int b1 = g & 1;
+                    mbar_wait(bar(BAR_W1FULL + b1), (g >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t w1b = sbase + SM_W1 + b1 * 2 * W1_BYTES;
+                    const uint64_t bh1 = make_desc(w1b, WLBO, 128), bl1 = make_desc(w1b + W1_BYTES, WLBO, 128);
+                    if (elect_one()) {
+                        mma_ss(d1, xh, bh1, 0, IDESC);
+                        mma_ss(d1, xl, bh1, 1, IDESC);
+                        mma_ss(d1, xh, bl1, 1, IDESC);
+                        tc_commit(bar(BAR_D1));
+                        tc_commit(bar(BAR_W1EMPTY + b1));
+                        if (b == nb - 1) tc_commit(bar(BAR_XEMPTY + (it & 1)));  // last read of this tile's X image
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int sl = 0; sl < NSL; ++sl, ++gs) {
+                        const int slot = gs % RING_SLOTS;
+                        mbar_wait(bar(BAR_SFULL + slot), (gs / RING_SLOTS) & 1);
+                        const uint32_t wb = sbase + SM_W + slot * RING_BYTES;
+                        const uint64_t bh0 = make_desc(wb, WLBO, 128), bl0 = make_desc(wb + SLICE_BYTES, WLBO, 128);
+#pragma unroll
+                        for (int h = 0; h < KSL / 16; ++h) {
+                            const int c = sl * (KSL / 16) + h;                   // k-step = A1 chunk
+                            mbar_wait(bar(BAR_A1 + c), g & 1);
+                            tc_fence_after();
+                            const uint64_t bh = bh0 + (uint64_t)(h * 2 * H), bl = bl0 + (uint64_t)(h * 2 * H);
+                            const uint32_t ah = d1 + 16 * c;
+                            if (elect_one()) {
+                                mma_ts(d2, ah, bh, c > 0, IDESC);
+                                if constexpr (!FAST) mma_ts(d2, ah + 8, bh, 1, IDESC);
+                                mma_ts(d2, ah, bl, 1, IDESC);
+                                if (h == KSL / 16 - 1) tc_commit(bar(BAR_SEMPTY + slot));
+                                if (c == NCH - 1) tc_commit(bar(BAR_D2));
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
         }
     } else if (warp >= 19) {
         // ===== prologue warpgroup: network inputs and distance modulus of the next pair's 256 points =====
@@ -180,7 +267,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 if (a.rows_ready && mine < npairs) {
                     // streaming host entry: this pair's rows of theta are still on their way over PCIe (copy engine
                     // writes, then the counter: both through L2; the rows are first touched after this load)
-                    int64_t need = ((int64_t)mine + 1) * (2 * TILE);
+                    int64_t need = ((int64_t)mine + 1) * (NT * TILE);
                     if (need > B) need = B;
                     while ((int64_t)*reinterpret_cast<const volatile int *>(a.rows_ready) < need) __nanosleep(256);
                     __threadfence();
@@ -195,8 +282,8 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 break;
             }
 #pragma unroll 1
-            for (int T = 0; T < 2; ++T) {
-                const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + tid;
+            for (int T = 0; T < NT; ++T) {
+                const int64_t p = (int64_t)pr * (NT * TILE) + T * TILE + tid;
                 PointState ps{0.0, 1.0, 0, 0};
                 float xs[8];
 #pragma unroll
@@ -297,12 +384,12 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
         int g = 0;
         // skew: tile 1 starts when tile 0 has finished its first layer-1 epilogue, so that one tile's waits for
         // the tensor pipe fall into the other tile's activation phases instead of coinciding with its own
-        if (T == 1) mbar_wait(bar(BAR_A1 + NCH - 1), 0);
-        for (int it = 0;; ++it) {
+        if (NT == 2 && T == 1) mbar_wait(bar(BAR_A1 + NCH - 1), 0);
+        for (int it = 0; T < NT; ++it) {               // one-tile form (NT = 1): the warpgroups of tile 1 have nothing to do
             mbar_wait(bar(BAR_XFULL + (it & 1)), (it >> 1) & 1);
             const int pr = *(volatile int *)&s_pair[it & 3];
             if (pr >= npairs) break;
-            const int64_t p = (int64_t)pr * (2 * TILE) + T * TILE + r;
+            const int64_t p = (int64_t)pr * (NT * TILE) + T * TILE + r;
             const bool live = half == 0 && p < B;
             bool ok = false;
             double mag0 = 0.0, agewgt = 1.0;
@@ -442,7 +529,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
     }
 #endif
     if (warp == 16) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(4 * H) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * NT * H) : "memory");
     }
 }
 
@@ -511,5 +598,5 @@ int pack_images(ms_ctx *ctx, std::vector<unsigned char> &img) {
     return MS_OK;
 }
 
-const TcVariant variant = {H, BAND_BYTES, CONST_BYTES, SM_FIXED, MAX_NB, pack_images,
+const TcVariant variant = {H, BAND_BYTES, CONST_BYTES, SM_FIXED, MAX_NB, NT * TILE, pack_images,
                            phot_mlp_tc_kernel<false>, phot_mlp_tc_kernel<true>};

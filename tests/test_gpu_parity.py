@@ -891,33 +891,35 @@ def test_lnlike_with_lsf_array_inst_r_vs_per_point_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('h', [64, 256])
 @pytest.mark.parametrize('n', [1, 257, 148 * 256 * 2 + 77])
-def test_phot_tc_hidden_width_64_vs_oracle(n):
-    """SURVEY.md section 8d asks for hidden widths 64 / 128 / 256: the tcgen05 kernel is instantiated for 64 and
-    128 (csrc/phot_mlp_tc_body.cuh); 256 does not fit its TMEM / shared-memory plan and is refused loudly (it runs
-    on the f32 CUDA-core kernel)."""
+def test_phot_tc_hidden_widths_vs_oracle(n, h):
+    """SURVEY.md section 8d asks for hidden widths 64 / 128 / 256: the tcgen05 kernel is instantiated for all three
+    (csrc/phot_mlp_tc_body.cuh; 256 as one tile per CTA with the layer-2 weights streamed in K slices).  Other widths
+    are refused loudly in tc mode (they run on the f32 CUDA-core kernel)."""
     from minesweeper_b200 import synth
     from minesweeper_b200._lib import MSError
     from oracle.payne_port import FastPayneSEDPredict
-    net = synth.make_phot_net(h=64, seed=41)
+    net = synth.make_phot_net(h=h, seed=41)
     pp = _rand_photpars(n, 50 + n % 7)
     ref = FastPayneSEDPredict(nnpath=net).sed_batch(pp)
     for prec, tol in (('tc', 1e-5), ('tc16', TC16_MAG_TOL)):
         eng = _engine(photnet=net, precision=prec)
         mags = eng.phot_sed(pp).cpu().numpy()
         np.testing.assert_allclose(mags, ref, rtol=tol, atol=tol)
-    with pytest.raises(MSError, match='64 or 128'):
-        _engine(photnet=synth.make_phot_net(h=256, seed=42), precision='tc')
+    with pytest.raises(MSError, match='64, 128 or 256'):
+        _engine(photnet=synth.make_phot_net(h=96, seed=42), precision='tc')
 
 
 @pytest.mark.gpu
-def test_fused_lnlike_hidden_width_64_vs_oracle():
-    """The one-kernel form (interpolation + 64-wide tcgen05 MLP + chi-square) against the dense oracle."""
+@pytest.mark.parametrize('h', [64, 256])
+def test_fused_lnlike_hidden_widths_vs_oracle(h):
+    """The one-kernel form (interpolation + 64- / 256-wide tcgen05 MLP + chi-square) against the dense oracle."""
     from minesweeper_b200 import synth
     from minesweeper_b200.likelihood import likelihood
     from oracle.like_port import lnlike_phot_dense
     mist = synth.make_mist(ne=60, nm=24, nf=7, na=5, seed=10)
-    phot = synth.make_phot_net(h=64, seed=43)
+    phot = synth.make_phot_net(h=h, seed=43)
     names = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R', 'log(R)', 'Dist', 'Av',
              'log(A)', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass']
     on = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
