@@ -650,7 +650,7 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
         const int64_t wave = (int64_t)ctx->sm_count * 256;
         if (iso && flags->phot && !flags->spec && !derived_host && ctx->fuse_interp && ctx->precision >= MS_PREC_TC &&
             B >= 4 * wave && B < (int64_t)1 << 31 && phot_tc_can_fuse(ctx) && !ctx->npeers) {
-            const int kChunks = 8;
+            const int kChunks = 4;
             if (!ctx->rows_ready_dev) {
                 MS_CUDA(cudaMalloc((void **)&ctx->rows_ready_dev, sizeof(int)));
                 MS_CUDA(cudaHostAlloc((void **)&ctx->rows_ready_host, (kChunks + 2) * sizeof(int), cudaHostAllocDefault));
@@ -671,14 +671,29 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
                 lnl_target = static_cast<double *>(at.devicePointer);
             else
                 cudaGetLastError();
-            // upload plan: one wave first (the kernel starts after 1.8 MB), then equal chunks
-            std::vector<int64_t> cuts{0, wave};
-            const int64_t step = ((B - wave + kChunks - 2) / (kChunks - 1) + 255) / 256 * 256;
-            while (cuts.back() < B) cuts.push_back(cuts.back() + step < B ? cuts.back() + step : B);
             if (flags->slot >= ctx->nslots || flags->slot >= (int)ctx->stars.size() || !ctx->stars[flags->slot].set) {
                 ms_set_error("star slot %d has no photometry loaded (ms_set_star)", flags->slot);
                 return MS_ESTATE;
             }
+            // In-place form: theta is pinned, device-mapped host memory too -> the kernel reads it where it is (its
+            // prologue stages a tile's rows through shared memory with coalesced loads, so every byte crosses PCIe once)
+            // and writes lnL where it belongs.  No copies, no counter, one launch.
+            if (lnl_target != lnl_d && (reinterpret_cast<uintptr_t>(theta_host) & 15) == 0 && phot_tc_can_stage(ctx, ndim) &&
+                cudaPointerGetAttributes(&at, theta_host) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+                ThetaView tv = tv0;
+                tv.theta = static_cast<const double *>(at.devicePointer);
+                PhotArgs pa{nullptr, nullptr, nullptr, nullptr};
+                pa.lnL = lnl_target; pa.ageweight = flags->ageweight; pa.slot0 = flags->slot;
+                pa.stage_theta = true;
+                if ((rc = launch_phot_tc_fused(ctx, tv, pa, nullptr, flags->mistdif, B, ctx->own_stream))) return fail(rc);
+                MS_CUDA(cudaStreamSynchronize(ctx->own_stream));
+                return MS_OK;
+            }
+            cudaGetLastError();
+            // upload plan: one wave first (the kernel starts after 1.8 MB), then equal chunks
+            std::vector<int64_t> cuts{0, wave};
+            const int64_t step = ((B - wave + kChunks - 2) / (kChunks - 1) + 255) / 256 * 256;
+            while (cuts.back() < B) cuts.push_back(cuts.back() + step < B ? cuts.back() + step : B);
             cudaError_t e = cudaMemsetAsync(ctx->rows_ready_dev, 0, sizeof(int), ctx->h2d_stream);
             auto upload = [&](size_t k) {
                 const int64_t b0 = cuts[k], nb = cuts[k + 1] - b0;
@@ -690,10 +705,13 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
                     e = cudaMemcpyAsync(ctx->rows_ready_dev, ctx->rows_ready_host + k, sizeof(int), cudaMemcpyHostToDevice,
                                         ctx->h2d_stream);
             };
-            // first chunk, then the launch, then the rest of the uploads: the kernel is in flight while the host is
-            // still queueing copies
-            upload(0);
-            if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_pool[0], ctx->h2d_stream);
+            // EVERY upload is queued before the launch: a tool that makes launches synchronous (ncu, compute-sanitizer,
+            // CUDA_LAUNCH_BLOCKING) would otherwise leave the kernel waiting for copies the host has not queued yet.
+            // Few chunks, so that queueing them delays the launch by tens of microseconds only.
+            for (size_t k = 0; k + 1 < cuts.size(); ++k) {
+                upload(k);
+                if (k == 0 && e == cudaSuccess) e = cudaEventRecord(ctx->ev_pool[0], ctx->h2d_stream);
+            }
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->own_stream, ctx->ev_pool[0], 0);
             if (e != cudaSuccess) { ms_set_error("host entry (streaming): %s", cudaGetErrorString(e)); return fail(MS_ECUDA); }
             ThetaView tv = tv0;
@@ -701,11 +719,7 @@ extern "C" int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const do
             PhotArgs pa{nullptr, nullptr, nullptr, nullptr};
             pa.lnL = lnl_target; pa.ageweight = flags->ageweight; pa.slot0 = flags->slot;
             pa.rows_ready = ctx->rows_ready_dev;
-            rc = launch_phot_tc_fused(ctx, tv, pa, nullptr, flags->mistdif, B, ctx->own_stream);
-            // the uploads are queued even if the launch failed part-way: a launched kernel must not wait forever
-            for (size_t k = 1; k + 1 < cuts.size(); ++k) upload(k);
-            if (rc) return fail(rc);
-            if (e != cudaSuccess) { ms_set_error("host entry (streaming): %s", cudaGetErrorString(e)); return fail(MS_ECUDA); }
+            if ((rc = launch_phot_tc_fused(ctx, tv, pa, nullptr, flags->mistdif, B, ctx->own_stream))) return fail(rc);
             if (lnl_target == lnl_d) {
                 e = cudaMemcpyAsync(lnL_host, lnl_d, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->own_stream);
                 if (e != cudaSuccess) { ms_set_error("host entry (streaming): %s", cudaGetErrorString(e)); return fail(MS_ECUDA); }

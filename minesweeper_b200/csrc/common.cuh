@@ -188,12 +188,16 @@ struct PhotArgs {
     // streaming host entry (fused tensor-core form only): theta rows [0, *rows_ready) have landed on the device; the
     // kernel waits for a pair's rows before touching them.  nullptr: every row is there.
     const int *rows_ready = nullptr;
+    // fused form: fetch each tile's rows of theta through shared memory with coalesced loads (theta in pinned HOST
+    // memory, read in place by the host entry); device-resident theta is read directly
+    bool stage_theta = false;
 };
 int launch_phot(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
 int phot_tc_prepare(ms_ctx *ctx);          // pack weights for the tensor-core kernel
 int launch_phot_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st);
 // fused kernels (1) + (2): the prologue warpgroup of the tensor-core kernel interpolates the grid itself
 bool phot_tc_can_fuse(const ms_ctx *ctx);
+bool phot_tc_can_stage(const ms_ctx *ctx, int ld);
 int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, double *derived, int mistdif,
                          int64_t B, cudaStream_t st);
 

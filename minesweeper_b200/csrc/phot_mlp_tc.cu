@@ -108,6 +108,7 @@ struct TcArgs {
     double *peers[MS_MAX_PEERS]; int npeers; int64_t peer_off;
     const double *obs_mag, *obs_err2;
     const unsigned char *wimg;         // [nb][BAND_BYTES]
+    int stage;                         // fused form: rows of theta staged through shared memory (ld <= 8, 16-byte aligned)
     const int *rows_ready;             // streaming host entry: rows of theta on the device so far (nullptr: all)
     int *sched;                        // [2]: next pair beyond the first wave, CTAs that have left (both 0 between launches)
     double xmin[8], xscale[8];
@@ -186,6 +187,8 @@ int phot_tc_prepare(ms_ctx *ctx) {
 
 namespace {
 
+inline int ngroups_of(int nb, int max_nb) { return (nb + max_nb - 1) / max_nb; }
+
 int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const ThetaView *tv, double *derived,
               int mistdif) {
     const PhotNetDev &n = ctx->phot;
@@ -211,7 +214,13 @@ int launch_tc(ms_ctx *ctx, const PhotArgs &a, int64_t B, cudaStream_t st, const 
         ka.tv = *tv; ka.axes = g.axes; ka.table = g.tab32;
         ka.ne = g.ne; ka.nm = g.nm; ka.nf = g.nf; ka.na = g.na; ka.mistdif = mistdif; ka.derived = derived;
         smem_extra = (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double);
+        // staging buffer for a tile's rows of theta, when it fits next to everything else
+        const int stage_bytes = 16 + TILE * 8 * (int)sizeof(double);
+        ka.stage = a.stage_theta && tv->ld <= 8 && (reinterpret_cast<uintptr_t>(tv->theta) & 15) == 0 &&
+                   SM_FIXED + n.nb * CONST_BYTES + smem_extra + stage_bytes <= SMEM_LIMIT && ngroups_of(n.nb, MAX_NB) == 1;
+        if (ka.stage) smem_extra += stage_bytes;
     } else {
+        ka.stage = 0;
         ka.axes = nullptr; ka.table = nullptr; ka.ne = ka.nm = ka.nf = ka.na = 0; ka.mistdif = 0; ka.derived = nullptr;
     }
     // A net with more bands than the resident constants allow runs as consecutive band groups: every group but
@@ -259,6 +268,16 @@ bool phot_tc_can_fuse(const ms_ctx *ctx) {
     if (!ctx->phot.tc_pack || !g.tab32 || !g.axes || !V) return false;
     return ctx->phot.nb <= V->max_nb &&
            V->sm_fixed + ctx->phot.nb * V->const_bytes + (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double) <= SMEM_LIMIT;
+}
+
+// whether the fused form would stage theta through shared memory for rows of `ld` doubles (the host entry reads pinned
+// host memory in place only then)
+bool phot_tc_can_stage(const ms_ctx *ctx, int ld) {
+    const GridDev &g = ctx->grid;
+    const TcVariant *V = variant_for(ctx->phot.h);
+    if (!phot_tc_can_fuse(ctx) || ld > 8) return false;
+    return V->sm_fixed + ctx->phot.nb * V->const_bytes + (g.ne + g.nm + g.nf + g.na) * (int)sizeof(double) + 16 +
+           TILE * 8 * (int)sizeof(double) <= SMEM_LIMIT;
 }
 
 int launch_phot_tc_fused(ms_ctx *ctx, const ThetaView &tv, const PhotArgs &a, double *derived, int mistdif,

@@ -97,6 +97,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             reinterpret_cast<const uint4 *>(a.wimg + (size_t)b * BAND_BYTES + OFF_CB2)[o];
     }
     double *s_axes = reinterpret_cast<double *>(smem + SM_CONST + nb * CONST_BYTES);     // grid axes (fused form)
+    double *s_stage = s_axes + ((a.ne + a.nm + a.nf + a.na + 1) & ~1);                   // [128][ld <= 8] rows of theta
     if (a.fused)
         for (int i = threadIdx.x; i < a.ne + a.nm + a.nf + a.na; i += NTHREADS) s_axes[i] = a.axes[i];
     tc_fence_before();
@@ -283,7 +284,26 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
             }
 #pragma unroll 1
             for (int T = 0; T < NT; ++T) {
-                const int64_t p = (int64_t)pr * (NT * TILE) + T * TILE + tid;
+                const int64_t r0 = (int64_t)pr * (NT * TILE) + T * TILE, p = r0 + tid;
+                if (a.stage) {
+                    // the tile's rows of theta through shared memory, fetched with coalesced 16-byte loads: theta may
+                    // be pinned HOST memory (ms_lnlike_batch_host reads it in place: no upload, every byte crosses PCIe
+                    // once), where the per-thread 8-byte loads of theta_get would fetch every line six times
+                    asm volatile("bar.sync 3, 128;" ::: "memory");      // the previous tile's rows are no longer read
+                    int64_t nrow = B - r0;
+                    nrow = nrow > TILE ? TILE : (nrow < 0 ? 0 : nrow);
+                    const int nd8 = (int)nrow * a.tv.ld;
+                    const double *src = a.tv.theta + r0 * a.tv.ld;
+                    for (int i = tid; i < (nd8 >> 1); i += 128)
+                        reinterpret_cast<double2 *>(s_stage)[i] = reinterpret_cast<const double2 *>(src)[i];
+                    if ((nd8 & 1) && tid == 0) s_stage[nd8 - 1] = src[nd8 - 1];
+                    asm volatile("bar.sync 3, 128;" ::: "memory");
+                }
+                auto tget = [&](int pid) {
+                    const int c = a.tv.col[pid];
+                    if (c < 0) return a.tv.fixed[pid];
+                    return a.stage ? s_stage[tid * a.tv.ld + c] : a.tv.theta[p * (int64_t)a.tv.ld + c];
+                };
                 PointState ps{0.0, 1.0, 0, 0};
                 float xs[8];
 #pragma unroll
@@ -296,10 +316,10 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         const double *g[4] = {s_axes, s_axes + a.ne, s_axes + a.ne + a.nm, s_axes + a.ne + a.nm + a.nf};
                         const int n[4] = {a.ne, a.nm, a.nf, a.na};
                         double x[4];
-                        x[0] = theta_get(a.tv, p, MS_P_EEP);
-                        x[1] = theta_get(a.tv, p, MS_P_INIT_MASS);
-                        x[2] = theta_get(a.tv, p, MS_P_INIT_FEH);
-                        x[3] = theta_get(a.tv, p, MS_P_INIT_AFE);
+                        x[0] = tget(MS_P_EEP);
+                        x[1] = tget(MS_P_INIT_MASS);
+                        x[2] = tget(MS_P_INIT_FEH);
+                        x[3] = tget(MS_P_INIT_AFE);
                         int idx[4];
                         float acc[MS_NCOL], wsum;
                         double accd[2], wsumd;
@@ -320,8 +340,8 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         afe = okp ? (a.mistdif ? (double)(acc[6] * inv) : x[3]) : inf;
                         logr = okp ? accd[0] * invd : inf;
                         ps.agewgt = okp ? (double)(acc[8] * inv) : inf;
-                        dist = theta_get(a.tv, p, MS_P_DIST);
-                        av = theta_get(a.tv, p, MS_P_AV);
+                        dist = tget(MS_P_DIST);
+                        av = tget(MS_P_AV);
                         if (a.derived) {
                             double *o = a.derived + p * MS_NDERIVED;
                             o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
