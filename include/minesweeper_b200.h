@@ -172,8 +172,11 @@ int ms_lnlike_batch(ms_ctx *ctx, const ms_flags *flags, const double *theta,
                     const double *fixed, double *lnL, double *derived, int32_t *brackets,
                     void *stream);
 
-/* Same with HOST buffers: copies theta in, runs, copies lnL (and derived when
- * non-NULL) out, synchronises. */
+/* Same with HOST buffers; returns with the results in place (synchronises).  Photometry-only isochrone batches in the
+ * tensor-core modes run as ONE launch of the fused kernel: when theta_host and lnL_host are pinned, device-mapped memory
+ * (cudaHostAlloc / cudaHostRegister; 16-byte aligned, ndim <= 8) the kernel reads theta and writes lnL in place over PCIe,
+ * otherwise theta is uploaded in chunks behind a device counter the kernel waits on and lnL is copied back.  Every other
+ * mode copies theta in, runs and copies lnL (and derived when non-NULL) out in a chunked three-stream pipeline. */
 int ms_lnlike_batch_host(ms_ctx *ctx, const ms_flags *flags, const double *theta_host,
                          int64_t B, int ndim, const int32_t *colmap, const double *fixed,
                          double *lnL_host, double *derived_host);
