@@ -479,6 +479,38 @@ def test_fused_interp_phot_matches_two_kernel_sequence(prec, n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('n', [148 * 256 * 4 + 77, 148 * 256 * 7, 5000])
+def test_host_entry_forms_agree_with_device_entry(n):
+    """ms_lnlike_batch_host in tc mode: (a) pinned buffers -> the fused kernel reads theta and writes lnL in place,
+    (b) ordinary NumPy arrays -> theta uploaded in chunks behind the device counter the kernel waits on, (c) a batch
+    below the fusion threshold -> the chunked copy / kernel / copy pipeline.  Each against the device entry on the same
+    rows (same kernel family: equal to the fp32-class bound; (a) and (b) run the same one-kernel form as the device entry
+    and are compared bit for bit), repeated calls included (the pair counter re-arms itself)."""
+    import torch
+    from minesweeper_b200.likelihood import likelihood
+    fitargs, fitpars, rb, th0 = _phot_fit(h=128)
+    th = np.tile(th0, (n // len(th0) + 1, 1))[:n].copy()
+    th[:, 0] *= np.linspace(0.9, 1.1, n)                                   # distinct rows
+    L = likelihood(fitargs, fitpars, rb, precision='tc', verbose=False)
+    dev = L.lnlike_batch(th, want_derived=False)[0].cpu().numpy()
+    fused = n >= 148 * 256 * 4
+    for rep in range(2):
+        lnl_b = L.lnlike_batch_host(th)[0]                                 # (b) / (c): pageable memory
+        th_pin = torch.from_numpy(th).pin_memory()
+        out_pin = torch.full((n,), 7.0, dtype=torch.float64).pin_memory()
+        L.lnlike_batch_host(th_pin.numpy(), lnl_out=out_pin.numpy())       # (a)
+        lnl_a = out_pin.numpy().copy()
+        for got in (lnl_a, lnl_b):
+            assert np.array_equal(np.isneginf(got), np.isneginf(dev)) and not np.any(got == 7.0)
+            fin = np.isfinite(dev)
+            if fused:
+                np.testing.assert_array_equal(got[fin], dev[fin])
+            else:
+                np.testing.assert_allclose(got[fin], dev[fin], rtol=1e-12, atol=1e-9)
+    assert np.isneginf(dev).sum() > 0
+
+
+@pytest.mark.gpu
 def test_fused_interp_phot_with_star_slots():
     """Catalog form of the fused kernel: every row carries its own star slot (its own observed magnitudes).
     One-kernel and two-kernel forms agree, and a row evaluated against slot s equals the single-star result
