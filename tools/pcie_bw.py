@@ -1,3 +1,4 @@
+"""Pinned host <-> device copy bandwidth of the box (the e2e figure of bench.py is judged against it)."""
 import torch, time
 x = torch.empty(50331648 // 8, dtype=torch.float64).pin_memory()
 d = torch.empty_like(x, device='cuda')
