@@ -435,7 +435,7 @@ class QueuedNestedSampler(object):
         self.max_queue = max(int(max_queue), self.Q)
         self.eng.check_star_slots(self.S, self.star_plx)
 
-    def run(self, check_every=4, verbose=False, min_compact=512, compact_frac=0.5):
+    def run(self, check_every=4, verbose=False, min_compact=512, compact_frac=0.85):
         # the rounds are captured into CUDA graphs that bake the ctx's scratch pointers in: size the scratch for the
         # largest batch of the run and pin it for its duration (another caller growing it would free it under us)
         self.eng.reserve(self.S * max(self.K, self.Q), lock=True)
@@ -444,7 +444,7 @@ class QueuedNestedSampler(object):
         finally:
             self.eng.reserve(0, lock=False)
 
-    def _run(self, check_every=4, verbose=False, min_compact=512, compact_frac=0.5):
+    def _run(self, check_every=4, verbose=False, min_compact=512, compact_frac=0.85):
         import ctypes as C
         if self.store and min_compact < self.S:
             raise ValueError('store_samples needs min_compact >= nstars (the dead-point buffer is not compacted)')

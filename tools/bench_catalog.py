@@ -172,8 +172,9 @@ def main():
     ap.add_argument('--maxiter', type=int, default=20000)
     ap.add_argument('--small-grid', action='store_true')
     ap.add_argument('--eager', action='store_true', help='use the eager sampler loop instead of the CUDA-graph one')
-    ap.add_argument('--compact-frac', type=float, default=0.5)
-    ap.add_argument('--check-every', type=int, default=64)
+    ap.add_argument('--compact-frac', type=float, default=0.85,
+                    help='shrink the working set (and re-capture the round graph) once this fraction of it is still running')
+    ap.add_argument('--check-every', type=int, default=16)
     ap.add_argument('--bruteforce', type=int, default=0, help='check this many stars against brute-force quadrature')
     ap.add_argument('--queued', type=int, default=4,
                     help='walkers per star of the kernel-bookkeeping sampler; 0 = torch-tensor sampler')
