@@ -100,6 +100,7 @@ struct ms_ctx {
     double *obs_mag = nullptr, *obs_err2 = nullptr;
     std::vector<StarDev> stars;
     StarView *stars_dev = nullptr; int stars_dev_n = 0;      // device copy of the spectrum views, refreshed by ms_set_star
+    int spec_gemm_ts = 1;          // tc modes: output layer of the spectral net with the activations resident in tensor memory
     int spec_fast = 1;             // f32-class modes: fast broadening kernel (ms_set_spec_fast); 0 = generic kernel only
     int *scr_fb = nullptr; size_t scr_fb_bytes = 0;          // fallback row list of the fast broadening kernel
     // scratch (grown on demand, stream-ordered use on one stream at a time)

@@ -25,6 +25,7 @@
 
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -89,6 +90,7 @@ struct GemmArgs {
     int P, nkc, m_tiles, n_tiles;    // P = valid output columns
     int nkc_out;
     float inv_scale, leak;
+    unsigned char *out_ts;           // PACK = true: when set, the next layer's A operand as a TMEM image (see spec_out_gemm_ts_kernel)
 };
 
 // PACK = false: out = acc * inv_scale + bias (f32 rows).  PACK = true: hidden layer: leaky ReLU, then the fp16
@@ -200,6 +202,15 @@ spec_gemm_tc_kernel(GemmArgs a) {
                             hi[i] = __float2half_rn(x);
                             lo[i] = __float2half_rn(x - __half2float(hi[i]));
                         }
+                        if (a.out_ts) {
+                            // TMEM image: [m_tile][k-step c][hi words 0-3 | hi 4-7 | lo 0-3 | lo 4-7][row][16 B]
+                            const int c = n0 / 16, t = (n0 / 8) & 1;
+                            unsigned char *dst = a.out_ts + (((size_t)mt * (a.nkc_out * (BK / 16)) + c) * 4 + t) * (BM * 16) +
+                                                 (size_t)(q * 32 + lane) * 16;
+                            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
+                            *reinterpret_cast<uint4 *>(dst + 2 * BM * 16) = *reinterpret_cast<const uint4 *>(lo);
+                            continue;
+                        }
                         unsigned char *dst = a.out_img + (((size_t)mt * a.nkc_out + kc_o) * 2) * OPER_BYTES +
                                              (size_t)((n0 % BK) / 8) * 2048 + (size_t)(q * 32 + lane) * 16;
                         *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(hi);
@@ -234,6 +245,187 @@ spec_gemm_tc_kernel(GemmArgs a) {
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
+// ---- output layer, A-stationary form -------------------------------------------------------------------------
+// The output GEMM above is bound by operand bytes into the SM (21 B/clk against the 85 a tensor-bound split-precision
+// 128 x 128 tile needs), and half of those bytes are the activations -- the same 128 x K block for every pixel tile of
+// an m-tile.  Here a CTA keeps the activations of ITS m-tile in tensor memory for the whole sweep (fp16 hi / lo pairs:
+// 16 columns per k-step, 320 columns for K <= 320) and issues the MMAs in the TS form (A from TMEM); only the weight
+// tiles stream through shared memory: 80 KB per 128 x 64 output tile instead of 160 KB, through a 12-deep ring of 16 KB
+// stages.  Two 64-column accumulators behind the activations (320 + 128 <= 512 columns) keep the epilogue of a tile under
+// the MMAs of the next.  Work item = (m-tile, every G-th pixel tile), G = CTAs per m-tile; m-fastest across CTAs so the
+// CTAs that run together read the same weight tiles through L2.
+constexpr int TBN = 64;                                   // pixel columns per tile
+constexpr int TS_OPER = (BK / 8) * TBN * 16;              // one half (hi or lo) of a weight stage: 8 KB
+constexpr int TS_STAGE = 2 * TS_OPER;                     // 16 KB
+constexpr int TS_NST = 11;
+constexpr int TS_ROWF = TBN + 4;                          // floats per staged row: 16-byte rows 17 slots apart -> no bank conflicts
+constexpr int TS_SM_STAGE_OUT = TS_NST * TS_STAGE;        // [4 epilogue warps][32 rows][TS_ROWF] f32: transposition buffer
+constexpr int TS_SM_BAR = TS_SM_STAGE_OUT + 4 * 32 * TS_ROWF * 4;
+constexpr int TS_SM_TOTAL = TS_SM_BAR + 256;
+constexpr uint32_t TS_IDESC = make_idesc_f16(BM, TBN);
+enum { TB_FULL = 0, TB_EMPTY = TS_NST, TB_ACC_FULL = 2 * TS_NST, TB_ACC_EMPTY = 2 * TS_NST + 2, TB_A_READY = 2 * TS_NST + 4 };
+
+struct TsArgs {
+    const unsigned char *a_ts;       // [m_tiles][nks][4][128 rows][16 B]
+    const unsigned char *b_img;      // [n_tiles (64 wide)][nkc][hi|lo][64 rows x 128 B, 128-byte swizzle]
+    const float *bias;
+    float *out;                      // [B][P] f32
+    int64_t B;
+    int P, nkc, m_tiles, n_tiles, G; // G: work items per m-tile
+    float inv_scale;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+spec_out_gemm_ts_kernel(TsArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint32_t s_tmem_base;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t sbase = smem_u32(smem);
+    auto bar = [&](int i) { return sbase + TS_SM_BAR + 8u * (uint32_t)i; };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TS_NST; ++i) { mbar_init(bar(TB_FULL + i), 1); mbar_init(bar(TB_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar(TB_ACC_FULL + i), 1); mbar_init(bar(TB_ACC_EMPTY + i), 4); }
+        mbar_init(bar(TB_A_READY), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&s_tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+    const int nkc = a.nkc, nks = nkc * (BK / 16);
+    const uint32_t dcol = (uint32_t)(16 * nks);              // accumulators start behind the activations
+    const int nitems = a.m_tiles * a.G;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int g = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                for (int nt = item / a.m_tiles; nt < a.n_tiles; nt += a.G) {
+                    for (int kc = 0; kc < nkc; ++kc, ++g) {
+                        const int st = g % TS_NST;
+                        mbar_wait(bar(TB_EMPTY + st), ((g / TS_NST) & 1) ^ 1);
+                        mbar_expect_tx(bar(TB_FULL + st), TS_STAGE);
+                        bulk_g2s(sbase + st * TS_STAGE, a.b_img + ((size_t)nt * nkc + kc) * TS_STAGE, TS_STAGE, bar(TB_FULL + st));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int g = 0, it = 0, ni = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++ni) {
+            mbar_wait(bar(TB_A_READY), ni & 1);                  // this m-tile's activations are in tensor memory
+            tc_fence_after();
+            for (int nt = item / a.m_tiles; nt < a.n_tiles; nt += a.G, ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar(TB_ACC_EMPTY + buf), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem + dcol + buf * TBN;
+                for (int kc = 0; kc < nkc; ++kc, ++g) {
+                    const int st = g % TS_NST;
+                    mbar_wait(bar(TB_FULL + st), (g / TS_NST) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = sbase + st * TS_STAGE;
+                    const uint64_t bh0 = make_desc_sw128(sa), bl0 = make_desc_sw128(sa + TS_OPER);
+                    const uint32_t a0 = tmem + 16 * (kc * (BK / 16));
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            const uint64_t o = (uint64_t)(ks * 2);                        // 32 B further along the 128-byte row
+                            const uint32_t ah = a0 + 16 * ks;
+                            mma_ts(d, ah, bh0 + o, (kc | ks) != 0, TS_IDESC);
+                            mma_ts(d, ah + 8, bh0 + o, 1, TS_IDESC);
+                            mma_ts(d, ah, bl0 + o, 1, TS_IDESC);
+                        }
+                        tc_commit(bar(TB_EMPTY + st));
+                        if (kc == nkc - 1) tc_commit(bar(TB_ACC_FULL + buf));
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        int it = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int mt = item % a.m_tiles;
+            // activations of the m-tile -> tensor memory (every MMA of the previous item has retired: its last
+            // accumulator was drained below)
+            {
+                const unsigned char *src = a.a_ts + ((size_t)mt * nks * 4) * (BM * 16) + (size_t)(q * 32 + lane) * 16;
+                for (int c = 0; c < nks; ++c) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(src + ((size_t)c * 4 + t) * (BM * 16)));
+                        v[4 * t] = w.x; v[4 * t + 1] = w.y; v[4 * t + 2] = w.z; v[4 * t + 3] = w.w;
+                    }
+                    TMEM_ST16(tmem + lane_base + 16 * c, v);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(TB_A_READY));
+            }
+            const int64_t row = (int64_t)mt * BM + q * 32 + lane;
+            for (int nt = item / a.m_tiles; nt < a.n_tiles; nt += a.G, ++it) {
+                const int buf = it & 1;
+                mbar_wait(bar(TB_ACC_FULL + buf), (it >> 1) & 1);
+                tc_fence_after();
+                // A thread owns a ROW of the accumulator; storing it directly would put 32 rows, 40 KB apart, into every
+                // store instruction (half-filled sectors: 23 of the 55 us of this kernel).  The warp's 32 x 64 block goes
+                // through shared memory instead and leaves as whole 256-byte row segments, two rows per instruction.
+                float *stg = reinterpret_cast<float *>(smem + TS_SM_STAGE_OUT) + (size_t)q * 32 * TS_ROWF;
+#pragma unroll 1
+                for (int j = 0; j < TBN / 32; ++j) {
+                    uint32_t v[32];
+                    TMEM_LD32(tmem + lane_base + dcol + buf * TBN + 32 * j, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<uint4 *>(stg + lane * TS_ROWF + 32 * j + 4 * i) = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(TB_ACC_EMPTY + buf));      // the accumulator is free: the MMAs of tile it + 2 may start
+                {
+                    const int col0 = nt * TBN, hl = lane & 15, rsel = lane >> 4;
+                    const int64_t row0 = (int64_t)mt * BM + q * 32;
+                    if (col0 + TBN <= a.P) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.bias + col0) + hl);
+#pragma unroll 4
+                        for (int rr = 0; rr < 32; rr += 2) {
+                            const int r = rr + rsel;
+                            const float4 x = *reinterpret_cast<const float4 *>(stg + r * TS_ROWF + 4 * hl);
+                            float4 r4;
+                            r4.x = fmaf(x.x, a.inv_scale, bb.x); r4.y = fmaf(x.y, a.inv_scale, bb.y);
+                            r4.z = fmaf(x.z, a.inv_scale, bb.z); r4.w = fmaf(x.w, a.inv_scale, bb.w);
+                            if (row0 + r < a.B) *reinterpret_cast<float4 *>(a.out + (row0 + r) * a.P + col0 + 4 * hl) = r4;
+                        }
+                    } else {
+                        for (int rr = 0; rr < 32; rr += 2) {
+                            const int r = rr + rsel;
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = col0 + 4 * hl + i;
+                                if (c < a.P && row0 + r < a.B)
+                                    a.out[(row0 + r) * a.P + c] = fmaf(stg[r * TS_ROWF + 4 * hl + i], a.inv_scale, a.bias[c]);
+                            }
+                        }
+                    }
+                    __syncwarp();                                       // the buffer is reused by the next tile
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 }  // namespace
 
 struct TcLayer {                      // packed weights of one GEMM layer
@@ -243,12 +435,14 @@ struct TcLayer {                      // packed weights of one GEMM layer
 };
 struct SpecTcPack {
     TcLayer l1, l2;
+    TcLayer l2ts;                                            // output layer in 64-wide tiles (A-stationary kernel); empty if K is too long
+    unsigned char *a2_ts = nullptr;                          // its A operand as a TMEM image
     unsigned char *a1_img = nullptr, *a2_img = nullptr;     // operand images of layer 1 and of the output layer
     size_t a_img_rows = 0;                                   // rows (multiple of BM) both images hold
 };
 
 // W[N][K] f32 (device) -> B image [n_tile][k_chunk][hi|lo][k8][row][8], scaled by a power of two
-static int pack_weights(const float *w_dev, int N, int K, TcLayer *L) {
+static int pack_weights(const float *w_dev, int N, int K, TcLayer *L, int bn = BN, bool sw128 = false) {
     std::vector<float> w((size_t)N * K);
     MS_CUDA(cudaMemcpy(w.data(), w_dev, w.size() * 4, cudaMemcpyDeviceToHost));
     float wmax = 0.f;
@@ -259,19 +453,23 @@ static int pack_weights(const float *w_dev, int N, int K, TcLayer *L) {
     const double scale = std::ldexp(1.0, shift);
     L->N = N;
     L->nkc = (K + BK - 1) / BK;
-    L->n_tiles = (N + BN - 1) / BN;
+    L->n_tiles = (N + bn - 1) / bn;
     L->inv_scale = (float)std::ldexp(1.0, -shift);
-    const size_t bytes = (size_t)L->n_tiles * L->nkc * 2 * OPER_BYTES;
+    const size_t oper = (size_t)(BK / 8) * bn * 16;          // one half (hi or lo) of a (tile, K chunk) block
+    const size_t bytes = (size_t)L->n_tiles * L->nkc * 2 * oper;
     std::vector<__half> img(bytes / 2, __float2half_rn(0.f));
     for (int n = 0; n < N; ++n)
         for (int k = 0; k < K; ++k) {
             const double v = scale * (double)w[(size_t)n * K + k];
             const __half hi = __float2half_rn((float)v);
             const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
-            const size_t at = (((size_t)(n / BN) * L->nkc + k / BK) * 2) * (OPER_BYTES / 2) +
-                              (size_t)((k % BK) / 8) * 1024 + (size_t)(n % BN) * 8 + (k % 8);
+            const int r = n % bn, kk = k % BK;
+            // no swizzle: [k / 8][row][k % 8]; 128-byte swizzle: [row / 8][row % 8][(k / 8) ^ (row % 8)][k % 8]
+            const size_t in_tile = sw128 ? (size_t)(r / 8) * 512 + (size_t)(r % 8) * 64 + (size_t)((kk / 8) ^ (r % 8)) * 8 + (kk % 8)
+                                         : (size_t)(kk / 8) * (bn * 8) + (size_t)r * 8 + (kk % 8);
+            const size_t at = (((size_t)(n / bn) * L->nkc + k / BK) * 2) * (oper / 2) + in_tile;
             img[at] = hi;
-            img[at + OPER_BYTES / 2] = lo;
+            img[at + oper / 2] = lo;
         }
     MS_CUDA(cudaMalloc((void **)&L->b_img, bytes));
     MS_CUDA(cudaMemcpy(L->b_img, img.data(), bytes, cudaMemcpyHostToDevice));
@@ -286,6 +484,10 @@ int spec_tc_prepare(ms_ctx *ctx) {
     int rc;
     if ((rc = pack_weights(S.w1, S.h, S.h, &pk->l1))) return rc;
     if ((rc = pack_weights(S.w2, S.npix, S.h, &pk->l2))) return rc;
+    if (16 * pk->l2.nkc * (BK / 16) + 2 * TBN <= 512) {     // activations + two accumulators fit tensor memory
+        if ((rc = pack_weights(S.w2, S.npix, S.h, &pk->l2ts, TBN, true))) return rc;
+        MS_CUDA(cudaFuncSetAttribute(spec_out_gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SM_TOTAL));
+    }
     MS_CUDA(cudaFuncSetAttribute(spec_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     MS_CUDA(cudaFuncSetAttribute(spec_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     return MS_OK;
@@ -294,7 +496,8 @@ int spec_tc_prepare(ms_ctx *ctx) {
 void spec_tc_release(ms_ctx *ctx) {
     SpecTcPack *pk = static_cast<SpecTcPack *>(ctx->spec.tc_pack);
     if (!pk) return;
-    cudaFree(pk->l1.b_img); cudaFree(pk->l2.b_img); cudaFree(pk->a1_img); cudaFree(pk->a2_img);
+    cudaFree(pk->l1.b_img); cudaFree(pk->l2.b_img); cudaFree(pk->l2ts.b_img); cudaFree(pk->a1_img); cudaFree(pk->a2_img);
+    cudaFree(pk->a2_ts);
     delete pk;
     ctx->spec.tc_pack = nullptr;
 }
@@ -306,10 +509,11 @@ int spec_tc_reserve(ms_ctx *ctx, int64_t chunk) {
     const size_t rows = (size_t)((chunk + BM - 1) / BM) * BM;
     if (pk->a_img_rows >= rows) return MS_OK;
     if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
-    cudaFree(pk->a1_img); cudaFree(pk->a2_img);
-    pk->a1_img = pk->a2_img = nullptr; pk->a_img_rows = 0;
+    cudaFree(pk->a1_img); cudaFree(pk->a2_img); cudaFree(pk->a2_ts);
+    pk->a1_img = pk->a2_img = pk->a2_ts = nullptr; pk->a_img_rows = 0;
     MS_CUDA(cudaMalloc((void **)&pk->a1_img, rows / BM * pk->l1.nkc * 2 * OPER_BYTES));
     MS_CUDA(cudaMalloc((void **)&pk->a2_img, rows / BM * pk->l2.nkc * 2 * OPER_BYTES));
+    if (pk->l2ts.b_img) MS_CUDA(cudaMalloc((void **)&pk->a2_ts, rows / BM * pk->l2.nkc * (BK / 16) * 4 * BM * 16));
     pk->a_img_rows = rows;
     return MS_OK;
 }
@@ -335,7 +539,10 @@ int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, 
     GemmArgs ga;
     ga.B = B; ga.m_tiles = m_tiles; ga.leak = (float)S.leak;
     // layer 1: H -> H, epilogue packs the operand image of the output layer
+    static const bool ts_env_off = getenv("MS_SPEC_GEMM_TS") && atoi(getenv("MS_SPEC_GEMM_TS")) == 0;   // A/B timing only
+    const bool ts = pk->l2ts.b_img != nullptr && ctx->spec_gemm_ts && !ts_env_off;
     ga.a_img = pk->a1_img; ga.b_img = pk->l1.b_img; ga.bias = S.b1; ga.out = nullptr; ga.out_img = pk->a2_img;
+    ga.out_ts = ts ? pk->a2_ts : nullptr;
     ga.P = S.h; ga.nkc = pk->l1.nkc; ga.n_tiles = pk->l1.n_tiles; ga.nkc_out = pk->l2.nkc; ga.inv_scale = pk->l1.inv_scale;
     {
         const int ntiles = m_tiles * ga.n_tiles;
@@ -343,7 +550,21 @@ int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, 
         ctx->launches++;
         MS_CUDA(cudaGetLastError());
     }
-    // output layer
+    // output layer: A-stationary form when the activations fit tensor memory
+    if (ts) {
+        TsArgs ta;
+        ta.a_ts = pk->a2_ts; ta.b_img = pk->l2ts.b_img; ta.bias = S.b2; ta.out = flux; ta.B = B; ta.P = S.npix;
+        ta.nkc = pk->l2ts.nkc; ta.m_tiles = m_tiles; ta.n_tiles = pk->l2ts.n_tiles; ta.inv_scale = pk->l2ts.inv_scale;
+        ta.G = ctx->sm_count / m_tiles;
+        if (ta.G < 1) ta.G = 1;
+        if (ta.G > ta.n_tiles) ta.G = ta.n_tiles;
+        const int nitems = m_tiles * ta.G;
+        spec_out_gemm_ts_kernel<<<nitems < ctx->sm_count ? nitems : ctx->sm_count, NTHREADS, TS_SM_TOTAL, st>>>(ta);
+        ctx->launches++;
+        MS_CUDA(cudaGetLastError());
+        return MS_OK;
+    }
+    ga.out_ts = nullptr;
     ga.a_img = pk->a2_img; ga.b_img = pk->l2.b_img; ga.bias = S.b2; ga.out = flux; ga.out_img = nullptr;
     ga.P = S.npix; ga.nkc = pk->l2.nkc; ga.n_tiles = pk->l2.n_tiles; ga.nkc_out = 0; ga.inv_scale = pk->l2.inv_scale;
     {

@@ -76,6 +76,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
            ((uint64_t)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
 }
 
+// K-major, 128-byte swizzle: rows of 128 B (64 fp16 along K), 8-row atoms of 1024 B, the 16-byte chunk index of a row
+// XORed with the row's index in its atom (the layout TMA writes for SWIZZLE_128B; here the images are packed that way on
+// the host).  SBO = 1024 B between atoms, LBO unused; the tile base must be 1024-byte aligned; a k-step of 16 advances the
+// start address by 32 B.  The no-swizzle layout above makes the tensor core fetch the B operand one 16-byte row per
+// clock (measured: MMA time proportional to N at ~2 clk per column); this one is read at full shared-memory width.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 #define TMEM_LD32(addr, v)                                                                          \
     asm volatile(                                                                                   \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                   \
