@@ -42,21 +42,30 @@ enum { BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_ACC_FULL = 2 * STAGES, BAR_ACC_EMPT
 // Layer 0 + operand packing: h1 = lrelu(W0 x + b0) for the scaled labels x of every point, written as the
 // A image [m_tile][k_chunk][hi|lo][k8][row][8] (fp16, zero padded in rows >= B and k >= H) of the layer-1 GEMM.
 // One thread per (row, group of 8 hidden units).
+// chunk_pad > 0: the image holds the rows of a super-batch chunk by chunk, every chunk padded to chunk_pad (a multiple of
+// BM) rows, so that each chunk's m-tiles start on an m-tile of the image: image row c * chunk_pad + r <- input row
+// c * chunk + r.  nrows_img = rows of the image (a multiple of BM).
 __global__ void spec_l0_pack_kernel(const double *__restrict__ pars, int64_t B, int d_in, int logt,
                                     const double *__restrict__ xms /*[16]: xmin | xscale*/,
                                     const float *__restrict__ w0, const float *__restrict__ b0, int H, float leak,
-                                    int nkc, __half *__restrict__ img) {
-    const int64_t ntask = (int64_t)((B + BM - 1) / BM) * BM * nkc * (BK / 8);
+                                    int nkc, __half *__restrict__ img, int64_t nrows_img, int chunk, int chunk_pad) {
+    const int64_t ntask = nrows_img * nkc * (BK / 8);
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ntask; t += (int64_t)gridDim.x * blockDim.x) {
         const int r = (int)(t % BM);
         const int k8 = (int)((t / BM) % (BK / 8));
         const int kc = (int)((t / (BM * (BK / 8))) % nkc);
         const int64_t mt = t / ((int64_t)BM * (BK / 8) * nkc);
-        const int64_t row = mt * BM + r;
+        int64_t row = mt * BM + r;                                   // row of the image -> row of the input
+        bool inb = row < B;
+        if (chunk_pad > 0) {
+            const int64_t c = row / chunk_pad, rr = row - c * chunk_pad;
+            row = c * chunk + rr;
+            inb = rr < chunk && row < B;
+        }
         const int k0 = kc * BK + k8 * 8;
         __half hi[8], lo[8];
         float xs[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        bool live = row < B;
+        bool live = inb;
         if (live) {
             const double *q = pars + row * MS_NPARS;
             live = q[PV_TEFF] != ms_inf();
@@ -66,7 +75,7 @@ __global__ void spec_l0_pack_kernel(const double *__restrict__ pars, int64_t B, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float v = 0.f;
-            if (row < B && k0 + i < H) {
+            if (inb && k0 + i < H) {
                 v = b0[k0 + i];
                 for (int d = 0; d < d_in; ++d) v = fmaf(xs[d], w0[(k0 + i) * d_in + d], v);
                 v = v > 0.f ? v : leak * v;
@@ -503,10 +512,11 @@ void spec_tc_release(ms_ctx *ctx) {
 }
 
 // operand-image scratch for chunks of up to `chunk` points
-int spec_tc_reserve(ms_ctx *ctx, int64_t chunk) {
+// chunk: points per chunk; nchunks: chunks whose hidden layers are computed in one go (spec_tc_hidden)
+int spec_tc_reserve(ms_ctx *ctx, int64_t chunk, int nchunks) {
     SpecTcPack *pk = static_cast<SpecTcPack *>(ctx->spec.tc_pack);
     if (!pk) { ms_set_error("spectral net not packed for MS_PREC_TC"); return MS_ESTATE; }
-    const size_t rows = (size_t)((chunk + BM - 1) / BM) * BM;
+    const size_t rows = (size_t)((chunk + BM - 1) / BM) * BM * (size_t)(nchunks < 1 ? 1 : nchunks);
     if (pk->a_img_rows >= rows) return MS_OK;
     if (ctx->scratch_locked) { ms_set_error("spectrum scratch reserved for a smaller batch (ms_reserve)"); return MS_ESTATE; }
     cudaFree(pk->a1_img); cudaFree(pk->a2_img); cudaFree(pk->a2_ts);
@@ -524,7 +534,7 @@ int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, 
     SpecTcPack *pk = static_cast<SpecTcPack *>(S.tc_pack);
     if (!pk) { ms_set_error("spectral net not packed for MS_PREC_TC"); return MS_ESTATE; }
     int rc;
-    if ((rc = spec_tc_reserve(ctx, B))) return rc;
+    if ((rc = spec_tc_reserve(ctx, B, 1))) return rc;
     const int m_tiles = (int)((B + BM - 1) / BM);
     KernelTimer timer_(ctx, MS_K_SPEC_MLP, st);
     {
@@ -532,7 +542,7 @@ int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, 
         int blocks = (int)((ntask + 255) / 256);
         if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
         spec_l0_pack_kernel<<<blocks, 256, 0, st>>>(pars, B, S.d_in, S.logt_input, S.xms, S.w0, S.b0, S.h, (float)S.leak,
-                                                    pk->l1.nkc, reinterpret_cast<__half *>(pk->a1_img));
+                                                    pk->l1.nkc, reinterpret_cast<__half *>(pk->a1_img), (int64_t)m_tiles * BM, 0, 0);
         ctx->launches++;
         MS_CUDA(cudaGetLastError());
     }
@@ -573,5 +583,65 @@ int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, 
         ctx->launches++;
         MS_CUDA(cudaGetLastError());
     }
+    return MS_OK;
+}
+
+// Hidden layers of a whole super-batch in one go (two launches instead of two per chunk: the 300 x 300 layer of one
+// 1480-row chunk is 36 tiles on 148 SMs, 14 us of latency): rows [0, B) of `pars`, laid out chunk by chunk with every chunk
+// padded to whole m-tiles so that spec_tc_out can sweep a chunk's own m-tiles.  Returns 1 when the A-stationary output
+// kernel is not available (the caller then uses launch_spec_mlp_tc per chunk), 0 on success, < 0 on error.
+int spec_tc_hidden(ms_ctx *ctx, const double *pars, int64_t B, int64_t chunk, cudaStream_t st) {
+    SpecNetDev &S = ctx->spec;
+    SpecTcPack *pk = static_cast<SpecTcPack *>(S.tc_pack);
+    if (!pk) { ms_set_error("spectral net not packed for MS_PREC_TC"); return MS_ESTATE; }
+    static const bool ts_env_off = getenv("MS_SPEC_GEMM_TS") && atoi(getenv("MS_SPEC_GEMM_TS")) == 0;
+    if (!pk->l2ts.b_img || !ctx->spec_gemm_ts || ts_env_off) return 1;
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    const int64_t chunk_pad = (chunk + BM - 1) / BM * BM;
+    int rc;
+    if ((rc = spec_tc_reserve(ctx, chunk, (int)nchunks))) return rc;
+    const int64_t rows_img = nchunks * chunk_pad;
+    const int m_tiles = (int)(rows_img / BM);
+    KernelTimer timer_(ctx, MS_K_SPEC_MLP, st);
+    {
+        const int64_t ntask = rows_img * pk->l1.nkc * (BK / 8);
+        int64_t blocks = (ntask + 255) / 256;
+        if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+        spec_l0_pack_kernel<<<(unsigned)blocks, 256, 0, st>>>(pars, B, S.d_in, S.logt_input, S.xms, S.w0, S.b0, S.h, (float)S.leak,
+                                                             pk->l1.nkc, reinterpret_cast<__half *>(pk->a1_img), rows_img,
+                                                             (int)chunk, (int)chunk_pad);
+        ctx->launches++;
+        MS_CUDA(cudaGetLastError());
+    }
+    GemmArgs ga;
+    ga.B = rows_img; ga.m_tiles = m_tiles; ga.leak = (float)S.leak;
+    ga.a_img = pk->a1_img; ga.b_img = pk->l1.b_img; ga.bias = S.b1; ga.out = nullptr; ga.out_img = pk->a2_img;
+    ga.out_ts = pk->a2_ts;
+    ga.P = S.h; ga.nkc = pk->l1.nkc; ga.n_tiles = pk->l1.n_tiles; ga.nkc_out = pk->l2.nkc; ga.inv_scale = pk->l1.inv_scale;
+    const int ntiles = m_tiles * ga.n_tiles;
+    spec_gemm_tc_kernel<true><<<ntiles < ctx->sm_count ? ntiles : ctx->sm_count, NTHREADS, SM_TOTAL, st>>>(ga);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+// Output layer of chunk `ci` (nb rows) of the super-batch prepared by spec_tc_hidden
+int spec_tc_out(ms_ctx *ctx, int64_t ci, int64_t chunk, int64_t nb, float *flux, cudaStream_t st) {
+    SpecNetDev &S = ctx->spec;
+    SpecTcPack *pk = static_cast<SpecTcPack *>(S.tc_pack);
+    const int64_t mt_per_chunk = (chunk + BM - 1) / BM;
+    const int m_tiles = (int)((nb + BM - 1) / BM);
+    KernelTimer timer_(ctx, MS_K_SPEC_MLP, st);
+    TsArgs ta;
+    ta.a_ts = pk->a2_ts + (size_t)ci * mt_per_chunk * pk->l2ts.nkc * (BK / 16) * 4 * BM * 16;
+    ta.b_img = pk->l2ts.b_img; ta.bias = S.b2; ta.out = flux; ta.B = nb; ta.P = S.npix;
+    ta.nkc = pk->l2ts.nkc; ta.m_tiles = m_tiles; ta.n_tiles = pk->l2ts.n_tiles; ta.inv_scale = pk->l2ts.inv_scale;
+    ta.G = ctx->sm_count / m_tiles;
+    if (ta.G < 1) ta.G = 1;
+    if (ta.G > ta.n_tiles) ta.G = ta.n_tiles;
+    const int nitems = m_tiles * ta.G;
+    spec_out_gemm_ts_kernel<<<nitems < ctx->sm_count ? nitems : ctx->sm_count, NTHREADS, TS_SM_TOTAL, st>>>(ta);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
     return MS_OK;
 }

@@ -631,6 +631,8 @@ int spec_mlp_chunk_t(ms_ctx *ctx, const double *pars, int64_t B, T *hid, T *flux
 // (chunk x npix x 4 B) stays resident in the 126 MB L2: the GEMM's stores and the smoother's loads then never
 // reach HBM (11 row tiles of 128 points x 80 pixel tiles = 880 tiles = 5.95 waves of 148 CTAs at npix = 10240).
 // f64 (validation mode): small chunks, CUDA-core GEMM.
+constexpr int64_t SPEC_SUPER = 64;      // tc modes: chunks whose hidden layers are computed in one go (operand images: 320 KB per 128 rows)
+
 static int64_t spec_chunk(const ms_ctx *ctx) {
     if (ctx->precision == MS_PREC_F64) return 1024;
     const int64_t by_l2 = (int64_t)(60u << 20) / ((int64_t)ctx->spec.npix * 4);      // <= 60 MB of flux in flight
@@ -666,7 +668,11 @@ int spec_reserve(ms_ctx *ctx, int64_t max_batch) {
     if ((rc = grow(&ctx->scr_flux, &ctx->scr_flux_bytes, flux_bytes))) return rc;
     if ((rc = grow(&ctx->scr_hid, &ctx->scr_hid_bytes, hid_bytes))) return rc;
     if ((rc = grow((void **)&ctx->scr_fb, &ctx->scr_fb_bytes, fb_bytes))) return rc;
-    if (ctx->precision >= MS_PREC_TC && (rc = spec_tc_reserve(ctx, chunk))) return rc;
+    if (ctx->precision >= MS_PREC_TC) {            // hidden layers of up to SPEC_SUPER chunks at a time
+        int64_t nch = (max_batch + chunk - 1) / chunk;
+        if (nch > SPEC_SUPER) nch = SPEC_SUPER;
+        if ((rc = spec_tc_reserve(ctx, chunk, (int)nch))) return rc;
+    }
     return MS_OK;
 }
 
@@ -711,10 +717,21 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
     int *fb_count = ctx->scr_fb;
     PointSetup *fb_setup = reinterpret_cast<PointSetup *>(ctx->scr_fb + 4);
     int *fb_rows = reinterpret_cast<int *>(fb_setup + chunk);
+    const bool tc = sizeof(T) == 4 && ctx->precision >= MS_PREC_TC;
+    bool hoisted = false;                          // hidden layers of the current super-batch are in place
+    int64_t super0 = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk) {
         const int64_t nb = (B - b0 < chunk) ? B - b0 : chunk;
-        int rc = spec_mlp_chunk_t<T>(ctx, a.pars + b0 * MS_NPARS, nb, (T *)ctx->scr_hid,
-                                     (T *)ctx->scr_flux, n.xms, st);
+        int rc;
+        if (tc && (b0 - super0) % (SPEC_SUPER * chunk) == 0) {     // a new super-batch starts here
+            super0 = b0;
+            const int64_t nsup = B - b0 < SPEC_SUPER * chunk ? B - b0 : SPEC_SUPER * chunk;
+            rc = spec_tc_hidden(ctx, a.pars + b0 * MS_NPARS, nsup, chunk, st);
+            if (rc < 0) return rc;
+            hoisted = rc == 0;
+        }
+        if (tc && hoisted) rc = spec_tc_out(ctx, (b0 - super0) / chunk, chunk, nb, (float *)ctx->scr_flux, st);
+        else rc = spec_mlp_chunk_t<T>(ctx, a.pars + b0 * MS_NPARS, nb, (T *)ctx->scr_hid, (T *)ctx->scr_flux, n.xms, st);
         if (rc) return rc;
         SmoothArgs sa;
         sa.pars = a.pars + b0 * MS_NPARS;
