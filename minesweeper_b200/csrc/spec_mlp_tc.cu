@@ -549,8 +549,7 @@ int launch_spec_mlp_tc(ms_ctx *ctx, const double *pars, int64_t B, float *flux, 
     GemmArgs ga;
     ga.B = B; ga.m_tiles = m_tiles; ga.leak = (float)S.leak;
     // layer 1: H -> H, epilogue packs the operand image of the output layer
-    static const bool ts_env_off = getenv("MS_SPEC_GEMM_TS") && atoi(getenv("MS_SPEC_GEMM_TS")) == 0;   // A/B timing only
-    const bool ts = pk->l2ts.b_img != nullptr && ctx->spec_gemm_ts && !ts_env_off;
+    const bool ts = pk->l2ts.b_img != nullptr && ctx->spec_gemm_ts;
     ga.a_img = pk->a1_img; ga.b_img = pk->l1.b_img; ga.bias = S.b1; ga.out = nullptr; ga.out_img = pk->a2_img;
     ga.out_ts = ts ? pk->a2_ts : nullptr;
     ga.P = S.h; ga.nkc = pk->l1.nkc; ga.n_tiles = pk->l1.n_tiles; ga.nkc_out = pk->l2.nkc; ga.inv_scale = pk->l1.inv_scale;
@@ -594,8 +593,7 @@ int spec_tc_hidden(ms_ctx *ctx, const double *pars, int64_t B, int64_t chunk, cu
     SpecNetDev &S = ctx->spec;
     SpecTcPack *pk = static_cast<SpecTcPack *>(S.tc_pack);
     if (!pk) { ms_set_error("spectral net not packed for MS_PREC_TC"); return MS_ESTATE; }
-    static const bool ts_env_off = getenv("MS_SPEC_GEMM_TS") && atoi(getenv("MS_SPEC_GEMM_TS")) == 0;
-    if (!pk->l2ts.b_img || !ctx->spec_gemm_ts || ts_env_off) return 1;
+    if (!pk->l2ts.b_img || !ctx->spec_gemm_ts) return 1;
     const int64_t nchunks = (B + chunk - 1) / chunk;
     const int64_t chunk_pad = (chunk + BM - 1) / BM * BM;
     int rc;
