@@ -140,6 +140,25 @@ def test_lnprobfn_with_reference_style_prior(g_like_phot):
         assert fitstar.lnprobfn(list(th[i]), L, P) == batch[i]
     assert np.isneginf(batch[np.isneginf(g['lnl'][:64])]).all()
 
+    # BatchPool: what dynesty hands to pool.map is its wrapper object around lnprobfn (attribute .func, called with one
+    # point) -- the queued points then go through ONE batched call; any other callable is mapped point by point
+    class _function_wrapper(object):                      # shape of dynesty.utils._function_wrapper
+        def __init__(self, func, args):
+            self.func, self.args = func, args
+
+        def __call__(self, x):
+            return self.func(x, *self.args)
+    pool = fitstar.BatchPool(L, P, size=16)
+    wrapped = _function_wrapper(fitstar.lnprobfn, (L, P))
+    c0 = L.engine.launch_count()
+    got = pool.map(wrapped, [list(t) for t in th[:16]])
+    nbatch = L.engine.launch_count() - c0
+    assert np.array_equal(np.asarray(got), batch[:16])
+    c0 = L.engine.launch_count()
+    serial = [wrapped(list(t)) for t in th[:16]]
+    assert np.array_equal(np.asarray(serial), batch[:16]) and L.engine.launch_count() - c0 == 16 * nbatch
+    assert pool.map(lambda x: 2.0 * x[0], [[1.0], [2.5]]) == [2.0, 5.0]
+
 
 # ---------------------------------------------------------------- kernel (3)
 @pytest.mark.parametrize('prec', PRECS + ['tc'])
