@@ -3,6 +3,15 @@
 // (512 columns), whose layer-2 weights (256 KB per band as hi + lo) do not fit shared memory either and are streamed
 // through the ring in K slices of 32 instead of as one image per band.
 constexpr int H = PH_H;              // hidden width of this instantiation
+// chunks of an epilogue loop in flight per thread (measured at H = 128, ms per 2^20 points: E1 / E2 = 1 / 1: 1.367,
+// 2 / 1: 1.349, 4 / 1: 1.328, 4 / 2: 1.308, 4 / 4: 1.383, 1 / 2: 1.368; H = 256: 3.67 -> 3.59; H = 64 is faster without)
+#ifndef MS_PH_E1_UNROLL
+#define MS_PH_E1_UNROLL (PH_H >= 128 ? 4 : 1)
+#endif
+#ifndef MS_PH_E2_UNROLL
+#define MS_PH_E2_UNROLL (PH_H >= 128 ? 2 : 1)
+#endif
+constexpr int PH_E1_UNROLL = MS_PH_E1_UNROLL, PH_E2_UNROLL = MS_PH_E2_UNROLL;
 constexpr int NT = H <= 128 ? 2 : 1; // tiles (of 128 points) a CTA works on at a time
 constexpr bool STREAM = H > 128;     // layer-2 weights arrive in K slices
 // Per-band weight image in global memory (and in each shared-memory ring slot).
@@ -435,7 +444,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 // ---- layer-1 epilogue: activation, fp16 (split), written back in place as the TS A operand
                 mbar_wait(bar(BAR_D1 + T), g & 1);
                 tc_fence_after();
-#pragma unroll 1
+#pragma unroll PH_E1_UNROLL
                 for (int i4 = 0; i4 < NCH / 2; ++i4) {
                     const int c = 2 * i4 + half;
                     uint32_t v[16], o[16];
@@ -476,7 +485,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                 float bc0 = 0.f, bc1 = 0.f;
                 mbar_wait(bar(BAR_D2 + T), g & 1);
                 tc_fence_after();
-#pragma unroll 1
+#pragma unroll PH_E2_UNROLL
                 for (int i4 = 0; i4 < NCH / 2; ++i4) {
                     const int c = 2 * i4 + half;
                     uint32_t v[16];
