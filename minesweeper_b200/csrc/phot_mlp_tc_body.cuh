@@ -12,6 +12,10 @@ constexpr int H = PH_H;              // hidden width of this instantiation
 #define MS_PH_E2_UNROLL (PH_H >= 128 ? 2 : 1)
 #endif
 constexpr int PH_E1_UNROLL = MS_PH_E1_UNROLL, PH_E2_UNROLL = MS_PH_E2_UNROLL;
+#ifndef MS_PH_ROWS
+#define MS_PH_ROWS 1
+#endif
+constexpr int PH_ROWS = MS_PH_ROWS;         // corner rows of the MIST gather per memory round trip in the prologue (1: 1.302 ms, 2: 1.308, 4: 1.459, 8: 1.573 -- spills)
 constexpr int NT = H <= 128 ? 2 : 1; // tiles (of 128 points) a CTA works on at a time
 constexpr bool STREAM = H > 128;     // layer-2 weights arrive in K slices
 // Per-band weight image in global memory (and in each shared-memory ring slot).
@@ -332,7 +336,7 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
                         int idx[4];
                         float acc[MS_NCOL], wsum;
                         double accd[2], wsumd;
-                        const bool inside = mist::interp_point_f32<FAST ? 1 : 2>(g, n, a.table, x, idx, acc, wsum, accd, wsumd);   // rows per round trip: measured
+                        const bool inside = mist::interp_point_f32<FAST ? 1 : PH_ROWS>(g, n, a.table, x, idx, acc, wsum, accd, wsumd);   // rows per round trip: measured
                         const bool okp = inside && (wsum > 0.f);
                         const float inv = okp ? __fdividef(1.f, wsum) : 0.f;
                         const double inf = ms_inf();
