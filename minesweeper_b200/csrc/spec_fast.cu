@@ -33,6 +33,13 @@ namespace {
 #define MS_IP_UNROLL 2        // butterflies in flight per thread in a transform stage (2 = all of them at 512 threads: 11.34 -> 10.67 ms)
 #endif
 constexpr int IP_UNROLL = MS_IP_UNROLL;
+#ifndef MS_FIR_UNROLL
+#define MS_FIR_UNROLL 2
+#endif
+#ifndef MS_BACK_UNROLL
+#define MS_BACK_UNROLL 4           // resampling back onto the native pixels: 10.89 -> 10.72 ms
+#endif
+constexpr int FIR_UNROLL = MS_FIR_UNROLL, BACK_UNROLL = MS_BACK_UNROLL;
 #ifndef MS_QUAD_UNROLL
 #define MS_QUAD_UNROLL 1
 #endif
@@ -463,6 +470,7 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
             // smoothing.py:262: interpolation of the filtered n1 grid at the native wavelengths
             AffinePos ap;
             ap.set((double)(n1 - 1) / (double)(npix - 1));
+#pragma unroll BACK_UNROLL
             for (int i = threadIdx.x; i < npix; i += FT) {
                 float t;
                 int k = ap.split(i, t);
@@ -550,7 +558,7 @@ spec_fast_kernel(SmoothArgs a, int nB, const PointSetup *__restrict__ setup) {
                     const float4 *wa = reinterpret_cast<const float4 *>(wtab + o * WSTRIDE);
                     float a0b = 0.f, a1b = 0.f;
                     float4 x = xa[0];
-#pragma unroll 2
+#pragma unroll FIR_UNROLL
                     for (int c = 0; c < nch; ++c) {
                         const float4 g = wa[c];
                         float4 xn = {0.f, 0.f, 0.f, 0.f};
