@@ -67,18 +67,19 @@ __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
     }
 }
 
-// One WARP per walker, a lane per element of its record (nd unit-cube coordinates, nd parameters, nder derived values,
+// Half a WARP per walker, a lane per element of its record (nd unit-cube coordinates, nd parameters, nder derived values,
 // the ln prob, the acceptance counter): consecutive lanes touch consecutive addresses.  The thread-per-walker form copied
 // 31 doubles per thread with a 248-byte stride between neighbours (107 us per 400 k walkers in the launch list of the
-// catalog run, 13 % of a sampler step; this form: 82 us).  Rejected walkers load nothing beyond their ln prob.
+// catalog run, 13 % of a sampler step; a warp per walker: 82 us).  Rejected walkers load nothing beyond their ln prob.
 __global__ void ns_accept_kernel(ms_ns_state s) {
+    // half a warp per walker (two independent walkers per warp iteration), a lane per element of the record
     const int nd = s.nd, ncol = s.nd + s.nder, w = nd + ncol + 1;        // elements per walker
-    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int64_t n = (int64_t)s.S * s.Q;
-    for (int64_t wk = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); wk < n; wk += (int64_t)gridDim.x * wpb) {
+    const int hl = threadIdx.x & 15;
+    const int64_t hpb = blockDim.x >> 4, n = (int64_t)s.S * s.Q;
+    for (int64_t wk = blockIdx.x * hpb + (threadIdx.x >> 4); wk < n; wk += (int64_t)gridDim.x * hpb) {
         const double lp = s.prop_lp[wk];
-        if (!(lp > s.lmin[wk / s.Q])) continue;                          // warp-uniform
-        for (int c = lane; c < w; c += 32) {
+        if (!(lp > s.lmin[wk / s.Q])) continue;
+        for (int c = hl; c < w; c += 16) {
             if (c < ncol) {
                 s.cur_row[wk * ncol + c] = c < nd ? s.prop_theta[wk * nd + c] : s.prop_der[wk * s.nder + (c - nd)];
             } else if (c < ncol + nd) {
@@ -324,8 +325,8 @@ extern "C" int ms_ns_accept(ms_ctx *ctx, const ms_ns_state *s, void *stream) {
     int rc = check_state(s);
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
-    const int64_t n = (int64_t)s->S * s->Q;                              // one warp per walker, 8 warps per CTA
-    int64_t blocks = (n + 7) / 8, cap = (int64_t)ctx->sm_count * 8;
+    const int64_t n = (int64_t)s->S * s->Q;                              // half a warp per walker, 16 walkers per CTA
+    int64_t blocks = (n + 15) / 16, cap = (int64_t)ctx->sm_count * 8;
     ns_accept_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(*s);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
