@@ -215,6 +215,7 @@ int spec_prepare(ms_ctx *ctx, const ms_spec_net_desc *d);
 int spec_reserve(ms_ctx *ctx, int64_t max_batch);      // allocate the chunk buffers of the spectrum path now
 int spec_tc_prepare(ms_ctx *ctx);           // pack W2 for the tensor-core output GEMM
 int spec_tc_reserve(ms_ctx *ctx, int64_t chunk, int nchunks);   // operand-image scratch of the tensor-core GEMMs: nchunks chunks of `chunk` points
+bool spec_tc_would_grow(const ms_ctx *ctx, int64_t chunk, int nchunks);
 int spec_tc_hidden(ms_ctx *ctx, const double *pars, int64_t B, int64_t chunk, cudaStream_t st);   // hidden layers of a super-batch (1: not available)
 int spec_tc_out(ms_ctx *ctx, int64_t ci, int64_t chunk, int64_t nb, float *flux, cudaStream_t st);  // output layer of its chunk ci
 void spec_tc_release(ms_ctx *ctx);

@@ -512,6 +512,13 @@ void spec_tc_release(ms_ctx *ctx) {
 }
 
 // operand-image scratch for chunks of up to `chunk` points
+// whether spec_tc_reserve(ctx, chunk, nchunks) would have to allocate (run_spec refuses that during stream capture)
+bool spec_tc_would_grow(const ms_ctx *ctx, int64_t chunk, int nchunks) {
+    const SpecTcPack *pk = static_cast<const SpecTcPack *>(ctx->spec.tc_pack);
+    if (!pk) return false;
+    return pk->a_img_rows < (size_t)((chunk + BM - 1) / BM) * BM * (size_t)(nchunks < 1 ? 1 : nchunks);
+}
+
 // chunk: points per chunk; nchunks: chunks whose hidden layers are computed in one go (spec_tc_hidden)
 int spec_tc_reserve(ms_ctx *ctx, int64_t chunk, int nchunks) {
     SpecTcPack *pk = static_cast<SpecTcPack *>(ctx->spec.tc_pack);

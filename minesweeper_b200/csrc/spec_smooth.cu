@@ -685,7 +685,10 @@ static int run_spec(ms_ctx *ctx, const SpecArgs &a, int64_t B, cudaStream_t st) 
         const bool capturing = cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
         const int64_t need = B < chunk ? B : chunk;
         const size_t esz = sizeof(T);
-        if (capturing && (ctx->scr_flux_bytes < (size_t)need * n.npix * esz || !ctx->scr_fb)) {
+        int64_t nch = (B + chunk - 1) / chunk;
+        if (nch > SPEC_SUPER) nch = SPEC_SUPER;
+        const bool tc_grow = ctx->precision >= MS_PREC_TC && spec_tc_would_grow(ctx, chunk, (int)nch);
+        if (capturing && (ctx->scr_flux_bytes < (size_t)need * n.npix * esz || !ctx->scr_fb || tc_grow)) {
             ms_set_error("spectrum scratch would be allocated during stream capture: call ms_reserve first");
             return MS_ESTATE;
         }
