@@ -530,6 +530,38 @@ def test_host_entry_forms_agree_with_device_entry(n):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('extra', [['Vmic', 'log(A)'], ['Vmic', 'log(A)', 'Vrad']])
+def test_host_entry_with_wider_theta(extra):
+    """Rows of 8 sampled parameters are still staged through shared memory and read in place from pinned memory; rows of
+    9 are not (the staging buffer holds 8 doubles per point) and take the upload form.  The extra columns are parameters
+    the photometric path ignores, so the results must equal those of the 6-column fit, interleaved columns and all."""
+    import torch
+    from minesweeper_b200.likelihood import likelihood
+    fitargs, fitpars, rb, th0 = _phot_fit(h=128)
+    n = 148 * 256 * 4 + 300
+    th6 = np.tile(th0, (n // len(th0) + 1, 1))[:n].copy()
+    th6[:, 0] *= np.linspace(0.9, 1.1, n)
+    L6 = likelihood(fitargs, fitpars, rb, precision='tc', verbose=False)
+    ref = L6.lnlike_batch(th6, want_derived=False)[0].cpu().numpy()
+    names = fitpars[0]
+    fp2 = [names, dict(fitpars[1], **{k: True for k in extra})]
+    L = likelihood(fitargs, fp2, rb, precision='tc', verbose=False)
+    assert L.ndim == 6 + len(extra)
+    rng = np.random.default_rng(3)
+    wide = np.empty((n, L.ndim))
+    six = [k for k in L6.fitpars_i]
+    for j, k in enumerate(L.fitpars_i):
+        wide[:, j] = th6[:, six.index(k)] if k in six else rng.normal(0.0, 1.0, n)
+    th_pin = torch.from_numpy(wide).pin_memory()
+    out_pin = torch.full((n,), 7.0, dtype=torch.float64).pin_memory()
+    L.lnlike_batch_host(th_pin.numpy(), lnl_out=out_pin.numpy())
+    got = out_pin.numpy()
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    np.testing.assert_array_equal(got[fin], ref[fin])
+
+
+@pytest.mark.gpu
 def test_fused_interp_phot_with_star_slots():
     """Catalog form of the fused kernel: every row carries its own star slot (its own observed magnitudes).
     One-kernel and two-kernel forms agree, and a row evaluated against slot s equals the single-star result
