@@ -12,6 +12,10 @@ constexpr int H = PH_H;              // hidden width of this instantiation
 #define MS_PH_E2_UNROLL (PH_H >= 128 ? 2 : 1)
 #endif
 constexpr int PH_E1_UNROLL = MS_PH_E1_UNROLL, PH_E2_UNROLL = MS_PH_E2_UNROLL;
+#ifndef MS_PH_E2_DOT
+#define MS_PH_E2_DOT 1
+#endif
+constexpr bool PH_E2_DOT = MS_PH_E2_DOT != 0;     // last layer: weighted sum of the sigmoids without forming them
 #ifndef MS_PH_ROWS
 #define MS_PH_ROWS 1
 #endif
@@ -498,6 +502,12 @@ phot_mlp_tc_kernel(TcArgs a, int64_t B, int npairs) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 cc = cb2[4 * c + i], w = w3[4 * c + i];
+                        if constexpr (!FAST && PH_E2_DOT) {
+                            const float sdot = sigmoid_dot_quad(__uint_as_float(v[4 * i]) + cc.x, __uint_as_float(v[4 * i + 1]) + cc.y,
+                                                               __uint_as_float(v[4 * i + 2]) + cc.z, __uint_as_float(v[4 * i + 3]) + cc.w, w);
+                            if (i & 1) bc1 += sdot; else bc0 += sdot;
+                            continue;
+                        }
                         float a0, a1, a2, a3;
                         if constexpr (FAST) {
                             a0 = tanh_approx(__uint_as_float(v[4 * i]) + cc.x);
