@@ -267,6 +267,11 @@ typedef struct {
     double *dead;                                     /* [S][dead_cap][nd+nder+MS_NS_TRAIL] or NULL: the row, then
                                                          log(lk) log(vol) log(wt) h nc log(z) delta(log(z))  */
     uint64_t *rng_round;                              /* device counter of completed rounds (graph-replay safe RNG stream) */
+    /* proposal: 0 = random walk from a live point (dynesty 'rwalk'), 1 = uniform in the bounding ellipsoid of the live
+     * points (dynesty 'unif': walks must be 1).  center[S][nd] and ell_r[S] (radius of the ellipsoid in units of the
+     * Cholesky factor `sigma`, enlargement included) are maintained by ms_ns_consume; they may be NULL when unif == 0. */
+    double *center, *ell_r;
+    int32_t unif;
 } ms_ns_state;
 /* step = walk step inside the current round (0 .. walks-1); the round number is read from rng_round */
 int ms_ns_propose(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t step, void *stream);

@@ -94,7 +94,8 @@ class NsState(C.Structure):
                 [(n, C.c_void_p) for n in ('live_u', 'live_lp', 'live_row', 'cur_u', 'cur_lp', 'cur_row', 'prop_u',
                                            'prop_lp', 'prop_theta', 'prop_der', 'nacc', 'lmin', 'sigma', 'scale',
                                            'logz', 'hacc', 'wmax', 'wtot', 'wsum', 'wsq', 'niter', 'ncall', 'done', 'dead',
-                                           'rng_round')])
+                                           'rng_round', 'center', 'ell_r')] +
+                [('unif', C.c_int32)])
 
 
 # every exported symbol of include/minesweeper_b200.h with its prototype

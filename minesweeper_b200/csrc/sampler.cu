@@ -55,6 +55,28 @@ __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
             if (d + 1 < s.nd) zv[d + 1] = rad * sn;
         }
         const double *Lc = s.sigma + (int64_t)star * s.nd * s.nd;
+        if (s.unif) {
+            // dynesty's 'unif': a point uniform in the bounding ellipsoid center + r L B (B = unit ball): direction
+            // from the Gaussian vector, radius r U^(1/nd); a point outside the unit cube is no proposal at all (NaN
+            // coordinates: the prior transform, the likelihood and the acceptance test all pass NaN through as a
+            // rejection) -- the rejection of the volume outside the cube that dynesty does by redrawing
+            double n2 = 0.0;
+            for (int d = 0; d < s.nd; ++d) n2 += zv[d] * zv[d];
+            const uint64_t zz = ns_mix(seed ^ 0x2545f4914f6cdd1dull, (uint64_t)wk, ctr + 15ull);
+            const double uu = ((double)(uint32_t)(zz >> 32) + 0.5) * 2.3283064365386963e-10;
+            const double rad = s.ell_r[star] * pow(uu, 1.0 / s.nd) / sqrt(n2);
+            const double *mu = s.center + (int64_t)star * s.nd;
+            bool inside = true;
+            double uv[MS_NPARAM];
+            for (int d = 0; d < s.nd; ++d) {
+                double step = 0.0;
+                for (int e = 0; e <= d; ++e) step = fma(Lc[d * s.nd + e], zv[e], step);
+                uv[d] = mu[d] + rad * step;
+                inside = inside && uv[d] > 0.0 && uv[d] < 1.0;
+            }
+            for (int d = 0; d < s.nd; ++d) s.prop_u[wk * s.nd + d] = inside ? uv[d] : ms_nan();
+            continue;
+        }
         for (int d = 0; d < s.nd; ++d) {
             double step = 0.0;
             for (int e = 0; e <= d; ++e) step = fma(Lc[d * s.nd + e], zv[e], step);
@@ -224,7 +246,7 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
     // at most Q of the K live points change per round, so it is refreshed every ~16 replacements.
     // Lane pe owns covariance entry pe (nd * nd <= 32 in practice, otherwise the lanes stride); the live
     // points stream through once per entry pair from L2, 7 KB per star.
-    const uint64_t cov_every = (uint64_t)(Q >= 16 ? 1 : 16 / Q);
+    const uint64_t cov_every = (uint64_t)((Q >= 16 || s.unif) ? 1 : 16 / Q);
     if (round % cov_every == 0) {
         const double *lu = s.live_u + lbase * nd;
         for (int d = lane; d < nd; d += 32) {
@@ -255,9 +277,31 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
                 }
             double *out = s.sigma + (int64_t)star * nd * nd;
             for (int i = 0; i < nd; ++i)
-                for (int j = 0; j < nd; ++j)
-                    out[i * nd + j] = ok ? (j <= i ? cov[i * nd + j] : 0.0)
-                                         : (i == j ? sqrt(fmax(diag[i], 1e-24)) : 0.0);   // degenerate: diagonal
+                for (int j = 0; j < nd; ++j) {
+                    const double v = ok ? (j <= i ? cov[i * nd + j] : 0.0)
+                                        : (i == j ? sqrt(fmax(diag[i], 1e-24)) : 0.0);    // degenerate: diagonal
+                    out[i * nd + j] = v;
+                    cov[i * nd + j] = v;                     // the factor actually used, for the radius below
+                }
+        }
+        __syncwarp();
+        if (s.unif) {
+            // bounding ellipsoid of the live points in the metric of the factor: r^2 = max_k |L^-1 (u_k - mean)|^2,
+            // enlarged by 25 % in volume as dynesty does (its default `enlarge`)
+            double r2 = 0.0;
+            for (int k = lane; k < K; k += 32) {
+                double y[MS_NPARAM], a2 = 0.0;
+                for (int i = 0; i < nd; ++i) {
+                    double a = lu[k * nd + i] - mean[i];
+                    for (int j = 0; j < i; ++j) a -= cov[i * nd + j] * y[j];
+                    y[i] = a / cov[i * nd + i];
+                    a2 += y[i] * y[i];
+                }
+                r2 = fmax(r2, a2);
+            }
+            for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+            if (lane == 0) s.ell_r[star] = sqrt(r2) * pow(1.25, 1.0 / nd);
+            for (int d = lane; d < nd; d += 32) s.center[(int64_t)star * nd + d] = mean[d];
         }
         __syncwarp();
     }
@@ -300,7 +344,7 @@ int check_state(const ms_ns_state *s) {
         !s->live_u || !s->live_lp || !s->live_row || !s->cur_u || !s->cur_lp || !s->cur_row || !s->prop_u ||
         !s->prop_lp || !s->prop_theta || !s->nacc || !s->lmin || !s->sigma || !s->scale || !s->logz || !s->hacc ||
         !s->wmax || !s->wtot || !s->wsum || !s->wsq || !s->niter || !s->ncall || !s->done || !s->rng_round ||
-        (s->nder && !s->prop_der)) {
+        (s->nder && !s->prop_der) || (s->unif && (!s->center || !s->ell_r || s->walks != 1))) {
         ms_set_error("ms_ns_state is incomplete");
         return MS_EINVAL;
     }

@@ -421,9 +421,17 @@ class QueuedNestedSampler(object):
     """
 
     def __init__(self, likeobj, priorobj, nstars=1, nlive=150, walks=5, queue=32, dlogz=0.01, maxiter=100000,
-                 seed=0, star_plx=None, store_samples=False, dead_cap=20000, max_queue=64):
+                 seed=0, star_plx=None, store_samples=False, dead_cap=20000, max_queue=64, sample='rwalk'):
+        """sample: 'rwalk' (random walk of ``walks`` steps from a live point; the reference's setting,
+        demo/etc/samplerinfo.dat) or 'unif' (dynesty's uniform proposal: one independent draw from the bounding ellipsoid
+        of the live points per walker and round, rejected outside the unit cube; ``walks`` is ignored)."""
         if not likeobj.iso_bool:
             raise NotImplementedError('the queued sampler tracks the derived MIST block (isochrone fits)')
+        if sample not in ('rwalk', 'unif'):
+            raise ValueError("sample must be 'rwalk' or 'unif' (dynesty's other proposals are not implemented)")
+        self.sample = sample
+        if sample == 'unif':
+            walks = 1
         self.L, self.P = likeobj, priorobj
         self.eng = likeobj.engine
         self.dev = self.eng.device
@@ -484,7 +492,7 @@ class QueuedNestedSampler(object):
                  logz=torch.full((S,), -float('inf'), dtype=f64, device=dev), hacc=z(S),
                  wmax=torch.full((S,), -float('inf'), dtype=f64, device=dev), wtot=z(S), wsum=z(S, ncol), wsq=z(S, ncol),
                  niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), done=z(S, dt=torch.int32),
-                 rng_round=z(1, dt=torch.int64))
+                 rng_round=z(1, dt=torch.int64), center=z(S, nd), ell_r=z(S))
         if self.store:
             t['dead'] = z(S, self.dead_cap, ncol + _lib.MS_NS_TRAIL)
         orig = torch.arange(S, device=dev)
@@ -493,7 +501,7 @@ class QueuedNestedSampler(object):
         seed = C.c_uint64(self.seed * 7919 + 17)
         stream = lambda: eng._stream()
         per_star_keys = ('live_u', 'live_lp', 'live_row', 'lmin', 'sigma', 'scale', 'logz', 'hacc', 'wmax', 'wtot',
-                         'wsum', 'wsq', 'niter', 'ncall', 'done', 'dead')
+                         'wsum', 'wsq', 'niter', 'ncall', 'done', 'dead', 'center', 'ell_r')
         walker_keys = ('cur_u', 'cur_lp', 'cur_row', 'prop_u', 'prop_lp', 'prop_theta', 'prop_der', 'lnl', 'nacc')
 
         def harvest(mask):
@@ -513,8 +521,10 @@ class QueuedNestedSampler(object):
                 st = _lib.NsState()
                 st.S, st.K, st.Q, st.nd, st.nder, st.walks = Sc, K, Q, nd, nder, self.walks
                 st.maxiter, st.dead_cap, st.dlogz = self.maxiter, self.dead_cap if self.store else 0, self.dlogz
-                for name, _ in _lib.NsState._fields_[9:]:
-                    setattr(st, name, t[name].data_ptr() if name in t else None)
+                st.unif = 1 if self.sample == 'unif' else 0
+                for name, typ in _lib.NsState._fields_[9:]:
+                    if typ is C.c_void_p:
+                        setattr(st, name, t[name].data_ptr() if name in t else None)
                 walker_slot = orig.to(torch.int32).repeat_interleave(Q).contiguous()
 
                 def consume():

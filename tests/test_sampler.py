@@ -181,6 +181,46 @@ def test_queued_sampler_single_star_matches_monte_carlo():
     assert np.all(np.abs(res['std'][:, :nd].mean(0) / std_mc - 1.0) < 0.35)
 
 
+def test_queued_sampler_unif_proposal_matches_monte_carlo():
+    """dynesty's 'unif' proposal ("unif / rwalk"): independent draws from the bounding
+    ellipsoid of the live points, rejected outside the unit cube, one likelihood call per proposal.  Evidence and
+    posterior moments against brute-force prior Monte-Carlo and against the rwalk run of the same problem."""
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200.sampler import QueuedNestedSampler
+    fitargs, fitpars, runbools, priordict = _problem()
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    gen = torch.Generator(device=L.engine.device).manual_seed(7)
+    lw, ths = [], []
+    for _ in range(8):
+        u = torch.rand(1 << 18, L.ndim, generator=gen, device=L.engine.device, dtype=torch.float64)
+        th = P.priortrans_batch(u)
+        lnl, der, _ = L.lnlike_batch(th)
+        lw.append(P.lnprob_batch(th, lnl, der)); ths.append(th)
+    lw, ths = torch.cat(lw), torch.cat(ths)
+    logz_mc = float(torch.logsumexp(lw, 0) - np.log(len(lw)))
+    w = torch.exp(lw - lw.max()); w = w / w.sum()
+    mean_mc = (w[:, None] * ths).sum(0).cpu().numpy()
+    std_mc = torch.sqrt((w[:, None] * (ths - torch.as_tensor(mean_mc, device=ths.device)) ** 2).sum(0)).cpu().numpy()
+    nd = L.ndim
+    S = 8
+    L.engine.set_stars_phot(np.tile([[fitargs['obs_phot'][b][0] for b in L.engine.bands]], (S, 1)),
+                            np.tile([[fitargs['obs_phot'][b][1] for b in L.engine.bands]], (S, 1)))
+    with pytest.raises(ValueError):
+        QueuedNestedSampler(L, P, nstars=S, sample='slice')
+    res = QueuedNestedSampler(L, P, nstars=S, nlive=150, queue=32, dlogz=0.05, seed=11, sample='unif').run()
+    assert res['converged'].all()
+    err = np.maximum(res['logzerr'], 0.05)
+    assert np.all(np.abs(res['logz'] - logz_mc) < 5 * err + 0.2), (res['logz'], logz_mc)
+    m_ns = res['mean'][:, :nd].mean(0)
+    assert np.all(np.abs(m_ns - mean_mc) < 0.35 * std_mc + 1e-3), (m_ns, mean_mc, std_mc)
+    assert np.all(np.abs(res['std'][:, :nd].mean(0) / std_mc - 1.0) < 0.35)
+    # every proposal is one likelihood call; the sampling efficiency of the ellipsoid stays sane
+    eff = res['niter'] / np.maximum(res['ncall'], 1)
+    assert np.all(eff > 0.002) and np.all(eff <= 1.0), eff
+
+
 def test_catalog_sampler_accuracy_gate_at_benched_settings():
     """The configuration bench.py times (catalog of stars with per-star parallax priors, nlive 150, 4 queued
     walkers, dlogz 0.01) against brute-force quadrature of a subsample through the same kernels
