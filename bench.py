@@ -458,11 +458,12 @@ def main():
                 secs = float(tcat.item())
                 return dict(stars=nstars * world, seconds=secs, stars_per_hour=nstars * world / secs * 3600.0,
                             loglike_calls=float(ncalls.item()), loglike_calls_per_sec=float(ncalls.item()) / secs,
-                            nlive=150, walks=walks, dlogz=0.01, queue=4, converged_frac=float(rc['converged'].mean()),
+                            nlive=150, walks=walks, dlogz=0.01, queue=ns.Q, converged_frac=float(rc['converged'].mean()),
                             accuracy=acc)
 
             catalog = run_catalog(args.catalog_stars, GATE_WALKS)
-            catalog['sampler'] = ('lock-step static nested sampling, rwalk, 4 queued walkers per star (up to 64 for the stragglers), bookkeeping in CUDA '
+            catalog['sampler'] = ('lock-step static nested sampling, rwalk, %d queued walkers per star (sampler.auto_queue; up to 64 for the '
+                                  'stragglers), bookkeeping in CUDA ' % catalog['queue'] +
                                   'kernels, CUDA-graph replay')
             catalog['note'] = 'configs[4]: stars per GPU fixed (weak scaling); walks = shortest walk passing accuracy.gate'
             catalog['demo_settings'] = run_catalog(max(args.catalog_stars // 5, 64), 5)

@@ -406,6 +406,22 @@ class BatchedNestedSampler(object):
                     converged=out['converged'].cpu().numpy(), graph_replays=total, graph_captures=ncapt)
 
 
+def auto_queue(nstars):
+    """Walkers per star for a catalog of ``nstars`` stars on one GPU (``queue='auto'``).  A larger queue gives the
+    fused photometry kernel bigger batches and fewer bookkeeping rounds; its price is the fraction of queued candidates
+    overtaken by the rising threshold (about q / 2K of them for q walkers and K live points).  Measured on a B200 at
+    nlive 150, walks 25 (profiles/r02_catalog_sweep.jsonl): 20 000 stars: 5.3 / 3.2 / 2.8 / 3.1 s with 4 / 8 / 16 / 32
+    walkers; 100 000 stars: 13.4 / 12.9 s with 4 / 8.  So: about 3e5-8e5 walkers per step, and never more than 64."""
+    n = int(nstars)
+    if n > 150000:
+        return 4
+    if n > 40000:
+        return 8
+    if n > 5000:
+        return 16
+    return 32 if n > 500 else 64
+
+
 class QueuedNestedSampler(object):
     """Static nested sampling with a proposal queue, bookkeeping in CUDA kernels (csrc/sampler.cu).
 
@@ -424,7 +440,8 @@ class QueuedNestedSampler(object):
                  seed=0, star_plx=None, store_samples=False, dead_cap=20000, max_queue=64, sample='rwalk'):
         """sample: 'rwalk' (random walk of ``walks`` steps from a live point; the reference's setting,
         demo/etc/samplerinfo.dat) or 'unif' (dynesty's uniform proposal: one independent draw from the bounding ellipsoid
-        of the live points per walker and round, rejected outside the unit cube; ``walks`` is ignored)."""
+        of the live points per walker and round, rejected outside the unit cube; ``walks`` is ignored).
+        queue: walkers per star, or 'auto' (``auto_queue``: sized from the number of stars)."""
         if not likeobj.iso_bool:
             raise NotImplementedError('the queued sampler tracks the derived MIST block (isochrone fits)')
         if sample not in ('rwalk', 'unif'):
@@ -435,6 +452,8 @@ class QueuedNestedSampler(object):
         self.L, self.P = likeobj, priorobj
         self.eng = likeobj.engine
         self.dev = self.eng.device
+        if queue is None or queue == 'auto':
+            queue = auto_queue(nstars)
         self.S, self.K, self.Q, self.walks = int(nstars), int(nlive), int(queue), int(walks)
         self.nd, self.nder = likeobj.ndim, _lib.MS_NDERIVED
         self.dlogz, self.maxiter, self.seed = float(dlogz), int(maxiter), int(seed)

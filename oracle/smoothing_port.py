@@ -117,8 +117,8 @@ def smooth_lsf(wave, spec, outwave, sigma, pix_per_sigma=2.0):
     Gaussian of ``x_per_sigma`` (the median over pixels of dx / (d lambda / sigma)), and interpolated onto
     ``outwave``.  The reference's mask for this mode pads by 20 x 100 wavelength units (smoothing.py:
     125-132), i.e. keeps the whole model spectrum for any realistic window, so no masking is restated.
-    Not on the CUDA path yet; this restatement and its golden vectors pin the
-    semantics for it."""
+    Row a14 of SURVEY.md section 8; the CUDA path (``spec_lsf_kernel``) is tested against this restatement and
+    the reference's golden vectors."""
     wave = np.asarray(wave, dtype=np.float64)
     spec = np.asarray(spec, dtype=np.float64)
     sigma = np.asarray(sigma, dtype=np.float64)

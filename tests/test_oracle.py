@@ -46,7 +46,7 @@ def test_smoothing_port_matches_reference(g_smooth):
 
 def test_lsf_smoothing_port_matches_reference(g_smooth):
     """Row a14 (array Inst_R / wavelength-dependent LSF, smoothing.py:412-514): oracle restatement against the
-    reference's own output.  The CUDA path does not implement this mode yet; the vectors pin it for when it does."""
+    reference's own output (the CUDA form is checked against the same vectors in test_gpu_parity.py)."""
     w, f, ow = g_smooth['wave'], g_smooth['flux'], g_smooth['outwave']
     for (a, b), ref in zip(g_smooth['lsf_ab'], g_smooth['lsf_out']):
         out = smoothing_port.smooth_lsf(w, f, ow, a + b * (w - w[0]))

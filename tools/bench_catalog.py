@@ -23,7 +23,7 @@ NAMES = ['Teff', 'log(g)', '[Fe/H]', '[a/Fe]', 'Vrad', 'Vrot', 'Vmic', 'Inst_R',
 ON = {'Dist', 'Av', 'EEP', 'initial_[Fe/H]', 'initial_[a/Fe]', 'initial_Mass'}
 
 
-def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed, queued=4, sample='rwalk'):
+def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed, queued='auto', sample='rwalk'):
     """Synthetic catalog of S stars on this device (truths from the prior, observations from the
     model itself, Gaia-like parallaxes) registered with the engine, and a sampler over it.
     Returns (sampler, truth_theta)."""
@@ -53,7 +53,8 @@ def make_catalog_sampler(L, P, S, dev, nlive, walks, dlogz, maxiter, seed, queue
     L.engine.set_stars_phot(obs.cpu().numpy(), err.cpu().numpy())
     star_plx = torch.stack([plx_obs, plx_err], 1)
     if queued:       # bookkeeping in CUDA kernels (csrc/sampler.cu), proposal queue of `queued` walkers per star
-        ns = QueuedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, queue=queued, dlogz=dlogz,
+        ns = QueuedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, dlogz=dlogz,
+                                 queue='auto' if (queued == 'auto' or queued < 0) else queued,
                                  maxiter=maxiter, seed=5 + seed, star_plx=star_plx, sample=sample)
     else:            # torch-tensor bookkeeping (reference implementation of the same sampler)
         ns = BatchedNestedSampler(L, P, nstars=S, nlive=nlive, walks=walks, dlogz=dlogz, maxiter=maxiter,
@@ -176,8 +177,9 @@ def main():
                     help='shrink the working set (and re-capture the round graph) once this fraction of it is still running')
     ap.add_argument('--check-every', type=int, default=16)
     ap.add_argument('--bruteforce', type=int, default=0, help='check this many stars against brute-force quadrature')
-    ap.add_argument('--queued', type=int, default=4,
-                    help='walkers per star of the kernel-bookkeeping sampler; 0 = torch-tensor sampler')
+    ap.add_argument('--queued', type=int, default=-1,
+                    help='walkers per star of the kernel-bookkeeping sampler; -1 = sized from the number of stars '
+                         '(sampler.auto_queue); 0 = torch-tensor sampler')
     ap.add_argument('--sample', default='rwalk', choices=['rwalk', 'unif'],
                     help="proposal of the queued sampler: random walk of --walks steps, or dynesty's uniform draw from "
                          "the bounding ellipsoid of the live points (one likelihood call per proposal)")
@@ -239,7 +241,7 @@ def main():
             metric='stars_fitted_per_hour', value=args.stars / secs * 3600.0, unit='stars/hour', n_gpus=world,
             stars=args.stars, seconds=secs, nlive=args.nlive, walks=args.walks, dlogz=args.dlogz, sample=args.sample,
             iterations_median=float(np.median(res['niter'])), iterations_max=int(res['niter'].max()),
-            converged_frac=float(res['converged'].mean()), mode=('queued-%d' % args.queued) if args.queued else ('eager' if args.eager else 'cuda-graph'),
+            converged_frac=float(res['converged'].mean()), mode=('queued-%d' % ns.Q) if args.queued else ('eager' if args.eager else 'cuda-graph'),
             loglike_calls=float(calls.item()), loglike_evals_per_sec=float(calls.item()) / secs,
             calls_per_star=float(calls.item()) / args.stars,
             rank0_posterior_z_rms={n: float(np.sqrt(np.mean(zs[:, i] ** 2))) for i, n in enumerate(L.fitpars_i)},

@@ -3,7 +3,7 @@
 the same synthetic catalog and is checked against brute-force quadrature (tools/bench_catalog.py:accuracy_block).
 
     python tools/catalog_sweep.py --stars 20000 --settings rwalk:25:4 unif:1:16 unif:1:32
-Each setting is ``sample:walks:queue``; one JSON line per setting."""
+Each setting is ``sample:walks:queue[:stars]``; one JSON line per setting."""
 import argparse
 import json
 import os
@@ -42,8 +42,10 @@ def main():
     L = likelihood(fitargs, fitpars, runbools, precision='tc', device=0, verbose=False)
     P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
     for setting in args.settings:
-        sample, walks, queue = setting.split(':')
-        ns, th = bc.make_catalog_sampler(L, P, args.stars, dev, args.nlive, int(walks), args.dlogz, args.maxiter, 0,
+        parts = setting.split(':')
+        sample, walks, queue = parts[:3]
+        nstars = int(parts[3]) if len(parts) > 3 else args.stars
+        ns, th = bc.make_catalog_sampler(L, P, nstars, dev, args.nlive, int(walks), args.dlogz, args.maxiter, 0,
                                          queued=int(queue), sample=sample)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -52,8 +54,8 @@ def main():
         secs = time.perf_counter() - t0
         acc = bc.accuracy_block(L, P, ns, res, th, priordict, args.bruteforce) if args.bruteforce else None
         calls = float(res['ncall'].sum())
-        print(json.dumps(dict(setting=setting, stars=args.stars, seconds=secs, stars_per_hour=args.stars / secs * 3600.0,
-                              calls_per_star=calls / args.stars, calls_per_iteration=calls / float(res['niter'].sum()),
+        print(json.dumps(dict(setting=setting, stars=nstars, seconds=secs, stars_per_hour=nstars / secs * 3600.0,
+                              calls_per_star=calls / nstars, calls_per_iteration=calls / float(res['niter'].sum()),
                               loglike_evals_per_sec=calls / secs, rounds=int(res['rounds']),
                               iterations_median=float(np.median(res['niter'])),
                               converged_frac=float(res['converged'].mean()), vs_bruteforce=acc)), flush=True)
