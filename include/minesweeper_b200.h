@@ -276,6 +276,16 @@ typedef struct {
 /* step = walk step inside the current round (0 .. walks-1); the round number is read from rng_round */
 int ms_ns_propose(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t step, void *stream);
 int ms_ns_accept(ms_ctx *ctx, const ms_ns_state *s, void *stream);
+/* Fused forms of a walk step (bit-identical to the separate calls, one launch each):
+ * ms_ns_propose_transform = ms_ns_propose + ms_prior_transform(prop_u -> prop_theta) with the column table `cols[nd]`;
+ * ms_ns_lnprob_accept = ms_lnprob_batch_adv(prop_theta, prop_der, lnL -> prop_lp) + ms_ns_accept, lnL[S*Q] being the
+ * ln likelihood of the proposals (ms_lnlike_batch on prop_theta); the other arguments as in ms_lnprob_batch_adv.
+ * Both write through the `const` proposal pointers of the state (prop_theta, prop_lp). */
+int ms_ns_propose_transform(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t step,
+                            const ms_prior_col *cols, void *stream);
+int ms_ns_lnprob_accept(ms_ctx *ctx, const ms_ns_state *s, const ms_flags *flags, const int32_t *colmap,
+                        const double *fixed, const ms_prior_term *terms, int nterms, int imf, const double *lnL,
+                        const int32_t *star_slot, const double *star_plx, const ms_adv_prior *adv, void *stream);
 /* consumes the queue, prepares the next round and advances rng_round */
 int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, void *stream);
 /* adds the remaining live points of every star with done == 1 and marks it 2 */

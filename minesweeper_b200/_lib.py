@@ -133,6 +133,11 @@ PROTOTYPES = {
     'ms_set_stars_phot': (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp, c_dp, C.c_int]),
     'ms_ns_propose': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_uint64, C.c_void_p]),
     'ms_ns_accept': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
+    'ms_ns_propose_transform': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_uint64, C.POINTER(PriorCol),
+                                          C.c_void_p]),
+    'ms_ns_lnprob_accept': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.POINTER(Flags), c_ip, c_dp,
+                                      C.POINTER(PriorTerm), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(AdvPrior), C.c_void_p]),
     'ms_ns_consume': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_void_p]),
     'ms_ns_finalize': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
     'ms_reserve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),

@@ -14,7 +14,10 @@
 //   ns_consume_kernel   worst point, ln Z / H / posterior moments, replacement, stopping rule,
 //                       live-point spread, step-scale adaptation, restart points of the next round
 //   ns_finalize_kernel  contribution of the remaining live points
-#include "common.cuh"
+// Fused forms used by the catalog sampler (one launch each instead of two; same arithmetic, bit-identical results):
+//   ns_propose_kernel<true>      propose + prior transform (theta leaves the kernel that drew the step)
+//   ns_lnprob_accept_kernel      lnL + ln prior (lnprobfn) + accept
+#include "prior_dev.cuh"
 
 
 namespace {
@@ -34,7 +37,11 @@ __device__ __forceinline__ uint64_t ns_mix(uint64_t seed, uint64_t stream, uint6
     return z ^ (z >> 31);
 }
 
-__global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
+// FUSE: also apply the prior transform to every coordinate and write theta (prop_theta) -- what
+// prior_transform_kernel would do in a second pass over prop_u.
+template <bool FUSE>
+__global__ void ns_propose_kernel(ms_ns_state s, TransformArgs ta, uint64_t seed, uint64_t step) {
+    double *theta_out = const_cast<double *>(s.prop_theta);
     const int64_t n = (int64_t)s.S * s.Q;
     for (int64_t wk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; wk < n; wk += (int64_t)gridDim.x * blockDim.x) {
         const int star = (int)(wk / s.Q);
@@ -74,7 +81,11 @@ __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
                 uv[d] = mu[d] + rad * step;
                 inside = inside && uv[d] > 0.0 && uv[d] < 1.0;
             }
-            for (int d = 0; d < s.nd; ++d) s.prop_u[wk * s.nd + d] = inside ? uv[d] : ms_nan();
+            for (int d = 0; d < s.nd; ++d) {
+                const double v = inside ? uv[d] : ms_nan();
+                s.prop_u[wk * s.nd + d] = v;
+                if (FUSE) theta_out[wk * s.nd + d] = prior_transform_value(ta, d, v);
+            }
             continue;
         }
         for (int d = 0; d < s.nd; ++d) {
@@ -85,6 +96,7 @@ __global__ void ns_propose_kernel(ms_ns_state s, uint64_t seed, uint64_t step) {
             if (v < 0.0) v += 2.0;
             if (v > 1.0) v = 2.0 - v;
             s.prop_u[wk * s.nd + d] = v;
+            if (FUSE) theta_out[wk * s.nd + d] = prior_transform_value(ta, d, v);
         }
     }
 }
@@ -109,6 +121,43 @@ __global__ void ns_accept_kernel(ms_ns_state s) {
             } else {
                 s.cur_lp[wk] = lp;
                 s.nacc[wk] += 1;
+            }
+        }
+    }
+}
+
+// lnprob + accept in one pass: a lane per walker evaluates lnprobfn (lnL + ln prior with its -inf short circuits, the
+// arithmetic of lnprior_kernel), then each half warp copies the records of its accepted walkers cooperatively, a lane per
+// element, exactly as ns_accept_kernel does.  a.out (= prop_lp) is still written: ns_consume never reads it, the tests do.
+__global__ void __launch_bounds__(256) ns_lnprob_accept_kernel(ms_ns_state s, LnPriorArgs a) {
+    const int nd = s.nd, ncol = s.nd + s.nder, w = nd + ncol + 1;
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    const int64_t n = (int64_t)s.S * s.Q;
+    const int64_t wpb = blockDim.x >> 5;
+    for (int64_t base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 32; base < n; base += (int64_t)gridDim.x * wpb * 32) {
+        const int64_t mine = base + lane;
+        double lp = -ms_inf();
+        bool ok = false;
+        if (mine < n) {
+            lp = lnprob_value(a, mine);
+            a.out[mine] = lp;
+            ok = lp > s.lmin[mine / s.Q];
+        }
+        for (int j = 0; j < 16; ++j) {                      // the j-th walker of each half warp
+            const int src = half * 16 + j;
+            const bool okj = __shfl_sync(0xffffffffu, ok ? 1 : 0, src) != 0;
+            const double lpj = __shfl_sync(0xffffffffu, lp, src);
+            if (!okj) continue;
+            const int64_t wk = base + src;
+            for (int c = hl; c < w; c += 16) {
+                if (c < ncol) {
+                    s.cur_row[wk * ncol + c] = c < nd ? s.prop_theta[wk * nd + c] : s.prop_der[wk * s.nder + (c - nd)];
+                } else if (c < ncol + nd) {
+                    s.cur_u[wk * nd + (c - ncol)] = s.prop_u[wk * nd + (c - ncol)];
+                } else {
+                    s.cur_lp[wk] = lpj;
+                    s.nacc[wk] += 1;
+                }
             }
         }
     }
@@ -359,7 +408,45 @@ extern "C" int ms_ns_propose(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, u
     MS_CUDA(cudaSetDevice(ctx->device));
     const int64_t n = (int64_t)s->S * s->Q;
     int64_t blocks = (n + 127) / 128, cap = (int64_t)ctx->sm_count * 16;
-    ns_propose_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(*s, seed, step);
+    TransformArgs none;
+    memset(&none, 0, sizeof(none));
+    ns_propose_kernel<false><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(*s, none, seed, step);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_ns_propose_transform(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, uint64_t step,
+                                       const ms_prior_col *cols, void *stream) {
+    int rc = check_state(s);
+    if (rc || !ctx) return rc ? rc : MS_EINVAL;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    TransformArgs ta;
+    rc = fill_transform_args(ctx, s->nd, cols, ta);
+    if (rc) return rc;
+    const int64_t n = (int64_t)s->S * s->Q;
+    int64_t blocks = (n + 127) / 128, cap = (int64_t)ctx->sm_count * 16;
+    ns_propose_kernel<true><<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, (cudaStream_t)stream>>>(*s, ta, seed, step);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_ns_lnprob_accept(ms_ctx *ctx, const ms_ns_state *s, const ms_flags *flags, const int32_t *colmap,
+                                   const double *fixed, const ms_prior_term *terms, int nterms, int imf,
+                                   const double *lnL, const int32_t *star_slot, const double *star_plx,
+                                   const ms_adv_prior *adv, void *stream) {
+    int rc = check_state(s);
+    if (rc || !ctx) return rc ? rc : MS_EINVAL;
+    if (!lnL) { ms_set_error("ms_ns_lnprob_accept needs the ln likelihood of the proposals"); return MS_EINVAL; }
+    MS_CUDA(cudaSetDevice(ctx->device));
+    LnPriorArgs a;
+    rc = fill_lnprior_args(flags, s->prop_theta, s->nd, colmap, fixed, s->nder ? s->prop_der : nullptr, terms, nterms, imf,
+                           lnL, const_cast<double *>(s->prop_lp), star_slot, star_plx, adv, a);
+    if (rc) return rc;
+    const int64_t n = (int64_t)s->S * s->Q;                              // a lane per walker, 256 walkers per CTA
+    int64_t blocks = (n + 255) / 256, cap = (int64_t)ctx->sm_count * 8;
+    ns_lnprob_accept_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(*s, a);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

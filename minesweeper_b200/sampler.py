@@ -437,11 +437,14 @@ class QueuedNestedSampler(object):
     """
 
     def __init__(self, likeobj, priorobj, nstars=1, nlive=150, walks=5, queue=32, dlogz=0.01, maxiter=100000,
-                 seed=0, star_plx=None, store_samples=False, dead_cap=20000, max_queue=64, sample='rwalk'):
+                 seed=0, star_plx=None, store_samples=False, dead_cap=20000, max_queue=64, sample='rwalk', fused=True):
         """sample: 'rwalk' (random walk of ``walks`` steps from a live point; the reference's setting,
         demo/etc/samplerinfo.dat) or 'unif' (dynesty's uniform proposal: one independent draw from the bounding ellipsoid
         of the live points per walker and round, rejected outside the unit cube; ``walks`` is ignored).
-        queue: walkers per star, or 'auto' (``auto_queue``: sized from the number of stars)."""
+        queue: walkers per star, or 'auto' (``auto_queue``: sized from the number of stars).
+        fused: a walk step is three launches (propose + prior transform, likelihood, ln prior + accept) instead of five;
+        same arithmetic, same random numbers (``fused=False`` keeps the separate kernels; the tests compare the two)."""
+        self.fused = bool(fused)
         if not likeobj.iso_bool:
             raise NotImplementedError('the queued sampler tracks the derived MIST block (isochrone fits)')
         if sample not in ('rwalk', 'unif'):
@@ -549,7 +552,27 @@ class QueuedNestedSampler(object):
                 def consume():
                     _lib.check(lib.ms_ns_consume(eng._ctx, C.byref(st), seed, stream()))
 
+                P = self.P
+                slot_plx = walker_slot if self.star_plx is not None else None
+
+                def round_fused():
+                    for step in range(self.walks):
+                        _lib.check(lib.ms_ns_propose_transform(eng._ctx, C.byref(st), seed, C.c_uint64(step), P._cols,
+                                                               stream()))
+                        eng.lnlike_batch(t['prop_theta'], self.L._colmap, self.L._fixed, self.L._flags,
+                                         star_slot=walker_slot if per_star else None, want_derived=True,
+                                         out=t['lnl'], derived_out=t['prop_der'])
+                        _lib.check(lib.ms_ns_lnprob_accept(
+                            eng._ctx, C.byref(st), C.byref(P._flags), P._colmap.ctypes.data_as(_lib.c_ip),
+                            P._fixed.ctypes.data_as(_lib.c_dp), P._terms_c, P._nterms, int(P.imf_bool), t['lnl'].data_ptr(),
+                            slot_plx.data_ptr() if slot_plx is not None else None,
+                            self.star_plx.data_ptr() if self.star_plx is not None else None,
+                            C.byref(P._adv) if P._adv is not None else None, stream()))
+                    consume()
+
                 def round_():
+                    if self.fused:
+                        return round_fused()
                     for step in range(self.walks):
                         _lib.check(lib.ms_ns_propose(eng._ctx, C.byref(st), seed, C.c_uint64(step), stream()))
                         self.P.priortrans_batch(t['prop_u'], out=t['prop_theta'])

@@ -258,3 +258,99 @@ def test_catalog_sampler_accuracy_gate_at_benched_settings():
     assert np.median(list(demo['std_ratio_median'].values())) < np.median(list(good['std_ratio_median'].values())) + 0.02
     # the exact (brute-force) posteriors are calibrated against the truths -- the ground truth itself is sound
     assert all(0.6 < v < 1.8 for v in good['truth_z_rms_bruteforce'].values()), good['truth_z_rms_bruteforce']
+
+
+def test_fused_walk_step_matches_the_separate_kernels():
+    """ms_ns_propose_transform / ms_ns_lnprob_accept (three launches per walk step) against ms_ns_propose +
+    ms_prior_transform + ms_lnprob_batch_adv + ms_ns_accept (five): one step on identical state gives identical
+    proposals, parameters, ln probabilities and walker records; whole runs from the same seed agree."""
+    import ctypes as C
+    from minesweeper_b200 import _lib
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.prior import prior
+    from minesweeper_b200.sampler import QueuedNestedSampler
+    fitargs, fitpars, runbools, priordict = _problem()
+    L = likelihood(fitargs, fitpars, runbools, precision='tc', verbose=False)
+    P = prior(fitargs, priordict, fitpars, runbools, likeobj=L)
+    eng, lib, dev = L.engine, L.engine.lib, L.engine.device
+    S, K, Q, nd, nder = 37, 20, 5, L.ndim, _lib.MS_NDERIVED
+    ncol = nd + nder
+    eng.set_stars_phot(np.tile([[fitargs['obs_phot'][b][0] for b in eng.bands]], (S, 1)),
+                       np.tile([[fitargs['obs_phot'][b][1] for b in eng.bands]], (S, 1)))
+    gen = torch.Generator(device=dev).manual_seed(5)
+    f64 = torch.float64
+    r = lambda *sh: torch.rand(*sh, generator=gen, device=dev, dtype=f64)
+    z = lambda *sh, dt=f64: torch.zeros(*sh, dtype=dt, device=dev)
+    plx = torch.stack([1000.0 / 14.0 + r(S), 3.0 + r(S)], 1).contiguous()
+    slot = torch.arange(S, device=dev, dtype=torch.int32).repeat_interleave(Q).contiguous()
+
+    def state():
+        g2 = torch.Generator(device=dev).manual_seed(9)
+        rr = lambda *sh: torch.rand(*sh, generator=g2, device=dev, dtype=f64)
+        sig = torch.zeros(S, nd, nd, dtype=f64, device=dev)
+        sig[:, torch.arange(nd), torch.arange(nd)] = 0.02
+        sig[:, 1, 0] = 0.01
+        t = dict(live_u=rr(S * K, nd), live_lp=rr(S * K), live_row=rr(S * K, ncol), cur_u=0.3 + 0.4 * rr(S * Q, nd),
+                 cur_lp=z(S * Q), cur_row=z(S * Q, ncol), prop_u=z(S * Q, nd), prop_lp=z(S * Q), prop_theta=z(S * Q, nd),
+                 prop_der=z(S * Q, nder), lnl=z(S * Q), nacc=z(S * Q, dt=torch.int32), lmin=z(S), sigma=sig.reshape(S, nd * nd).contiguous(),
+                 scale=torch.ones(S, dtype=f64, device=dev), logz=z(S), hacc=z(S), wmax=z(S), wtot=z(S), wsum=z(S, ncol),
+                 wsq=z(S, ncol), niter=z(S, dt=torch.int64), ncall=z(S, dt=torch.int64), done=z(S, dt=torch.int32),
+                 rng_round=z(1, dt=torch.int64) + 3, center=z(S, nd), ell_r=z(S))
+        st = _lib.NsState()
+        st.S, st.K, st.Q, st.nd, st.nder, st.walks = S, K, Q, nd, nder, 4
+        st.maxiter, st.dead_cap, st.dlogz, st.unif = 1000, 0, 0.01, 0
+        for name, typ in _lib.NsState._fields_[9:]:
+            if typ is C.c_void_p:
+                setattr(st, name, t[name].data_ptr() if name in t else None)
+        return t, st
+
+    seed = C.c_uint64(1234)
+    stream = eng._stream()
+
+    def like(t):
+        eng.lnlike_batch(t['prop_theta'], L._colmap, L._fixed, L._flags, star_slot=slot, want_derived=True,
+                         out=t['lnl'], derived_out=t['prop_der'])
+
+    with torch.cuda.device(dev):
+        ta, sa = state()
+        tb, sb = state()
+        for step in range(2):
+            # separate kernels
+            _lib.check(lib.ms_ns_propose(eng._ctx, C.byref(sa), seed, C.c_uint64(step), stream))
+            P.priortrans_batch(ta['prop_u'], out=ta['prop_theta'])
+            like(ta)
+            if step == 0:                                      # threshold: about half of the proposals pass
+                fin = ta['lnl'][torch.isfinite(ta['lnl'])]
+                assert len(fin) > 10
+                pre = P.lnprob_batch(ta['prop_theta'], ta['lnl'], ta['prop_der'], star_slot=slot, star_plx=plx)
+                thr = pre[torch.isfinite(pre)].median()
+                ta['lmin'].fill_(float(thr)); tb['lmin'].fill_(float(thr))
+            P.lnprob_batch(ta['prop_theta'], ta['lnl'], ta['prop_der'], out=ta['prop_lp'], star_slot=slot, star_plx=plx)
+            _lib.check(lib.ms_ns_accept(eng._ctx, C.byref(sa), stream))
+            # fused
+            _lib.check(lib.ms_ns_propose_transform(eng._ctx, C.byref(sb), seed, C.c_uint64(step), P._cols, stream))
+            like(tb)
+            _lib.check(lib.ms_ns_lnprob_accept(
+                eng._ctx, C.byref(sb), C.byref(P._flags), P._colmap.ctypes.data_as(_lib.c_ip),
+                P._fixed.ctypes.data_as(_lib.c_dp), P._terms_c, P._nterms, int(P.imf_bool), tb['lnl'].data_ptr(),
+                slot.data_ptr(), plx.data_ptr(), C.byref(P._adv) if P._adv is not None else None, stream))
+            torch.cuda.synchronize()
+            assert torch.equal(ta['prop_u'], tb['prop_u'])
+            assert torch.allclose(ta['prop_theta'], tb['prop_theta'], rtol=1e-15, atol=0, equal_nan=True)
+            assert torch.allclose(ta['prop_lp'], tb['prop_lp'], rtol=1e-13, atol=1e-12, equal_nan=True)
+            nacc = int(ta['nacc'].sum())
+            assert 0 < nacc < (step + 1) * S * Q
+            assert torch.equal(ta['nacc'], tb['nacc'])
+            assert torch.equal(ta['cur_u'], tb['cur_u'])
+            assert torch.allclose(ta['cur_row'], tb['cur_row'], rtol=1e-15, atol=0)
+            assert torch.allclose(ta['cur_lp'], tb['cur_lp'], rtol=1e-13, atol=1e-12)
+    # whole runs from the same seed
+    kw = dict(nstars=S, nlive=60, walks=6, queue=4, dlogz=0.1, seed=2, star_plx=plx)
+    ra = QueuedNestedSampler(L, P, fused=False, **kw).run()
+    rb = QueuedNestedSampler(L, P, fused=True, **kw).run()
+    assert ra['converged'].all() and rb['converged'].all()
+    if np.array_equal(ra['niter'], rb['niter']):               # same trajectories (the usual case)
+        np.testing.assert_allclose(ra['logz'], rb['logz'], rtol=0, atol=1e-8)
+    else:                                                      # a last-bit difference flipped an acceptance somewhere
+        err = np.maximum(np.hypot(ra['logzerr'], rb['logzerr']), 0.1)
+        assert np.all(np.abs(ra['logz'] - rb['logz']) < 5 * err)
