@@ -553,10 +553,25 @@ def main():
         in_ms, in_n = prof2['interp']
         fused = prof['interp'][1] == 0 and args.precision in ('tc', 'tc16')
         achieved = flop_pt * B * ph_n / (ph_ms * 1e-3) / 1e12 if ph_ms > 0 else 0.0
-        traffic = None
+        # DRAM bytes per launch from the last `ncu --set full` capture (tools/traffic_from_ncu.py), with a check that the
+        # kernel's sources are still the ones that were captured
+        traffic, traffic_capture = None, None
         tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(('phot_fused_' if fused else 'phot_') + args.precision)
+            tj = json.load(open(tp))
+            tkey = ('phot_fused_' if fused else 'phot_') + args.precision
+            traffic = tj.get(tkey)
+            cap = tj.get(tkey + '_capture')
+            if cap:
+                import hashlib
+                hsh = hashlib.sha256()
+                try:
+                    for f in cap['sources']:
+                        hsh.update(open(os.path.join(ROOT, 'minesweeper_b200', 'csrc', f), 'rb').read())
+                    same = hsh.hexdigest() == cap['sources_sha256']
+                except OSError:
+                    same = None
+                traffic_capture = dict(report=cap['report'], kernel_sources_unchanged_since_capture=same)
         tbl_b = 4 if args.precision != 'f64' else 8
         # theta row in, 16 corners x 9 columns gathered, 20-double parameter block out (fused kernel)
         interp_bytes = theta_np.shape[1] * 8 + 16 * 9 * tbl_b + 20 * 8
@@ -577,6 +592,7 @@ def main():
             roofline=dict(bound='tensor', kernel='phot_mlp_tc (MIST interpolation fused into its prologue)' if fused
                           else 'phot_mlp', achieved=achieved, peak=pk['tf_burst'],
                           unit='TFLOP/s', frac=achieved / pk['tf_burst'], traffic=traffic,
+                          traffic_capture=traffic_capture,
                           peak_source=pk['src'], ms_per_launch=ph_ms / max(ph_n, 1),
                           share_of_step=ph_ms / ms if ms else None),
             roofline_interp=dict(bound='hbm', kernel='mist_interp (on its own: two-kernel sequence, 5 extra steps)',

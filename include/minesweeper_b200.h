@@ -290,6 +290,10 @@ int ms_ns_lnprob_accept(ms_ctx *ctx, const ms_ns_state *s, const ms_flags *flags
 int ms_ns_consume(ms_ctx *ctx, const ms_ns_state *s, uint64_t seed, void *stream);
 /* adds the remaining live points of every star with done == 1 and marks it 2 */
 int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream);
+/* sigma[S][nd][nd] = lower Cholesky factor of the covariance of the point sets U[S][K][nd] (device f64): the proposal
+ * shape dynesty's rwalk takes from the bounding ellipsoid; a covariance that is not positive definite gives the
+ * diagonal of standard deviations.  The same code maintains ms_ns_state.sigma inside ms_ns_consume. */
+int ms_ns_spread(ms_ctx *ctx, const double *U, int S, int K, int nd, double *sigma, void *stream);
 
 /* In the tensor-core modes a photometry-only isochrone batch (likelihood.lnlikefn with runbools =
  * [spec off, phot on], reference likelihood.py:92-181) runs as ONE kernel: the MIST interpolation of

@@ -140,6 +140,7 @@ PROTOTYPES = {
                                       C.POINTER(AdvPrior), C.c_void_p]),
     'ms_ns_consume': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_uint64, C.c_void_p]),
     'ms_ns_finalize': (C.c_int, [C.c_void_p, C.POINTER(NsState), C.c_void_p]),
+    'ms_ns_spread': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'ms_reserve': (C.c_int, [C.c_void_p, C.c_int64, C.c_int]),
     'ms_launch_count': (C.c_int64, [C.c_void_p]),
     'ms_set_fusion': (C.c_int, [C.c_void_p, C.c_int]),

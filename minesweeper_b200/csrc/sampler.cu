@@ -224,6 +224,48 @@ __device__ __forceinline__ void ns_minmax(const double *lp, int K, int lane, dou
     vmin = mn; imin = im; vmax = mx;
 }
 
+// Mean, covariance and Cholesky factor (lower triangle, row-major [nd][nd]) of the K points lu[K][nd], by one warp:
+// lane pe owns covariance entry pe (nd * nd <= 32 in practice, otherwise the lanes stride); a covariance that is not
+// positive definite falls back to the diagonal of standard deviations.  mean[nd], diag[nd], cov[nd*nd] are the warp's
+// scratch (shared memory); on return cov holds the factor that was written to `out`.
+__device__ __forceinline__ void ns_spread(const double *lu, int K, int nd, int lane, double *mean, double *diag,
+                                          double *cov, double *out) {
+    for (int d = lane; d < nd; d += 32) {
+        double a = 0.0;
+        for (int k = 0; k < K; ++k) a += lu[k * nd + d];
+        mean[d] = a / K;
+    }
+    __syncwarp();
+    for (int pe = lane; pe < nd * nd; pe += 32) {
+        const int d = pe / nd, e = pe - d * nd;
+        if (e > d) { cov[pe] = 0.0; continue; }
+        double a = 0.0;
+        const double md = mean[d], me = mean[e];
+        for (int k = 0; k < K; ++k) a += (lu[k * nd + d] - md) * (lu[k * nd + e] - me);
+        cov[pe] = a / (K - 1);
+    }
+    __syncwarp();
+    for (int d = lane; d < nd; d += 32) diag[d] = cov[d * nd + d];      // kept for the degenerate fallback
+    __syncwarp();
+    if (lane == 0) {                                     // in-place Cholesky, row by row, lower triangle
+        bool ok = true;
+        for (int i = 0; i < nd && ok; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double a = cov[i * nd + j] + (i == j ? 1e-14 : 0.0);
+                for (int k = 0; k < j; ++k) a -= cov[i * nd + k] * cov[j * nd + k];
+                if (i == j) { if (!(a > 0.0)) { ok = false; break; } cov[i * nd + i] = sqrt(a); }
+                else cov[i * nd + j] = a / cov[j * nd + j];
+            }
+        for (int i = 0; i < nd; ++i)
+            for (int j = 0; j < nd; ++j) {
+                const double v = ok ? (j <= i ? cov[i * nd + j] : 0.0)
+                                    : (i == j ? sqrt(fmax(diag[i], 1e-24)) : 0.0);    // degenerate: diagonal
+                out[i * nd + j] = v;
+                cov[i * nd + j] = v;                     // the factor actually used, for the radius below
+            }
+    }
+}
+
 __global__ void __launch_bounds__(32 * NS_WARPS, 8)
 ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
     extern __shared__ double sm_all[];
@@ -298,41 +340,7 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
     const uint64_t cov_every = (uint64_t)((Q >= 16 || s.unif) ? 1 : 16 / Q);
     if (round % cov_every == 0) {
         const double *lu = s.live_u + lbase * nd;
-        for (int d = lane; d < nd; d += 32) {
-            double a = 0.0;
-            for (int k = 0; k < K; ++k) a += lu[k * nd + d];
-            mean[d] = a / K;
-        }
-        __syncwarp();
-        for (int pe = lane; pe < nd * nd; pe += 32) {
-            const int d = pe / nd, e = pe - d * nd;
-            if (e > d) { cov[pe] = 0.0; continue; }
-            double a = 0.0;
-            const double md = mean[d], me = mean[e];
-            for (int k = 0; k < K; ++k) a += (lu[k * nd + d] - md) * (lu[k * nd + e] - me);
-            cov[pe] = a / (K - 1);
-        }
-        __syncwarp();
-        for (int d = lane; d < nd; d += 32) diag[d] = cov[d * nd + d];      // kept for the degenerate fallback
-        __syncwarp();
-        if (lane == 0) {                                     // in-place Cholesky, row by row, lower triangle
-            bool ok = true;
-            for (int i = 0; i < nd && ok; ++i)
-                for (int j = 0; j <= i; ++j) {
-                    double a = cov[i * nd + j] + (i == j ? 1e-14 : 0.0);
-                    for (int k = 0; k < j; ++k) a -= cov[i * nd + k] * cov[j * nd + k];
-                    if (i == j) { if (!(a > 0.0)) { ok = false; break; } cov[i * nd + i] = sqrt(a); }
-                    else cov[i * nd + j] = a / cov[j * nd + j];
-                }
-            double *out = s.sigma + (int64_t)star * nd * nd;
-            for (int i = 0; i < nd; ++i)
-                for (int j = 0; j < nd; ++j) {
-                    const double v = ok ? (j <= i ? cov[i * nd + j] : 0.0)
-                                        : (i == j ? sqrt(fmax(diag[i], 1e-24)) : 0.0);    // degenerate: diagonal
-                    out[i * nd + j] = v;
-                    cov[i * nd + j] = v;                     // the factor actually used, for the radius below
-                }
-        }
+        ns_spread(lu, K, nd, lane, mean, diag, cov, s.sigma + (int64_t)star * nd * nd);
         __syncwarp();
         if (s.unif) {
             // bounding ellipsoid of the live points in the metric of the factor: r^2 = max_k |L^-1 (u_k - mean)|^2,
@@ -368,6 +376,17 @@ ns_consume_kernel(ms_ns_state s, uint64_t seed, double log_shrink) {
         for (int d = lane; d < nd; d += 32) s.cur_u[wk * nd + d] = s.live_u[(lbase + j) * nd + d];
         for (int c = lane; c < ncol; c += 32) s.cur_row[wk * ncol + c] = s.live_row[(lbase + j) * ncol + c];
     }
+}
+
+// Cholesky factors of the covariances of S point sets U[S][K][nd] (the proposal shape of the torch-tensor sampler)
+__global__ void __launch_bounds__(32 * NS_WARPS)
+ns_spread_kernel(const double *__restrict__ U, int S, int K, int nd, double *__restrict__ sigma) {
+    extern __shared__ double sm_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int star = blockIdx.x * NS_WARPS + wib;
+    if (star >= S) return;
+    double *mean = sm_all + wib * (2 * nd + nd * nd), *diag = mean + nd, *cov = diag + nd;
+    ns_spread(U + (int64_t)star * K * nd, K, nd, lane, mean, diag, cov, sigma + (int64_t)star * nd * nd);
 }
 
 __global__ void ns_tick_kernel(uint64_t *counter) { *counter += 1; }
@@ -482,6 +501,17 @@ extern "C" int ms_ns_finalize(ms_ctx *ctx, const ms_ns_state *s, void *stream) {
     if (rc || !ctx) return rc ? rc : MS_EINVAL;
     MS_CUDA(cudaSetDevice(ctx->device));
     ns_finalize_kernel<<<(unsigned)((s->S + NS_WARPS - 1) / NS_WARPS), 32 * NS_WARPS, 0, (cudaStream_t)stream>>>(*s);
+    ctx->launches++;
+    MS_CUDA(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_ns_spread(ms_ctx *ctx, const double *U, int S, int K, int nd, double *sigma, void *stream) {
+    if (ctx && S == 0) return MS_OK;
+    if (!ctx || !U || !sigma || S < 0 || K < 2 || nd < 1 || nd > MS_NPARAM) { ms_set_error("bad arguments"); return MS_EINVAL; }
+    MS_CUDA(cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)NS_WARPS * (2 * nd + nd * nd) * sizeof(double);
+    ns_spread_kernel<<<(unsigned)((S + NS_WARPS - 1) / NS_WARPS), 32 * NS_WARPS, smem, (cudaStream_t)stream>>>(U, S, K, nd, sigma);
     ctx->launches++;
     MS_CUDA(cudaGetLastError());
     return MS_OK;

@@ -28,15 +28,16 @@ import torch
 from . import _lib
 
 
-def _chol_cov(U):
-    """Cholesky factors [S, nd, nd] of the covariance of the live points U[S, K, nd] (the shape of
-    the random-walk proposal, as dynesty's rwalk uses the bounding ellipsoid)."""
-    d = U - U.mean(dim=1, keepdim=True)
-    cov = torch.matmul(d.transpose(1, 2), d) / (U.shape[1] - 1)
-    eye = torch.eye(U.shape[2], dtype=U.dtype, device=U.device)
-    L, info = torch.linalg.cholesky_ex(cov + 1e-14 * eye)
-    diag = torch.diag_embed(torch.sqrt(torch.diagonal(cov, dim1=1, dim2=2).clamp_min(1e-24)))
-    return torch.where((info == 0)[:, None, None], L, diag)
+def _chol_cov(eng, U):
+    """Cholesky factors [S, nd, nd] of the covariance of the live points U[S, K, nd] (the shape of the random-walk
+    proposal, as dynesty's rwalk uses the bounding ellipsoid): ``ms_ns_spread``, the kernel code that also maintains
+    the queued sampler's proposal shape (no cuBLAS / cuSOLVER call on the sampler's path)."""
+    U = U.contiguous()
+    S, K, nd = U.shape
+    sig = torch.empty((S, nd, nd), dtype=torch.float64, device=U.device)
+    with torch.cuda.device(eng.device):
+        _lib.check(eng.lib.ms_ns_spread(eng._ctx, U.data_ptr(), S, K, nd, sig.data_ptr(), eng._stream()))
+    return sig
 
 
 class BatchedNestedSampler(object):
@@ -155,12 +156,12 @@ class BatchedNestedSampler(object):
             lcur = LP[act, j].clone()
             thcur = TH[act, j].clone()
             dcur = DER[act, j].clone() if DER is not None else None
-            sig = _chol_cov(U[act]) * scale[act, None, None]
+            sig = _chol_cov(self.eng, U[act]) * scale[act, None, None]
             nacc = torch.zeros(A, dtype=torch.int64, device=dev)
             steps = 0
             while True:
                 for _ in range(self.walks):
-                    prop = ucur + torch.bmm(sig, self._randn(A, nd, 1)).squeeze(2)
+                    prop = ucur + (sig * self._randn(A, 1, nd)).sum(2)       # L z, element-wise (6 x 6: no library GEMM)
                     prop = torch.remainder(prop, 2.0)                      # reflect into [0, 1]
                     prop = torch.where(prop > 1.0, 2.0 - prop, prop)
                     lpn, thn, dern = self._lnprob(prop, act)
@@ -339,10 +340,10 @@ class BatchedNestedSampler(object):
                 j = j + (j >= w).to(j.dtype)
                 ucur, lcur, thcur = U_[star, j], LP[star, j], TH[star, j]
                 dcur = DER[star, j] if DER is not None else None
-                sig = _chol_cov(U_) * st['scale'][:, None, None]
+                sig = _chol_cov(self.eng, U_) * st['scale'][:, None, None]
                 nacc = torch.zeros(Sc, dtype=f64, device=dev)
                 for _ in range(self.walks):
-                    prop = ucur + torch.bmm(sig, torch.randn(Sc, nd, 1, device=dev, dtype=f64)).squeeze(2)
+                    prop = ucur + (sig * torch.randn(Sc, 1, nd, device=dev, dtype=f64)).sum(2)
                     prop = torch.remainder(prop, 2.0)
                     prop = torch.where(prop > 1.0, 2.0 - prop, prop)
                     lpn, thn, dern = lnprob_static(prop)

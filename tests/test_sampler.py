@@ -354,3 +354,34 @@ def test_fused_walk_step_matches_the_separate_kernels():
     else:                                                      # a last-bit difference flipped an acceptance somewhere
         err = np.maximum(np.hypot(ra['logzerr'], rb['logzerr']), 0.1)
         assert np.all(np.abs(ra['logz'] - rb['logz']) < 5 * err)
+
+
+def test_spread_kernel_matches_a_library_cholesky():
+    """ms_ns_spread (covariance + Cholesky of the live points, one warp per star; also the code inside ms_ns_consume)
+    against torch.linalg as the checker, including the degenerate fallback."""
+    from minesweeper_b200.likelihood import likelihood
+    from minesweeper_b200.sampler import _chol_cov
+    fitargs, fitpars, runbools, _ = _problem()
+    L = likelihood(fitargs, fitpars, runbools, precision='f32', verbose=False)
+    dev = L.engine.device
+    gen = torch.Generator(device=dev).manual_seed(1)
+    S, K, nd = 133, 150, 6
+    mix = torch.randn(S, nd, nd, generator=gen, device=dev, dtype=torch.float64)
+    U = torch.bmm(torch.randn(S, K, nd, generator=gen, device=dev, dtype=torch.float64), mix) * 0.05 + 0.5
+    U[7] = U[7, :1]                                            # all live points equal: zero covariance
+    U[11, :, 2] = 0.25                                         # one coordinate constant: singular covariance
+    sig = _chol_cov(L.engine, U)
+    d = U - U.mean(dim=1, keepdim=True)
+    cov = torch.matmul(d.transpose(1, 2), d) / (K - 1)
+    good = torch.ones(S, dtype=torch.bool, device=dev)
+    good[7] = good[11] = False
+    ref = torch.linalg.cholesky(cov[good] + 1e-14 * torch.eye(nd, dtype=torch.float64, device=dev))
+    assert torch.allclose(sig[good], ref, rtol=1e-8, atol=1e-11)
+    assert torch.equal(sig[good].triu(1), torch.zeros_like(sig[good]))
+    # star 7: zero covariance + 1e-14 jitter is still positive definite -> a tiny factor; star 11: the singular
+    # coordinate gets sqrt(jitter) on the diagonal, or the diagonal fallback; either way finite and lower triangular
+    assert torch.isfinite(sig).all() and torch.equal(sig.triu(1), torch.zeros_like(sig))
+    assert float(sig[7].abs().max()) <= 1.1e-7 and float(sig[11, 2, 2]) <= 1.1e-7
+    rec = torch.matmul(sig[11], sig[11].T)
+    keep = [0, 1, 3, 4, 5]
+    assert torch.allclose(rec[keep][:, keep], cov[11][keep][:, keep], rtol=1e-8, atol=1e-12)
