@@ -215,6 +215,7 @@ def main():
 
     # ---- CPU baseline first: its workers are forked, so CUDA must not be initialised yet
     cpu = None
+    cpu_rate1 = cpu_kind = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_baseline import CpuArm
         arm = CpuArm(fitargs, fitpars, runbools, synth.draw_theta_phot(1 << 16, seed=3, box=box))
@@ -227,6 +228,7 @@ def main():
                    sample='%d per-point lnlikefn evaluations of the same workload over %d worker '
                           'processes (%.1f s; %s); single-core probe %.0f evals/s'
                           % (ne, arm.cores, te, KIND_TEXT[arm.kind], r1))
+        cpu_rate1, cpu_kind = r1, arm.kind
         del arm
 
     # ---- oracle values for the in-run parity sample (CPU leg): the first PARITY_ROWS rows of THIS rank-0 batch,
@@ -467,6 +469,34 @@ def main():
                                   'kernels, CUDA-graph replay')
             catalog['note'] = 'configs[4]: stars per GPU fixed (weak scaling); walks = shortest walk passing accuracy.gate'
             catalog['demo_settings'] = run_catalog(max(args.catalog_stars // 5, 64), 5)
+            # configs[3]: ONE star fitted on its own (64 queued walkers), a few stars one after the other; next to it
+            # what the same fit costs the reference's one-point-at-a-time loop on one host core (dynesty itself is not
+            # installed: iterations x walks + nlive sequential lnlikefn calls at the measured single-core rate)
+            if world == 1:
+                fits = []
+                for i in range(6):
+                    ns1, tht1 = make_catalog_sampler(L, Pc, 1, dev, 150, GATE_WALKS, 0.01, 20000, 1000 + i)
+                    torch.cuda.synchronize()
+                    tf0 = time.perf_counter()
+                    r1f = ns1.run()
+                    torch.cuda.synchronize()
+                    tfit = time.perf_counter() - tf0
+                    a1 = accuracy_block(L, Pc, ns1, r1f, tht1, cpd, 1)
+                    fits.append(dict(seconds=tfit, iterations=int(r1f['niter'][0]), rounds=int(r1f['rounds']),
+                                     loglike_calls=int(r1f['ncall'][0]), logz=float(r1f['logz'][0]),
+                                     logzerr=float(r1f['logzerr'][0]), dlnz_vs_bruteforce=a1['dlnz_median'],
+                                     max_mean_bias_in_sigma=max(a1['mean_bias_median_abs_in_sigma'].values()),
+                                     converged=bool(r1f['converged'][0])))
+                med = sorted(f['seconds'] for f in fits)[len(fits) // 2]
+                seq = [f['iterations'] * GATE_WALKS + 150 for f in fits]
+                catalog['single_fit'] = dict(
+                    workload='configs[3]: one full nested-sampling fit of one star (10 bands + parallax prior; static, rwalk, '
+                             'nlive 150, walks %d, dlogz 0.01), %d stars fitted one after the other' % (GATE_WALKS, len(fits)),
+                    seconds_median=med, queue=ns1.Q, fits=fits,
+                    cpu_seconds_estimate_1core=(float(np.median(seq)) / cpu_rate1) if cpu_rate1 else None,
+                    cpu_note='median (iterations x walks + nlive) = %d sequential lnlikefn calls at the single-core rate of '
+                             'the CPU arm (%s); prior and sampler overhead of dynesty not included'
+                             % (int(np.median(seq)), KIND_TEXT.get(cpu_kind, 'not measured')))
         except Exception as e:                                           # never lose the main line
             catalog = dict(error=repr(e))
 
