@@ -2,8 +2,10 @@
 """Config 4 (BASELINE.json configs[3]): one full nested-sampling fit of one synthetic star
 (10 bands + Gaussian parallax prior, demo sampler settings: static, rwalk, 150 live points,
 walks 5, dlogz 0.01) with the GPU proposal-queue sampler, next to the cost of the same number
-of sequential likelihood calls on one CPU core with the per-point oracle (dynesty itself is
-not installed, so the CPU figure is calls x measured per-call time, stated as such).
+of sequential likelihood calls on one CPU core with the reference's own likelihood class from
+oracle/_ref (the oracle port where that copy is absent; dynesty itself is not installed, so the
+CPU figure is calls x measured per-call time, stated as such).  bench.py reports the
+photometric form of this configuration as ``catalog.single_fit``.
 """
 import argparse
 import json
@@ -21,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, 'tools'))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--queue', type=int, default=64)
-    ap.add_argument('--walks', type=int, default=5)
+    ap.add_argument('--walks', type=int, default=5, help='demo/etc/samplerinfo.dat: 5; the accuracy gate needs 25')
     ap.add_argument('--nlive', type=int, default=150)
     ap.add_argument('--dlogz', type=float, default=0.01)
     ap.add_argument('--repeat', type=int, default=5)
@@ -95,8 +97,8 @@ def main():
         if r:
             times.append(time.perf_counter() - t0)
     # CPU: per-call cost of lnprob(priortrans(u)) with the per-point oracle, one core
-    from oracle.like_port import LikelihoodPort
-    ref = LikelihoodPort(fitargs, fitpars, runbools)
+    from oracle.cpu_baseline import make_likeobj      # the reference's own likelihood class where its copy exists
+    ref, cpu_kind = make_likeobj(fitargs, fitpars, runbools)
     u = np.random.default_rng(0).random((args.cpu_calls, L.ndim))
     th = P.priortrans_batch(u).cpu().numpy()
     t0 = time.perf_counter()
@@ -111,10 +113,10 @@ def main():
         logz=float(res['logz'][0]), logzerr=float(res['logzerr'][0]), spec=bool(args.spec), ndim=L.ndim,
         truth=[float(v) for v in truth[0].cpu().numpy()], post_mean=[float(v) for v in res['mean'][0, :L.ndim]],
         post_std=[float(v) for v in res['std'][0, :L.ndim]],
-        cpu_us_per_call_1core=cpu_call * 1e6, sequential_calls_equivalent=seq_calls,
+        cpu_us_per_call_1core=cpu_call * 1e6, cpu_kind=cpu_kind, sequential_calls_equivalent=seq_calls,
         cpu_seconds_estimate_1core=seq_calls * cpu_call,
         note='CPU figure = (iterations x walks + nlive) sequential calls x measured per-call time of the '
-             'per-point oracle likelihood on one host core; the prior and sampler overhead of dynesty are not included')))
+             'per-point likelihood (cpu_kind) on one host core; the prior and sampler overhead of dynesty are not included')))
 
 
 if __name__ == '__main__':
