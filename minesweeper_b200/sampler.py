@@ -22,6 +22,8 @@ counts, posterior mean / std of theta and of the derived MIST block, and (option
 points with ln weights in the column layout of the reference's samples file
 (fitstar.py:235-242, 392-425).
 """
+import time
+
 import numpy as np
 import torch
 
@@ -407,6 +409,24 @@ class BatchedNestedSampler(object):
                     converged=out['converged'].cpu().numpy(), graph_replays=total, graph_captures=ncapt)
 
 
+def _capture_graph(fn, dev):
+    """One call of ``fn`` captured into a CUDA graph on a side stream.  ``torch.cuda.graph`` does the same after a
+    ``gc.collect()`` and ``torch.cuda.empty_cache()``; with the arrays of the previous, larger working set just released
+    to the caching allocator that ``cudaFree`` of a few GB cost 0.5 s at the first compaction of a 100 000-star run
+    (12 % of its tail), and nothing inside a round allocates."""
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        g.capture_begin()
+        try:
+            fn()
+        finally:
+            g.capture_end()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    return g
+
+
 def auto_queue(nstars):
     """Walkers per star for a catalog of ``nstars`` stars on one GPU (``queue='auto'``).  A larger queue gives the
     fused photometry kernel bigger batches and fewer bookkeeping rounds; its price is the fraction of queued candidates
@@ -538,6 +558,12 @@ class QueuedNestedSampler(object):
 
         rounds, captures = 0, 0
         bootstrap, reseed = True, False
+        t_start = time.perf_counter()
+
+        def lap(what):
+            if verbose:
+                torch.cuda.synchronize(dev)
+                print('    %-28s %.3f s' % (what, time.perf_counter() - t_start))
         with torch.cuda.device(dev):
             while True:
                 Sc = len(orig)
@@ -595,15 +621,16 @@ class QueuedNestedSampler(object):
                     consume()
                     t['scale'].copy_(keep_scale); t['ncall'].copy_(keep_calls)
                 reseed = False
+                lap('state ready')
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
                     round_()                              # warm-up (scratch allocation), a real round
                 torch.cuda.current_stream(dev).wait_stream(side)
                 torch.cuda.synchronize(dev)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    round_()
+                lap('warm-up round')
+                graph = _capture_graph(round_, dev)
+                lap('graph captured')
                 rounds += 2
                 captures += 1
                 while True:
@@ -612,14 +639,17 @@ class QueuedNestedSampler(object):
                     rounds += check_every
                     nrun = int((t['done'] == 0).sum().item())
                     if verbose:
-                        print('round %d: %d / %d stars running (working set %d)' % (rounds, nrun, S, Sc))
+                        print('round %d: %d / %d stars running (working set %d, %d walkers per star, %.2f s)'
+                              % (rounds, nrun, S, Sc, Q, time.perf_counter() - t_start))
                     if nrun == 0 or (Sc > min_compact and nrun <= compact_frac * Sc) or rounds >= self.maxiter + 16:
                         break
                 del graph
                 if rounds >= self.maxiter + 16:
                     t['done'][t['done'] == 0] = 3         # give up on the rest: finalise as they are, NOT converged
                     nrun = 0
+                lap('replays done')
                 _lib.check(lib.ms_ns_finalize(eng._ctx, C.byref(st), stream()))
+                lap('finalize')
                 fin = (t['done'] == 2) | (t['done'] == 4)
                 harvest(fin)
                 out['converged'][orig[fin]] = t['done'][fin] == 2        # 2: stopped by the dlogz test; 4: at maxiter
