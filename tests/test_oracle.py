@@ -249,3 +249,31 @@ def test_payne_weight_file_ingestion_roundtrip():
     # stub the lookup of the unknown file fails instead -- loudly either way
     with pytest.raises((ImportError, KeyError, OSError)):
         ingest.load_model_file('/nonexistent/MIST.h5', 'mist')
+
+
+@pytest.mark.parametrize('which', ['phot', 'spec'])
+def test_golden_lnl_is_what_the_reference_class_returns(which, g_like_phot, g_like_spec):
+    """The committed vectors are outputs of the reference: its own ``likelihood.likelihood`` class (from the checkout
+    or the verbatim copy in oracle/_ref), built from the model arrays stored in the golden file, returns the stored
+    lnL and parsdict values again -- so a stale or hand-edited fixture cannot pass unnoticed."""
+    from oracle import refshim
+    from oracle.cpu_baseline import make_likeobj
+    if not refshim.available():
+        pytest.skip('no reference checkout and no oracle/_ref copy')
+    g = g_like_phot if which == 'phot' else g_like_spec
+    fitargs, fitpars, runbools = fit_setup(g)
+    R, kind = make_likeobj(fitargs, fitpars, runbools)
+    assert kind == 'reference' and type(R).__module__ == 'minesweeper.likelihood'
+    keys = [str(k) for k in g['parsdict_keys']]
+    n = 60 if which == 'phot' else 12
+    import contextlib
+    import io
+    for i in range(n):
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            lnl = R.lnlikefn(list(g['theta'][i]))
+        if np.isfinite(g['lnl'][i]):
+            assert abs(lnl - g['lnl'][i]) <= 1e-12 * max(1.0, abs(g['lnl'][i])), i
+            got = np.array([R.parsdict.get(k, np.nan) for k in keys], dtype=np.float64)
+            np.testing.assert_allclose(got, g['parsdict'][i], rtol=1e-14, atol=0)
+        else:
+            assert lnl == g['lnl'][i] or (np.isnan(lnl) and np.isnan(g['lnl'][i]))

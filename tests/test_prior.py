@@ -157,3 +157,34 @@ def test_advanced_priors_golden(g_prior_adv):
         pdict = {k: float(v) for k, v in zip(keys, g['parsdict'][i])}
         v = P.lnpriorfn(pdict)
         assert (v == g['lnprior'][i]) or abs(v - g['lnprior'][i]) <= 1e-7 + 1e-10 * abs(g['lnprior'][i])
+
+
+def test_golden_prior_vectors_are_what_the_reference_class_returns(g_prior):
+    """The committed prior vectors are outputs of the reference: its own ``prior.prior`` class (checkout or the verbatim
+    copy in oracle/_ref) maps the stored unit-cube points to the stored theta again, and its ``lnpriorfn`` on the
+    parsdict the reference likelihood leaves behind gives the stored ln prior."""
+    import contextlib
+    import io
+    from oracle import refshim
+    from oracle.cpu_baseline import make_likeobj
+    if not refshim.available():
+        pytest.skip('no reference checkout and no oracle/_ref copy')
+    g = g_prior
+    fitargs, fitpars, runbools, priordict = _setup(g)
+    R, kind = make_likeobj(fitargs, fitpars, runbools)
+    assert kind == 'reference'
+    from minesweeper.prior import prior as RefPrior
+    with contextlib.redirect_stdout(io.StringIO()):
+        P = RefPrior(fitargs, priordict, fitpars, runbools)
+    assert type(P).__module__ == 'minesweeper.prior' and P.fitpars_i == [str(s) for s in g['fitpars_i']]
+    for i in range(80):
+        th = np.array(P.priortrans(list(g['u'][i])), dtype=np.float64)
+        np.testing.assert_allclose(th, g['theta'][i], rtol=1e-14, atol=0)
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all='ignore'):
+            lnl = R.lnlikefn(list(g['theta'][i]))
+        assert (lnl == g['lnl'][i]) or abs(lnl - g['lnl'][i]) <= 1e-12 * max(1.0, abs(g['lnl'][i]))
+        if np.isfinite(lnl):
+            with np.errstate(all='ignore'):
+                lnp = P.lnpriorfn(dict(R.parsdict))
+            want = g['lnprior'][i]
+            assert (lnp == want) or abs(lnp - want) <= 1e-12 * max(1.0, abs(want)), (i, lnp, want)
