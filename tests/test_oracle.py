@@ -277,3 +277,25 @@ def test_golden_lnl_is_what_the_reference_class_returns(which, g_like_phot, g_li
             np.testing.assert_allclose(got, g['parsdict'][i], rtol=1e-14, atol=0)
         else:
             assert lnl == g['lnl'][i] or (np.isnan(lnl) and np.isnan(g['lnl'][i]))
+
+
+def test_golden_smoothing_vectors_are_what_the_reference_module_returns(g_smooth):
+    """tests/golden/smoothing.npz against the reference's own ``smoothing.smoothspec`` (checkout or oracle/_ref) on the
+    stored spectrum: rotational, resolution (with Doppler shift and input resolution) and LSF-array modes."""
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip('no reference checkout and no oracle/_ref copy')
+    refshim.install()
+    from minesweeper import smoothing as S
+    g = g_smooth
+    w, f, ow = g['wave'], g['flux'], g['outwave']
+    for v, ref in zip(g['vsini'], g['vsini_out']):
+        out = S.smoothspec(w, f, v, outwave=None, smoothtype='vsini', fftsmooth=True, inres=0.0)
+        np.testing.assert_array_equal(out, ref)
+    ws = w * (1 + float(g['r_vshift']) / 299792.458)
+    for r, ref in zip(g['rsigma'], g['r_out']):
+        out = S.smoothspec(ws, f, r, outwave=ow, smoothtype='R', fftsmooth=True, inres=float(g['r_inres']))
+        np.testing.assert_array_equal(out, ref)
+    for (a, b), ref in zip(g['lsf_ab'], g['lsf_out']):
+        out = S.smoothspec(w, f, a + b * (w - w[0]), outwave=ow, smoothtype='lsf', fftsmooth=True)
+        np.testing.assert_array_equal(out, ref)
