@@ -4,6 +4,7 @@
 #pragma once
 #include "common.cuh"
 #include <cstring>
+#include <cmath>
 
 namespace {
 
@@ -121,6 +122,7 @@ struct LnPriorArgs {
     const double *lnL;              // [B] or nullptr (then out = lnprior)
     double *out;
     int mistdif, nterms, imf;
+    double imf_hi_off, imf_lognorm; // constants of the Kroupa-like IMF, computed once on the host (fill_lnprior_args)
     const int32_t *star_slot; const double *star_plx;   // per-star Gaussian parallax prior or nullptr
     ms_prior_term term[MS_MAX_PRIOR_TERMS];
     int has_adv; ms_adv_prior adv;
@@ -190,10 +192,8 @@ __device__ __forceinline__ double lnprob_value(const LnPriorArgs &a, int64_t p) 
         const double al = 1.3, ah = 2.3, mb = 0.5;
         double v = neg_inf;
         if (m <= mb && m > 0.08) v = -al * log(m);
-        else if (m > mb) v = -ah * log(m) + (ah - al) * log(mb);
-        double nlo = pow(mb, 1.0 - al) / (ah - 1.0);
-        double nhi = pow(0.08, 1.0 - al) / (al - 1.0) - pow(mb, 1.0 - al) / (al - 1.0);
-        lp += v - log(nlo + nhi);
+        else if (m > mb) v = -ah * log(m) + a.imf_hi_off;                 // + (ah - al) log(mb)
+        lp += v - a.imf_lognorm;                                         // - log(norm_low + norm_high)
     }
     if (a.star_plx) {
         const double *pe = a.star_plx + 2 * (int64_t)(a.star_slot ? a.star_slot[p] : 0);
@@ -296,6 +296,13 @@ inline int fill_lnprior_args(const ms_flags *flags, const double *theta, int ndi
         a.tv.col[colmap[c]] = c;
     }
     a.derived = derived; a.lnL = lnL; a.out = out; a.mistdif = flags->mistdif; a.nterms = nterms; a.imf = imf;
+    {   // normalisation of the broken power law (advancedpriors.py:93-137): three pow() and a log() per point otherwise
+        const double al = 1.3, ah = 2.3, mb = 0.5;
+        const double nlo = std::pow(mb, 1.0 - al) / (ah - 1.0);
+        const double nhi = std::pow(0.08, 1.0 - al) / (al - 1.0) - std::pow(mb, 1.0 - al) / (al - 1.0);
+        a.imf_hi_off = (ah - al) * std::log(mb);
+        a.imf_lognorm = std::log(nlo + nhi);
+    }
     a.star_slot = star_slot; a.star_plx = star_plx;
     a.has_adv = adv != nullptr;
     if (adv) a.adv = *adv; else memset(&a.adv, 0, sizeof(a.adv));

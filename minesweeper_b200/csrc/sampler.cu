@@ -127,11 +127,11 @@ __global__ void ns_accept_kernel(ms_ns_state s) {
 }
 
 // lnprob + accept in one pass: a lane per walker evaluates lnprobfn (lnL + ln prior with its -inf short circuits, the
-// arithmetic of lnprior_kernel), then each half warp copies the records of its accepted walkers cooperatively, a lane per
-// element, exactly as ns_accept_kernel does.  a.out (= prop_lp) is still written: ns_consume never reads it, the tests do.
+// arithmetic of lnprior_kernel), then the warp copies the records of its accepted walkers (ballot) cooperatively, a lane
+// per element; same stores as ns_accept_kernel.  a.out (= prop_lp) is still written: ns_consume never reads it, the tests do.
 __global__ void __launch_bounds__(256) ns_lnprob_accept_kernel(ms_ns_state s, LnPriorArgs a) {
     const int nd = s.nd, ncol = s.nd + s.nder, w = nd + ncol + 1;
-    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    const int lane = threadIdx.x & 31;
     const int64_t n = (int64_t)s.S * s.Q;
     const int64_t wpb = blockDim.x >> 5;
     for (int64_t base = (blockIdx.x * wpb + (threadIdx.x >> 5)) * 32; base < n; base += (int64_t)gridDim.x * wpb * 32) {
@@ -143,13 +143,15 @@ __global__ void __launch_bounds__(256) ns_lnprob_accept_kernel(ms_ns_state s, Ln
             a.out[mine] = lp;
             ok = lp > s.lmin[mine / s.Q];
         }
-        for (int j = 0; j < 16; ++j) {                      // the j-th walker of each half warp
-            const int src = half * 16 + j;
-            const bool okj = __shfl_sync(0xffffffffu, ok ? 1 : 0, src) != 0;
+        // the accepted walkers of this warp, one after the other: the whole warp copies a record (26 elements for a
+        // 6-parameter isochrone fit: one element per lane, consecutive addresses)
+        unsigned todo = __ballot_sync(0xffffffffu, ok);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
             const double lpj = __shfl_sync(0xffffffffu, lp, src);
-            if (!okj) continue;
             const int64_t wk = base + src;
-            for (int c = hl; c < w; c += 16) {
+            for (int c = lane; c < w; c += 32) {
                 if (c < ncol) {
                     s.cur_row[wk * ncol + c] = c < nd ? s.prop_theta[wk * nd + c] : s.prop_der[wk * s.nder + (c - nd)];
                 } else if (c < ncol + nd) {
